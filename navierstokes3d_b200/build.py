@@ -1,0 +1,60 @@
+"""In-tree build of libns3d.so (hand-written CUDA for sm_100a + the C ABI of include/ns3d.h).
+
+``python -m navierstokes3d_b200.build`` or ``build()``; nvcc cross-compiles without a GPU.
+The shared object lands next to the sources (navierstokes3d_b200/csrc/libns3d.so) so that it
+travels with the repo snapshot to the GPU box; it is git-ignored.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+LIB = os.path.join(CSRC, "libns3d.so")
+SOURCES = ["ns3d_core.cu", "ns3d_ops.cu", "ns3d_pt.cu"]
+HEADERS = ["ns3d_internal.cuh", os.path.join("..", "..", "include", "ns3d.h")]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    # The reference's CPU backend never contracts a*b+c; FMA is used only via explicit fma().
+    "--fmad=false",
+    "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden",
+    "-shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build libns3d.so")
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, s)) > t for s in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    cmd = [_nvcc(), *NVCC_FLAGS, "-Xptxas", "-v" if verbose else "-warn-spills",
+           *[os.path.join(CSRC, s) for s in SOURCES], "-o", LIB, "-ldl"]
+    env = dict(os.environ)
+    env.pop("CC", None)  # the image exports a gcc wrapper that nvcc must not pick up
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libns3d.so (see stderr)")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,404 @@
+// libns3d.so -- lifecycle, device field allocator, reductions, z-slab communicator.
+//
+// Replaces: @init_parallel_stencil / IGG device selection, the
+// ParallelStencil allocator `@zeros` (M:343-360), `Data.Array(host)` (M:370), `Array(dev)`
+// (M:399), ImplicitGlobalGrid's update_halo! and MPI.Allreduce(MAX) in max_g (M:21).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstring>
+
+#include "ns3d_internal.cuh"
+
+static thread_local std::string g_create_error;
+
+int ns3d_fail(ns3d_ctx* ctx, int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+
+extern "C" const char* ns3d_version(void) { return "ns3d-b200 0.1.0 (sm_100a)"; }
+
+extern "C" const char* ns3d_last_error(const ns3d_ctx* ctx)
+{
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int ns3d_create(int device, ns3d_ctx** out)
+{
+    if (!out) return ns3d_fail(nullptr, NS3D_EINVAL, "ns3d_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return ns3d_fail(nullptr, NS3D_ENODEV, "ns3d_create: no CUDA device (%s); there is no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev)
+        return ns3d_fail(nullptr, NS3D_EINVAL, "ns3d_create: device %d out of range [0,%d)", device, ndev);
+    ns3d_ctx* ctx = new ns3d_ctx();
+    ctx->device = device;
+#define CREATE_CUDA(call)                                                                          \
+    do {                                                                                           \
+        cudaError_t e2 = (call);                                                                   \
+        if (e2 != cudaSuccess) {                                                                   \
+            int rc = ns3d_fail(nullptr, NS3D_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e2)); \
+            delete ctx;                                                                            \
+            return rc;                                                                             \
+        }                                                                                          \
+    } while (0)
+    CREATE_CUDA(cudaSetDevice(device));
+    CREATE_CUDA(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device));
+    int lo = 0, hi = 0;
+    CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CREATE_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, lo));
+    CREATE_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
+    CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
+    CREATE_CUDA(cudaMalloc(&ctx->d_maxbits, 64 * sizeof(unsigned long long)));
+    CREATE_CUDA(cudaMemset(ctx->d_maxbits, 0, 64 * sizeof(unsigned long long)));
+    CREATE_CUDA(cudaMallocHost(&ctx->h_maxbits, 64 * sizeof(unsigned long long)));
+#undef CREATE_CUDA
+    *out = ctx;
+    return NS3D_OK;
+}
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+// NCCL is bound lazily so that single-GPU users need no libnccl at all.  If the host
+// process already loaded one (torch ships libnccl.so.2) the loader hands us that copy.
+static int load_nccl(ns3d_ctx* ctx)
+{
+    if (g_nccl.handle) return NS3D_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return ns3d_fail(ctx, NS3D_ECOMM, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                              \
+    do {                                                                              \
+        *(void**)(&g_nccl.field) = dlsym(h, name);                                    \
+        if (!g_nccl.field) return ns3d_fail(ctx, NS3D_ECOMM, "libnccl lacks %s", name); \
+    } while (0)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.handle = h;
+    return NS3D_OK;
+}
+
+#define NS3D_NCCL(ctx, call)                                                                    \
+    do {                                                                                        \
+        ncclResult_t r__ = (call);                                                              \
+        if (r__ != ncclSuccess)                                                                 \
+            return ns3d_fail((ctx), NS3D_ECOMM, "%s failed: %s", #call, g_nccl.GetErrorString(r__)); \
+    } while (0)
+
+extern "C" int ns3d_destroy(ns3d_ctx* ctx)
+{
+    NS3D_CHECK_CTX(ctx);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->comm_stream);
+    if (ctx->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl);
+    for (auto& kv : ctx->allocs) cudaFree(kv.first);
+    if (ctx->pr_shadow) cudaFree(ctx->pr_shadow);
+    cudaFree(ctx->d_maxbits);
+    cudaFreeHost(ctx->h_maxbits);
+    cudaEventDestroy(ctx->ev_a);
+    cudaEventDestroy(ctx->ev_b);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->comm_stream);
+    delete ctx;
+    return NS3D_OK;
+}
+
+extern "C" int ns3d_set_mode(ns3d_ctx* ctx, int mode)
+{
+    NS3D_CHECK_CTX(ctx);
+    if (mode != NS3D_PARITY && mode != NS3D_FAST && mode != NS3D_FASTEST)
+        return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_set_mode: unknown mode %d", mode);
+    ctx->mode = mode;
+    return NS3D_OK;
+}
+extern "C" int ns3d_get_mode(const ns3d_ctx* ctx) { return ctx ? ctx->mode : NS3D_EINVAL; }
+
+extern "C" int ns3d_sync(ns3d_ctx* ctx)
+{
+    NS3D_CHECK_CTX(ctx);
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
+    NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NS3D_OK;
+}
+
+extern "C" long long ns3d_launch_count(const ns3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void* ns3d_stream(ns3d_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// ---------------------------------------------------------------------------------------------
+// allocator
+// ---------------------------------------------------------------------------------------------
+extern "C" int ns3d_zeros(ns3d_ctx* ctx, int sx, int sy, int sz, double** dptr)
+{
+    NS3D_CHECK_CTX(ctx);
+    if (!dptr || sx <= 0 || sy <= 0 || sz <= 0)
+        return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_zeros: bad shape (%d,%d,%d)", sx, sy, sz);
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t bytes = (size_t)sx * sy * sz * sizeof(double);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);  // cudaMalloc returns >= 256-byte aligned blocks
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ns3d_fail(ctx, NS3D_ENOMEM, "ns3d_zeros: cudaMalloc(%zu B) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    NS3D_CUDA(ctx, cudaMemsetAsync(p, 0, bytes, ctx->stream));
+    ctx->allocs[p] = bytes;
+    ctx->bytes += bytes;
+    *dptr = (double*)p;
+    return NS3D_OK;
+}
+
+extern "C" int ns3d_free(ns3d_ctx* ctx, double* dptr)
+{
+    NS3D_CHECK_CTX(ctx);
+    auto it = ctx->allocs.find((void*)dptr);
+    if (it == ctx->allocs.end()) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_free: pointer not owned by this context");
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NS3D_CUDA(ctx, cudaFree(dptr));
+    ctx->bytes -= it->second;
+    ctx->allocs.erase(it);
+    return NS3D_OK;
+}
+
+extern "C" size_t ns3d_bytes_allocated(const ns3d_ctx* ctx) { return ctx ? ctx->bytes : 0; }
+
+extern "C" int ns3d_h2d(ns3d_ctx* ctx, double* dptr, const double* h_src, size_t count)
+{
+    NS3D_CHECK_CTX(ctx);
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    NS3D_CUDA(ctx, cudaMemcpyAsync(dptr, h_src, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host buffer may be pageable / reused
+    return NS3D_OK;
+}
+
+extern "C" int ns3d_d2h(ns3d_ctx* ctx, double* h_dst, const double* dptr, size_t count)
+{
+    NS3D_CHECK_CTX(ctx);
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    NS3D_CUDA(ctx, cudaMemcpyAsync(h_dst, dptr, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NS3D_OK;
+}
+
+extern "C" int ns3d_copy(ns3d_ctx* ctx, double* dst, const double* src, size_t count)
+{
+    NS3D_CHECK_CTX(ctx);
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    NS3D_CUDA(ctx, cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return NS3D_OK;
+}
+
+__global__ void fill_kernel(double* __restrict__ a, double v, size_t n)
+{
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) a[q] = v;
+}
+
+extern "C" int ns3d_fill(ns3d_ctx* ctx, double* dptr, double value, size_t count)
+{
+    NS3D_CHECK_CTX(ctx);
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned blocks = (unsigned)std::min<size_t>((count + 255) / 256, (size_t)ctx->num_sms * 16);
+    fill_kernel<<<blocks ? blocks : 1, 256, 0, ctx->stream>>>(dptr, value, count);
+    NS3D_LAUNCH_CHECK(ctx);
+    return NS3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// maximum(abs.(A))   (K8' of SURVEY.md: the reference allocates abs.(Rp) and reduces it;
+// here one pass, no temporary)
+// ---------------------------------------------------------------------------------------------
+__global__ void max_abs_kernel(const double* __restrict__ a, size_t n, unsigned long long* out)
+{
+    unsigned long long m = 0ULL;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long b = absbits(a[q]);
+        m = b > m ? b : m;
+    }
+    block_max_to_global(m, out);
+}
+
+int ns3d_internal_max_abs_async(ns3d_ctx* ctx, const double* A, size_t count)
+{
+    NS3D_CUDA(ctx, cudaMemsetAsync(ctx->d_maxbits, 0, sizeof(unsigned long long), ctx->stream));
+    unsigned blocks = (unsigned)std::min<size_t>((count + 255) / 256, (size_t)ctx->num_sms * 8);
+    max_abs_kernel<<<blocks ? blocks : 1, 256, 0, ctx->stream>>>(A, count, ctx->d_maxbits);
+    NS3D_LAUNCH_CHECK(ctx);
+    return NS3D_OK;
+}
+
+// Reads ctx->d_maxbits[0] back (synchronising) and max-reduces it over the ranks.
+int ns3d_internal_read_max(ns3d_ctx* ctx, double* h_out)
+{
+    if (ctx->nccl) {
+        // Unsigned 64-bit max over bit patterns of |x| == NaN-propagating max over |x|.
+        NS3D_NCCL(ctx, g_nccl.AllReduce(ctx->d_maxbits, ctx->d_maxbits, 1, ncclUint64, ncclMax,
+                                        (ncclComm_t)ctx->nccl, ctx->stream));
+    }
+    NS3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_maxbits, ctx->d_maxbits, sizeof(unsigned long long),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+    NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long b = ctx->h_maxbits[0];
+    double v;
+    memcpy(&v, &b, sizeof v);
+    *h_out = v;
+    return NS3D_OK;
+}
+
+extern "C" int ns3d_max_abs(ns3d_ctx* ctx, const double* A, size_t count, double* h_out)
+{
+    NS3D_CHECK_CTX(ctx);
+    if (!A || !h_out || count == 0) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_max_abs: bad argument");
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    NS3D_TRY(ns3d_internal_max_abs_async(ctx, A, count));
+    return ns3d_internal_read_max(ctx, h_out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// communicator: z-slabs, rank r <-> r+-1
+// ---------------------------------------------------------------------------------------------
+extern "C" int ns3d_comm_unique_id(char id[128])
+{
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    if (!id) return NS3D_EINVAL;
+    NS3D_TRY(load_nccl(nullptr));
+    ncclUniqueId uid;
+    ncclResult_t r = g_nccl.GetUniqueId(&uid);
+    if (r != ncclSuccess) return ns3d_fail(nullptr, NS3D_ECOMM, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+    memcpy(id, &uid, 128);
+    return NS3D_OK;
+}
+
+extern "C" int ns3d_comm_init(ns3d_ctx* ctx, int rank, int nranks, const char id[128])
+{
+    NS3D_CHECK_CTX(ctx);
+    if (nranks < 1 || rank < 0 || rank >= nranks || !id)
+        return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_comm_init: bad rank %d / nranks %d", rank, nranks);
+    if (ctx->nccl) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_comm_init: communicator already attached");
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    if (nranks == 1) return NS3D_OK;  // singleton: every update_halo! is a no-op, like IGG on one rank
+    NS3D_TRY(load_nccl(ctx));
+    ncclUniqueId uid;
+    memcpy(&uid, id, 128);
+    ncclComm_t comm;
+    NS3D_NCCL(ctx, g_nccl.CommInitRank(&comm, nranks, uid, rank));
+    ctx->nccl = comm;
+    return NS3D_OK;
+}
+
+extern "C" int ns3d_comm_rank(const ns3d_ctx* ctx) { return ctx ? ctx->rank : NS3D_EINVAL; }
+extern "C" int ns3d_comm_size(const ns3d_ctx* ctx) { return ctx ? ctx->nranks : NS3D_EINVAL; }
+
+// IGG update_halo! for dims=(1,1,N), overlap 2, halo width 1: a field
+// with sz planes has overlap ol = 2 + (sz - nz); 1-based plane `ol` goes to the lower
+// neighbour's plane `sz`, plane `sz-ol+1` to the upper neighbour's plane 1.  z-planes are
+// contiguous (x fastest, z slowest) so no packing is needed.
+int ns3d_internal_halo_z(ns3d_ctx* ctx, cudaStream_t s, double* const* fields, const int* sx, const int* sy,
+                         const int* sz, int nfields, int nz)
+{
+    if (ctx->nranks == 1) return NS3D_OK;
+    if (!ctx->nccl) return ns3d_fail(ctx, NS3D_ECOMM, "update_halo: no communicator attached");
+    ncclComm_t comm = (ncclComm_t)ctx->nccl;
+    const int lo = ctx->rank - 1, hi = ctx->rank + 1;
+    NS3D_NCCL(ctx, g_nccl.GroupStart());
+    for (int f = 0; f < nfields; ++f) {
+        const int ol = 2 + (sz[f] - nz);
+        if (ol < 2) {
+            g_nccl.GroupEnd();
+            return ns3d_fail(ctx, NS3D_EINVAL, "update_halo: field %d has overlap %d < 2 and cannot be exchanged", f, ol);
+        }
+        const size_t plane = (size_t)sx[f] * sy[f];
+        double* a = fields[f];
+        if (lo >= 0) {
+            NS3D_NCCL(ctx, g_nccl.Send(a + plane * (size_t)(ol - 1), plane, ncclDouble, lo, comm, s));
+            NS3D_NCCL(ctx, g_nccl.Recv(a, plane, ncclDouble, lo, comm, s));
+        }
+        if (hi < ctx->nranks) {
+            NS3D_NCCL(ctx, g_nccl.Send(a + plane * (size_t)(sz[f] - ol), plane, ncclDouble, hi, comm, s));
+            NS3D_NCCL(ctx, g_nccl.Recv(a + plane * (size_t)(sz[f] - 1), plane, ncclDouble, hi, comm, s));
+        }
+    }
+    NS3D_NCCL(ctx, g_nccl.GroupEnd());
+    return NS3D_OK;
+}
+
+extern "C" int ns3d_update_halo(ns3d_ctx* ctx, double* const* fields, const int* sx, const int* sy,
+                                const int* sz, int nfields, int nz)
+{
+    NS3D_CHECK_CTX(ctx);
+    if (nfields < 0 || (nfields > 0 && (!fields || !sx || !sy || !sz)))
+        return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_update_halo: bad argument");
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ns3d_internal_halo_z(ctx, ctx->stream, fields, sx, sy, sz, nfields, nz);
+}
+
+extern "C" int ns3d_allreduce_max(ns3d_ctx* ctx, double* h_inout)
+{
+    NS3D_CHECK_CTX(ctx);
+    if (!h_inout) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_allreduce_max: NULL");
+    if (ctx->nranks == 1) return NS3D_OK;
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    // MPI.MAX on doubles; NaN must win (Julia's maximum already produced NaN locally).
+    double v = *h_inout;
+    unsigned long long b;
+    if (std::isnan(v)) {
+        b = 0xffffffffffffffffULL;
+    } else {
+        // order-preserving map double -> uint64
+        memcpy(&b, &v, sizeof b);
+        b = (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+    }
+    ctx->h_maxbits[1] = b;
+    NS3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_maxbits + 1, ctx->h_maxbits + 1, sizeof b, cudaMemcpyHostToDevice, ctx->stream));
+    NS3D_NCCL(ctx, g_nccl.AllReduce(ctx->d_maxbits + 1, ctx->d_maxbits + 1, 1, ncclUint64, ncclMax,
+                                    (ncclComm_t)ctx->nccl, ctx->stream));
+    NS3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_maxbits + 1, ctx->d_maxbits + 1, sizeof b, cudaMemcpyDeviceToHost, ctx->stream));
+    NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    b = ctx->h_maxbits[1];
+    if (b == 0xffffffffffffffffULL) {
+        *h_inout = NAN;
+    } else {
+        b = (b & 0x8000000000000000ULL) ? (b & 0x7fffffffffffffffULL) : ~b;
+        memcpy(h_inout, &b, sizeof b);
+    }
+    return NS3D_OK;
+}

@@ -1,0 +1,112 @@
+// Internal declarations shared by the translation units of libns3d.so.
+// Nothing in here crosses the C ABI (include/ns3d.h).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <unordered_map>
+
+#include "../../include/ns3d.h"
+
+struct ns3d_ctx {
+    int device = 0;
+    int mode = NS3D_PARITY;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;       // all operators run here
+    cudaStream_t comm_stream = nullptr;  // halo exchange, overlapped with interior compute
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    long long launches = 0;
+    std::string err;
+    std::unordered_map<void*, size_t> allocs;
+    size_t bytes = 0;
+    // scratch owned by the context
+    double* pr_shadow = nullptr;  // ping-pong partner of Pr in the fused PT loop
+    size_t pr_shadow_count = 0;
+    unsigned long long* d_maxbits = nullptr;  // device accumulator of max |x| bit patterns
+    unsigned long long* h_maxbits = nullptr;  // pinned host mirror
+    // communicator (z-slabs, one rank per GPU)
+    void* nccl = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+int ns3d_fail(ns3d_ctx* ctx, int code, const char* fmt, ...);
+
+#define NS3D_CHECK_CTX(ctx)            \
+    do {                               \
+        if (!(ctx)) return NS3D_EINVAL; \
+    } while (0)
+
+#define NS3D_CUDA(ctx, call)                                                                  \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return ns3d_fail((ctx), NS3D_ECUDA, "%s failed: %s (%s:%d)", #call,               \
+                             cudaGetErrorString(e__), __FILE__, __LINE__);                    \
+    } while (0)
+
+#define NS3D_LAUNCH_CHECK(ctx)                                                                \
+    do {                                                                                      \
+        (ctx)->launches++;                                                                    \
+        cudaError_t e__ = cudaGetLastError();                                                 \
+        if (e__ != cudaSuccess)                                                               \
+            return ns3d_fail((ctx), NS3D_ECUDA, "kernel launch failed: %s (%s:%d)",           \
+                             cudaGetErrorString(e__), __FILE__, __LINE__);                    \
+    } while (0)
+
+#define NS3D_TRY(expr)            \
+    do {                          \
+        int rc__ = (expr);        \
+        if (rc__ != NS3D_OK) return rc__; \
+    } while (0)
+
+// 0-based column-major index into an array with leading sizes (sx, sy).
+__host__ __device__ __forceinline__ size_t idx3(int i, int j, int k, int sx, int sy)
+{
+    return (size_t)i + (size_t)sx * ((size_t)j + (size_t)sy * (size_t)k);
+}
+
+static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+// Bit pattern of |x|: for non-negative doubles the unsigned order of the patterns is the
+// numeric order, +Inf sorts above every finite value and every NaN above +Inf -- so an
+// unsigned max over patterns is a NaN-propagating maximum(abs.(A)) like Julia's.
+__device__ __forceinline__ unsigned long long absbits(double x)
+{
+    return (unsigned long long)__double_as_longlong(x) & 0x7fffffffffffffffULL;
+}
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w > v ? w : v;
+    }
+    return v;
+}
+
+// Block-wide max of bit patterns, then one atomicMax per CTA.
+__device__ __forceinline__ void block_max_to_global(unsigned long long v, unsigned long long* out)
+{
+    __shared__ unsigned long long smax[32];
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+    v = warp_max_u64(v);
+    if ((tid & 31) == 0) smax[tid >> 5] = v;
+    __syncthreads();
+    if (tid < 32) {
+        v = tid < (nthreads + 31) / 32 ? smax[tid] : 0ULL;
+        v = warp_max_u64(v);
+        if (tid == 0 && v != 0ULL) atomicMax(out, v);
+    }
+}
+
+// internal cross-TU entry points
+int ns3d_internal_max_abs_async(ns3d_ctx* ctx, const double* A, size_t count);  // result -> ctx->d_maxbits
+int ns3d_internal_read_max(ns3d_ctx* ctx, double* h_out);                       // sync + allreduce
+int ns3d_internal_halo_z(ns3d_ctx* ctx, cudaStream_t s, double* const* fields, const int* sx,
+                         const int* sy, const int* sz, int nfields, int nz);

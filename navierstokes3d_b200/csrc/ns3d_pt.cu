@@ -1,0 +1,382 @@
+// libns3d.so -- the hot loop: fused pseudo-transient (PT) pressure iteration.
+//
+// Reference (per PT iteration, M:459-463 / G:127-129): update_dPrdτ! (K5), update_Pr! (K6),
+// set_bc_Pr! = 3-4 face kernels (K7) and up to three update_halo! calls: >= 5 synchronous
+// launches and 7+ full-field passes.  Here ONE launch per iteration does all of it in
+// 5 passes (read Pr, dPrdτ, ∇V; write Pr', dPrdτ): Pr ping-pongs between the caller's array
+// and a context-owned shadow so that every thread reads a consistent old iterate, and the
+// boundary conditions are folded in: after x,y,z zero-gradient copies every boundary point
+// equals the new value at its index clamped into the interior, so the
+// thread that owns an interior point next to a face also stores its mirror images.
+//
+// Thread mapping: x on threadIdx.x (coalesced rows), a (32 x BY) tile of interior columns
+// per CTA, each thread marches `zchunk` planes along z keeping Pr[k-1], Pr[k], Pr[k+1] of
+// its column in registers (2.5-D blocking); the x/y neighbours come through L1.
+//
+// Arithmetic (template MODE): see NS3D_PARITY / NS3D_FAST / NS3D_FASTEST in ns3d.h.  The file
+// is compiled with --fmad=false; FMA appears only where fma() is written explicitly.
+#include <cmath>
+#include <cstring>
+
+#include "ns3d_internal.cuh"
+
+namespace {
+
+enum { X_NEUMANN = 0, X_DIRICHLET = 1, X_HYDRO = 2 };
+
+struct PtK {
+    int nx, ny, nz;
+    double omd;   // 1.0 - damp
+    double dtau;
+    double rdt;   // rho / dt
+    double dx, dy, dz;
+    double rdx, rdy, rdz;     // RN(1/dx) ...      (FAST)
+    double rdx2, rdy2, rdz2;  // RN(1/(dx*dx)) ... (FASTEST)
+    int xlo_kind, xhi_kind;   // X_*
+    double xlo_val, xhi_val;  // Dirichlet value / hydrostatic offset (+100 at the inlet, G:258)
+    double rho_g, hyd_dz;     // hydrostatic: ((rho*g)*((hyd_nz-iz)+0.5))*dz, iz 1-based (G:258-259)
+    int hyd_nz;
+    int zlo_halo, zhi_halo;   // z faces that are slab interfaces: left to the halo exchange
+    int zchunk;
+};
+
+// a / b with y = RN(1/b): one multiply + two FMAs (Markstein's correction step).
+__device__ __forceinline__ double div3(double a, double b, double y)
+{
+    const double q = a * y;
+    const double r = fma(-b, q, a);
+    return fma(r, y, q);
+}
+
+template <int MODE>
+__device__ __forceinline__ double bracket(const PtK& p, double pc, double xm, double xp, double ym, double yp,
+                                          double zm, double zp, double divv)
+{
+    const double d2x = (xp - pc) - (pc - xm);
+    const double d2y = (yp - pc) - (pc - ym);
+    const double d2z = (zp - pc) - (pc - zm);
+    if (MODE == NS3D_PARITY) {
+        return ((d2x / p.dx / p.dx + d2y / p.dy / p.dy) + d2z / p.dz / p.dz) - p.rdt * divv;
+    } else if (MODE == NS3D_FAST) {
+        const double tx = div3(div3(d2x, p.dx, p.rdx), p.dx, p.rdx);
+        const double ty = div3(div3(d2y, p.dy, p.rdy), p.dy, p.rdy);
+        const double tz = div3(div3(d2z, p.dz, p.rdz), p.dz, p.rdz);
+        return ((tx + ty) + tz) - p.rdt * divv;
+    } else {
+        return fma(-p.rdt, divv, fma(d2z, p.rdz2, fma(d2y, p.rdy2, d2x * p.rdx2)));
+    }
+}
+
+// Value stored at x-face point (i in {0, nx-1}) of plane k (0-based) given the mirrored
+// interior value u.  Neumann: u.  M outlet: val (bc_x_Pr!, M:147-150).  G: bc_xhydstatic!.
+__device__ __forceinline__ double xface(const PtK& p, bool hi, int k, double u)
+{
+    const int kind = hi ? p.xhi_kind : p.xlo_kind;
+    if (kind == X_NEUMANN) return u;
+    if (kind == X_DIRICHLET) return hi ? p.xhi_val : p.xlo_val;
+    const double h = p.rho_g * ((double)(p.hyd_nz - (k + 1)) + 0.5) * p.hyd_dz;
+    return hi ? h : h + p.xlo_val;
+}
+
+// Stores the new value u of interior point (i,j) into plane k of PrN together with its
+// x/y mirror images (k may itself be a z-mirror plane 0 / nz-1).
+__device__ __forceinline__ void store_with_mirrors(const PtK& p, double* __restrict__ PrN, int i, int j, int k,
+                                                   double u)
+{
+    const int nx = p.nx, ny = p.ny;
+    const bool xl = (i == 1), xh = (i == nx - 2), yl = (j == 1), yh = (j == ny - 2);
+    double* row = PrN + idx3(0, j, k, nx, ny);
+    row[i] = u;
+    if (xl) row[0] = xface(p, false, k, u);
+    if (xh) row[nx - 1] = xface(p, true, k, u);
+    if (yl | yh) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (s == 0 ? !yl : !yh) continue;
+            double* r2 = PrN + idx3(0, s == 0 ? 0 : ny - 1, k, nx, ny);
+            r2[i] = u;
+            if (xl) r2[0] = xface(p, false, k, u);
+            if (xh) r2[nx - 1] = xface(p, true, k, u);
+        }
+    }
+}
+
+// One fused PT iteration: K5 + K6 + set_bc_Pr!.
+template <int MODE>
+__global__ void __launch_bounds__(256) pt_iter_kernel(const double* __restrict__ Pr, double* __restrict__ PrN,
+                                                      double* __restrict__ dP, const double* __restrict__ divV,
+                                                      const PtK p)
+{
+    const int nx = p.nx, ny = p.ny, nz = p.nz;
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (i > nx - 2 || j > ny - 2) return;
+    const int kb = 1 + blockIdx.z * p.zchunk;
+    const int ke = min(kb + p.zchunk, nz - 1);  // interior planes [kb, ke)
+    const size_t sxy = (size_t)nx * ny;
+    const size_t dxy = (size_t)(nx - 2) * (ny - 2);
+    const double* c = Pr + idx3(i, j, kb, nx, ny);
+    const double* dv = divV + idx3(i, j, kb, nx, ny);
+    double* dp = dP + idx3(i - 1, j - 1, kb - 1, nx - 2, ny - 2);
+    double pm = c[-(ptrdiff_t)sxy];
+    double pc = c[0];
+    for (int k = kb; k < ke; ++k) {
+        const double pp = c[sxy];
+        const double L = bracket<MODE>(p, pc, c[-1], c[1], c[-nx], c[nx], pm, pp, dv[0]);
+        double dn, u;
+        if (MODE == NS3D_FASTEST) {
+            dn = fma(p.dtau, L, dp[0] * p.omd);
+            u = fma(p.dtau, dn, pc);
+        } else {
+            dn = dp[0] * p.omd + p.dtau * L;  // M:71
+            u = pc + p.dtau * dn;             // M:80
+        }
+        dp[0] = dn;
+        store_with_mirrors(p, PrN, i, j, k, u);
+        if (k == 1 && !p.zlo_halo) store_with_mirrors(p, PrN, i, j, 0, u);            // bc_z! M:129
+        if (k == nz - 2 && !p.zhi_halo) store_with_mirrors(p, PrN, i, j, nz - 1, u);  // bc_z! M:130
+        pm = pc;
+        pc = pp;
+        c += sxy;
+        dv += sxy;
+        dp += dxy;
+    }
+}
+
+// compute_res! + abs + maximum (K8 + K8') in one pass, no Rp array: max over the interior of
+// the bit pattern of |bracket| (NaN-propagating, see absbits()).
+template <int MODE>
+__global__ void __launch_bounds__(256) pt_residual_kernel(const double* __restrict__ Pr,
+                                                          const double* __restrict__ divV, const PtK p,
+                                                          unsigned long long* __restrict__ out)
+{
+    const int nx = p.nx, ny = p.ny, nz = p.nz;
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    unsigned long long m = 0ULL;
+    if (i <= nx - 2 && j <= ny - 2) {
+        const int kb = 1 + blockIdx.z * p.zchunk;
+        const int ke = min(kb + p.zchunk, nz - 1);
+        const size_t sxy = (size_t)nx * ny;
+        const double* c = Pr + idx3(i, j, kb, nx, ny);
+        const double* dv = divV + idx3(i, j, kb, nx, ny);
+        double pm = c[-(ptrdiff_t)sxy];
+        double pc = c[0];
+        for (int k = kb; k < ke; ++k) {
+            const double pp = c[sxy];
+            const double L = bracket<MODE>(p, pc, c[-1], c[1], c[-nx], c[nx], pm, pp, dv[0]);
+            const unsigned long long b = absbits(L);
+            m = b > m ? b : m;
+            pm = pc;
+            pc = pp;
+            c += sxy;
+            dv += sxy;
+        }
+    }
+    block_max_to_global(m, out);
+}
+
+int make_ptk(ns3d_ctx* ctx, const ns3d_pt_params* p, PtK* k)
+{
+    if (!p) return ns3d_fail(ctx, NS3D_EINVAL, "pt: params is NULL");
+    if (p->nx < 3 || p->ny < 3 || p->nz < 3) return ns3d_fail(ctx, NS3D_EINVAL, "pt: grid must be at least 3^3");
+    if (p->variant != NS3D_VARIANT_M && p->variant != NS3D_VARIANT_G)
+        return ns3d_fail(ctx, NS3D_EINVAL, "pt: unknown variant %d", p->variant);
+    memset(k, 0, sizeof *k);
+    k->nx = p->nx; k->ny = p->ny; k->nz = p->nz;
+    k->omd = 1.0 - p->damp;
+    k->dtau = p->dtau;
+    k->rdt = p->rho / p->dt;
+    k->dx = p->dx; k->dy = p->dy; k->dz = p->dz;
+    k->rdx = 1.0 / p->dx; k->rdy = 1.0 / p->dy; k->rdz = 1.0 / p->dz;
+    k->rdx2 = 1.0 / (p->dx * p->dx); k->rdy2 = 1.0 / (p->dy * p->dy); k->rdz2 = 1.0 / (p->dz * p->dz);
+    if (p->variant == NS3D_VARIANT_M) {
+        k->xlo_kind = X_NEUMANN;
+        k->xhi_kind = p->outlet_guard ? X_DIRICHLET : X_NEUMANN;
+        k->xhi_val = p->outlet_val;
+    } else {
+        k->xlo_kind = k->xhi_kind = X_HYDRO;
+        k->xlo_val = 100;
+        k->rho_g = p->rho * p->g;
+        k->hyd_dz = p->dz;
+        k->hyd_nz = p->nz;
+    }
+    // z-slab interfaces (variant M only: the G script is single-GPU)
+    k->zlo_halo = ctx->nranks > 1 && ctx->rank > 0;
+    k->zhi_halo = ctx->nranks > 1 && ctx->rank < ctx->nranks - 1;
+    int zc = p->zchunk;
+    if (zc <= 0) {
+        // enough CTAs for several waves on 148 SMs, but chunks long enough to amortise the
+        // two extra plane loads at the start of every chunk
+        const long long xy = (long long)cdiv(p->nx - 2, 32) * cdiv(p->ny - 2, 8);
+        zc = 16;
+        while (zc > 4 && xy * cdiv(p->nz - 2, zc) < 8LL * 8 * ctx->num_sms) zc /= 2;
+    }
+    k->zchunk = zc;
+    return NS3D_OK;
+}
+
+int ensure_shadow(ns3d_ctx* ctx, size_t count)
+{
+    if (ctx->pr_shadow_count >= count) return NS3D_OK;
+    if (ctx->pr_shadow) {
+        NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        NS3D_CUDA(ctx, cudaFree(ctx->pr_shadow));
+        ctx->pr_shadow = nullptr;
+        ctx->pr_shadow_count = 0;
+    }
+    cudaError_t e = cudaMalloc(&ctx->pr_shadow, count * sizeof(double));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ns3d_fail(ctx, NS3D_ENOMEM, "pt: cannot allocate the Pr shadow (%zu B)", count * sizeof(double));
+    }
+    ctx->pr_shadow_count = count;
+    return NS3D_OK;
+}
+
+inline dim3 pt_block() { return dim3(32, 8, 1); }
+inline dim3 pt_grid(const PtK& k) { return dim3(cdiv(k.nx - 2, 32), cdiv(k.ny - 2, 8), cdiv(k.nz - 2, k.zchunk)); }
+
+int launch_iter(ns3d_ctx* ctx, const PtK& k, const double* cur, double* nxt, double* dP, const double* divV)
+{
+    switch (ctx->mode) {
+        case NS3D_PARITY: pt_iter_kernel<NS3D_PARITY><<<pt_grid(k), pt_block(), 0, ctx->stream>>>(cur, nxt, dP, divV, k); break;
+        case NS3D_FAST: pt_iter_kernel<NS3D_FAST><<<pt_grid(k), pt_block(), 0, ctx->stream>>>(cur, nxt, dP, divV, k); break;
+        default: pt_iter_kernel<NS3D_FASTEST><<<pt_grid(k), pt_block(), 0, ctx->stream>>>(cur, nxt, dP, divV, k); break;
+    }
+    NS3D_LAUNCH_CHECK(ctx);
+    return NS3D_OK;
+}
+
+int launch_residual(ns3d_ctx* ctx, const PtK& k, const double* cur, const double* divV)
+{
+    NS3D_CUDA(ctx, cudaMemsetAsync(ctx->d_maxbits, 0, sizeof(unsigned long long), ctx->stream));
+    switch (ctx->mode) {
+        case NS3D_PARITY: pt_residual_kernel<NS3D_PARITY><<<pt_grid(k), pt_block(), 0, ctx->stream>>>(cur, divV, k, ctx->d_maxbits); break;
+        case NS3D_FAST: pt_residual_kernel<NS3D_FAST><<<pt_grid(k), pt_block(), 0, ctx->stream>>>(cur, divV, k, ctx->d_maxbits); break;
+        default: pt_residual_kernel<NS3D_FASTEST><<<pt_grid(k), pt_block(), 0, ctx->stream>>>(cur, divV, k, ctx->d_maxbits); break;
+    }
+    NS3D_LAUNCH_CHECK(ctx);
+    return NS3D_OK;
+}
+
+// update_halo!(Pr) for the freshly written iterate (replaces M:462 and M:182; the third call,
+// update_halo!(∇V) M:460, is redundant: ∇V does not change inside the loop).
+int halo_pr(ns3d_ctx* ctx, const PtK& k, double* a)
+{
+    if (ctx->nranks == 1) return NS3D_OK;
+    double* f[1] = {a};
+    return ns3d_internal_halo_z(ctx, ctx->stream, f, &k.nx, &k.ny, &k.nz, 1, k.nz);
+}
+
+}  // namespace
+
+extern "C" int ns3d_pt_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const double* divV,
+                             const ns3d_pt_params* p, int* h_iters, double* h_err_hist, int err_cap,
+                             int* h_nchecks)
+{
+    NS3D_CHECK_CTX(ctx);
+    if (!Pr || !dPrdtau || !divV) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_pt_solve: NULL field");
+    PtK k;
+    NS3D_TRY(make_ptk(ctx, p, &k));
+    if (p->nchk <= 0 || p->niter < 0) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_pt_solve: bad niter/nchk");
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)p->nx * p->ny * p->nz;
+    NS3D_TRY(ensure_shadow(ctx, n));
+    double* cur = Pr;
+    double* nxt = ctx->pr_shadow;
+    int iters = 0, nc = 0;
+    for (int iter = 1; iter <= p->niter; ++iter) {
+        NS3D_TRY(launch_iter(ctx, k, cur, nxt, dPrdtau, divV));
+        NS3D_TRY(halo_pr(ctx, k, nxt));
+        double* t = cur; cur = nxt; nxt = t;
+        iters = iter;
+        if (iter % p->nchk == 0) {
+            NS3D_TRY(launch_residual(ctx, k, cur, divV));
+            double m = 0.0;
+            NS3D_TRY(ns3d_internal_read_max(ctx, &m));
+            const double err = m * p->err_num / p->err_den;  // max*ly^2/psc  M:466
+            if (h_err_hist && nc < err_cap) h_err_hist[nc] = err;
+            ++nc;
+            if (err < p->eps_it || !std::isfinite(err)) break;  // M:469
+        }
+    }
+    if (cur != Pr) NS3D_CUDA(ctx, cudaMemcpyAsync(Pr, cur, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_iters) *h_iters = iters;
+    if (h_nchecks) *h_nchecks = nc;
+    return NS3D_OK;
+}
+
+extern "C" int ns3d_pt_iterate(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const double* divV,
+                               const ns3d_pt_params* p, int n_iter)
+{
+    NS3D_CHECK_CTX(ctx);
+    if (!Pr || !dPrdtau || !divV || n_iter < 0) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_pt_iterate: bad argument");
+    PtK k;
+    NS3D_TRY(make_ptk(ctx, p, &k));
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)p->nx * p->ny * p->nz;
+    NS3D_TRY(ensure_shadow(ctx, n));
+    double* cur = Pr;
+    double* nxt = ctx->pr_shadow;
+    for (int iter = 0; iter < n_iter; ++iter) {
+        NS3D_TRY(launch_iter(ctx, k, cur, nxt, dPrdtau, divV));
+        NS3D_TRY(halo_pr(ctx, k, nxt));
+        double* t = cur; cur = nxt; nxt = t;
+    }
+    if (cur != Pr) NS3D_CUDA(ctx, cudaMemcpyAsync(Pr, cur, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return NS3D_OK;
+}
+
+// One time step, M:449-477 / G:121-142.
+extern "C" int ns3d_step(ns3d_ctx* ctx, const ns3d_fields* f, const ns3d_step_params* sp, int* h_iters,
+                         double* h_err_hist, int err_cap, int* h_nchecks)
+{
+    NS3D_CHECK_CTX(ctx);
+    if (!f || !sp) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_step: NULL argument");
+    const ns3d_pt_params& p = sp->pt;
+    const int nx = p.nx, ny = p.ny, nz = p.nz;
+    const bool M = p.variant == NS3D_VARIANT_M;
+    auto cyl = [&]() {
+        return M ? ns3d_set_cylinder_M(ctx, f->C, f->Vx, f->Vy, f->Vz, sp->a2, sp->b2, sp->ox, sp->oy, sp->sinb, sp->cosb,
+                                       sp->xco_g, sp->yco_g, p.dx, p.dy, nx, ny, nz)
+                 : ns3d_set_cylinder_G(ctx, f->C, f->Vx, f->Vy, f->Vz, sp->a2, sp->b2, sp->ox, sp->oy, sp->sinb, sp->cosb,
+                                       sp->lx, sp->ly, p.dx, p.dy, nx, ny, nz);
+    };
+    NS3D_TRY(ns3d_update_tau(ctx, f->txx, f->tyy, f->tzz, f->txy, f->txz, f->tyz, f->Vx, f->Vy, f->Vz, sp->mu, p.dx, p.dy,
+                             p.dz, nx, ny, nz));                                                       // M:449
+    // update_halo!(τxx,τyy,τzz) M:450 is redundant: τ is computed on the halo cells too.
+    NS3D_TRY(ns3d_predict_V(ctx, f->Vx, f->Vy, f->Vz, f->txx, f->tyy, f->tzz, f->txy, f->txz, f->tyz, p.rho, p.g, p.dt,
+                            p.dx, p.dy, p.dz, nx, ny, nz));                                            // M:451
+    NS3D_TRY(cyl());                                                                                   // M:452
+    if (ctx->nranks > 1) {                                                                             // M:453
+        double* h[4] = {f->C, f->Vx, f->Vy, f->Vz};
+        const int sx[4] = {nx, nx + 1, nx, nx}, sy[4] = {ny, ny, ny + 1, ny}, sz[4] = {nz, nz, nz, nz + 1};
+        NS3D_TRY(ns3d_internal_halo_z(ctx, ctx->stream, h, sx, sy, sz, 4, nz));
+    }
+    NS3D_TRY(ns3d_update_divV(ctx, f->divV, f->Vx, f->Vy, f->Vz, p.dx, p.dy, p.dz, nx, ny, nz));      // M:454
+    if (ctx->nranks > 1) {                                                                             // M:455
+        double* h[1] = {f->divV};
+        NS3D_TRY(ns3d_internal_halo_z(ctx, ctx->stream, h, &nx, &ny, &nz, 1, nz));
+    }
+    NS3D_TRY(ns3d_pt_solve(ctx, f->Pr, f->dPrdtau, f->divV, &p, h_iters, h_err_hist, err_cap, h_nchecks));  // M:458-471
+    NS3D_TRY(ns3d_correct_V(ctx, f->Vx, f->Vy, f->Vz, f->Pr, p.dt, p.rho, p.dx, p.dy, p.dz, nx, ny, nz));   // M:472
+    NS3D_TRY(cyl());                                                                                   // M:473
+    if (M)
+        NS3D_TRY(ns3d_set_bc_Vel_M(ctx, f->Vx, f->Vy, f->Vz, sp->inlet_guard, sp->vin, nx, ny, nz));   // M:474
+    else
+        NS3D_TRY(ns3d_set_bc_Vel_G(ctx, f->Vx, f->Vy, f->Vz, nx, ny, nz));                             // G:140
+    NS3D_TRY(ns3d_copy(ctx, f->Vx_o, f->Vx, (size_t)(nx + 1) * ny * nz));                              // M:475
+    NS3D_TRY(ns3d_copy(ctx, f->Vy_o, f->Vy, (size_t)nx * (ny + 1) * nz));
+    NS3D_TRY(ns3d_copy(ctx, f->Vz_o, f->Vz, (size_t)nx * ny * (nz + 1)));
+    NS3D_TRY(ns3d_copy(ctx, f->C_o, f->C, (size_t)nx * ny * nz));
+    NS3D_TRY(ns3d_advect(ctx, f->Vx, f->Vx_o, f->Vy, f->Vy_o, f->Vz, f->Vz_o, f->C, f->C_o, p.dt, p.dx, p.dy, p.dz, nx,
+                         ny, nz));                                                                     // M:476
+    if (ctx->nranks > 1) {                                                                             // M:477
+        double* h[3] = {f->Vx, f->Vy, f->Vz};
+        const int sx[3] = {nx + 1, nx, nx}, sy[3] = {ny, ny + 1, ny}, sz[3] = {nz, nz, nz + 1};
+        NS3D_TRY(ns3d_internal_halo_z(ctx, ctx->stream, h, sx, sy, sz, 3, nz));
+    }
+    return NS3D_OK;
+}

@@ -1,0 +1,260 @@
+"""Host drivers with the reference's run-script surface, on top of libns3d.so.
+
+* ``run_navierstokes3D(; do_vis, do_save, do_print, nx, nt)`` -- scripts/NavierStokes3D_multi_gpu.jl
+  (M:287-536): returns the interior arrays ``C_v, Pr_v, Vx_v, Vy_v, Vz_v`` (M:528-535).
+* ``runme(; do_vis, do_save)`` -- scripts/NavierStokes3D_gpu.jl (G:12-173).
+
+The time loop is the scripts' (M:446-477 / G:119-142): ``Simulation.step()`` runs it through
+the fused level-2 entry point ``ns3d_step`` and ``Simulation.step_level1()`` line by line
+through the level-1 operators, i.e. exactly what a Julia driver re-pointed at the C ABI does.
+There is no CPU path: every field lives in device memory allocated by the library.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import native
+from .params import Setup, setup_gpu, setup_multi_gpu
+
+
+def _linrange(start: float, stop: float, n: int) -> np.ndarray:
+    """Julia ``LinRange(start, stop, n)``: element i is (1-t)*start + t*stop with t = (i-1)/(n-1)."""
+    t = np.arange(n, dtype=np.float64) / max(n - 1, 1)
+    return (1 - t) * start + t * stop
+
+
+def initial_host_fields(s: Setup) -> dict:
+    """Host arrays that differ from zero at t = 0 (before set_cylinder!).
+
+    Variant M (M:369-370): ``Vy[1,:,:] .= vin`` (sic) and the hydrostatic ``Pr`` (= +-0.0, g = 0).
+    Variant G (G:86-87): 1/7-power-law ``Vx`` profile and hydrostatic ``Pr``.
+    """
+    nx, ny, nz = s.nx, s.ny, s.nz
+    yc = _linrange(-(s.ly - s.dy) / 2, (s.ly - s.dy) / 2, ny)
+    zc = _linrange(-(s.lz - s.dz) / 2, (s.lz - s.dz) / 2, nz)
+    out = {}
+    if s.variant == native.VARIANT_M:
+        vy = np.zeros((nx, ny + 1, nz), order="F")
+        vy[0, :, :] = s.vin
+        zg = np.array([s.grid.x_g(iz, s.dz, nz, 2) for iz in range(1, nz + 1)])
+        pr = (-(zg - s.dz / 2) * s.rho * s.g)[None, None, :] + (0 * yc)[None, :, None] + (0 * zc)[None, None, :]
+        out["Vy"] = vy
+        out["Pr"] = np.asfortranarray(np.broadcast_to(pr, (nx, ny, nz)))
+    else:
+        xc = _linrange(-(s.lx - s.dx) / 2, (s.lx - s.dx) / 2, nx)
+        xv = _linrange(-s.lx / 2, s.lx / 2, nx + 1)
+        prof = s.vin * (7.0 / 6.0) * np.power((zc + s.lz / 2) / s.lz, 1.0 / 6.0)
+        out["Vx"] = np.asfortranarray(prof[None, None, :] + (0 * yc)[None, :, None] + (0 * xv)[:, None, None])
+        out["Pr"] = np.asfortranarray((-(zc - s.lz / 2) * s.rho * s.g)[None, None, :] + (0 * yc)[None, :, None]
+                                      + (0 * xc)[:, None, None])
+    return out
+
+
+class Simulation:
+    """Device state of one rank + the time step."""
+
+    def __init__(self, setup: Setup, ctx: native.Context | None = None, *, device: int | None = None,
+                 mode: int = native.FAST, host_fields: dict | None = None, zchunk: int = 0):
+        self.s = setup
+        if ctx is None:
+            if device is None:
+                device = int(os.environ.get("LOCAL_RANK", "0"))
+            ctx = native.Context(device, mode)
+        self.ctx = ctx
+        self.zchunk = zchunk
+        self.f = {name: ctx.zeros(*shape) for name, shape in setup.shapes().items()}   # M:343-360
+        init = initial_host_fields(setup) if host_fields is None else host_fields
+        for name, arr in init.items():
+            self.f[name].set(arr)
+        if host_fields is None:
+            if setup.variant == native.VARIANT_M:
+                self.update_halo("Pr")                                                 # M:371
+                self.set_cylinder()                                                    # M:372
+                self.update_halo("C", "Vx", "Vy", "Vz")                                # M:373
+        self._fields_struct = native.Fields()
+        for name in native.FIELD_NAMES:
+            setattr(self._fields_struct, name, self.f[name].ptr)
+        self.iters: list[int] = []
+        self.err_hist: list[list[float]] = []
+
+    # -- pieces of the time loop -----------------------------------------------------------------
+    def update_halo(self, *names):
+        if self.s.grid.nranks > 1:
+            self.ctx.update_halo([self.f[n] for n in names], self.s.nz)
+
+    def set_cylinder(self):
+        s, f, c = self.s, self.f, self.ctx
+        if s.variant == native.VARIANT_M:
+            c.call("ns3d_set_cylinder_M", f["C"], f["Vx"], f["Vy"], f["Vz"], s.a2, s.b2, s.ox, s.oy, s.sinb, s.cosb,
+                   s.xco_g, s.yco_g, s.dx, s.dy, s.nx, s.ny, s.nz)
+        else:
+            c.call("ns3d_set_cylinder_G", f["C"], f["Vx"], f["Vy"], f["Vz"], s.a2, s.b2, s.ox, s.oy, s.sinb, s.cosb,
+                   s.lx, s.ly, s.dx, s.dy, s.nx, s.ny, s.nz)
+
+    def set_bc_Pr(self):
+        s, f, c = self.s, self.f, self.ctx
+        if s.variant == native.VARIANT_M:
+            c.call("ns3d_set_bc_Pr_M", f["Pr"], int(s.outlet_guard), 0.0, s.nx, s.ny, s.nz)
+        else:
+            c.call("ns3d_set_bc_Pr_G", f["Pr"], s.dz, s.nz, s.g, s.rho, s.nx, s.ny, s.nz)
+
+    def set_bc_Vel(self):
+        s, f, c = self.s, self.f, self.ctx
+        if s.variant == native.VARIANT_M:
+            c.call("ns3d_set_bc_Vel_M", f["Vx"], f["Vy"], f["Vz"], int(s.inlet_guard), s.vin, s.nx, s.ny, s.nz)
+        else:
+            c.call("ns3d_set_bc_Vel_G", f["Vx"], f["Vy"], f["Vz"], s.nx, s.ny, s.nz)
+
+    def step(self):
+        """One time step through the fused entry point ``ns3d_step``."""
+        it, hist = self.ctx.step(self._fields_struct, self.s.step_params(self.zchunk))
+        self.iters.append(it)
+        self.err_hist.append(hist)
+        return it, hist
+
+    def step_level1(self):
+        """The same time step, call site by call site (M:449-477 / G:121-142) through level 1."""
+        s, f, c = self.s, self.f, self.ctx
+        n = (s.nx, s.ny, s.nz)
+        c.call("ns3d_update_tau", f["txx"], f["tyy"], f["tzz"], f["txy"], f["txz"], f["tyz"], f["Vx"], f["Vy"],
+               f["Vz"], s.mu, s.dx, s.dy, s.dz, *n)                                            # M:449
+        self.update_halo("txx", "tyy", "tzz")                                                  # M:450
+        c.call("ns3d_predict_V", f["Vx"], f["Vy"], f["Vz"], f["txx"], f["tyy"], f["tzz"], f["txy"], f["txz"],
+               f["tyz"], s.rho, s.g, s.dt, s.dx, s.dy, s.dz, *n)                               # M:451
+        self.set_cylinder()                                                                    # M:452
+        self.update_halo("C", "Vx", "Vy", "Vz")                                                # M:453
+        c.call("ns3d_update_divV", f["divV"], f["Vx"], f["Vy"], f["Vz"], s.dx, s.dy, s.dz, *n)  # M:454
+        self.update_halo("divV")                                                               # M:455
+        iters, hist = 0, []
+        for it in range(1, s.niter + 1):                                                       # M:458
+            c.call("ns3d_update_dPrdtau", f["Pr"], f["dPrdtau"], f["divV"], s.rho, s.dt, s.dtau, s.damp, s.dx,
+                   s.dy, s.dz, *n)                                                             # M:459
+            c.call("ns3d_update_Pr", f["Pr"], f["dPrdtau"], s.dtau, *n)                        # M:461
+            self.set_bc_Pr()                                                                   # M:463 (halo inside)
+            iters = it
+            if it % s.nchk == 0:                                                               # M:464
+                c.call("ns3d_compute_res", f["Rp"], f["Pr"], f["divV"], s.rho, s.dt, s.dx, s.dy, s.dz, *n)
+                err = c.max_abs(f["Rp"]) * (s.ly * s.ly) / s.psc                               # M:466
+                hist.append(err)
+                if err < s.eps_it or not np.isfinite(err):                                     # M:469
+                    break
+        c.call("ns3d_correct_V", f["Vx"], f["Vy"], f["Vz"], f["Pr"], s.dt, s.rho, s.dx, s.dy, s.dz, *n)   # M:472
+        self.set_cylinder()                                                                    # M:473
+        self.set_bc_Vel()                                                                      # M:474
+        for a in ("Vx", "Vy", "Vz", "C"):                                                      # M:475
+            c.copy(f[a + "_o"], f[a])
+        c.call("ns3d_advect", f["Vx"], f["Vx_o"], f["Vy"], f["Vy_o"], f["Vz"], f["Vz_o"], f["C"], f["C_o"], s.dt,
+               s.dx, s.dy, s.dz, *n)                                                           # M:476
+        self.update_halo("Vx", "Vy", "Vz")                                                     # M:477
+        self.iters.append(iters)
+        self.err_hist.append(hist)
+        return iters, hist
+
+    # -- results ---------------------------------------------------------------------------------
+    def host(self, name: str) -> np.ndarray:
+        return self.f[name].to_host()
+
+    def interior(self, name: str) -> np.ndarray:
+        """``Array(A)[2:end-1,2:end-1,2:end-1]`` (M:528-532)."""
+        return self.host(name)[1:-1, 1:-1, 1:-1]
+
+
+def _dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, world, local
+
+
+def attach_communicator(ctx: native.Context, rank: int, world: int):
+    """Bootstraps the library's NCCL communicator: rank 0 creates the id, torch.distributed
+    carries the 128 bytes to the other ranks (what MPI.bcast does in the Julia shim)."""
+    if world == 1:
+        ctx.comm_init(0, 1, b"\0" * 128)
+        return
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        raise native.NS3DError("torch.distributed must be initialised before attach_communicator()")
+    box = [ctx.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.comm_init(rank, world, box[0])
+
+
+def run_navierstokes3D(*, do_vis: bool = False, do_save: bool = False, do_print: bool = False, nx: int = 255,
+                       nt: int = 10, ny: int | None = None, nz: int | None = None, mode: int = native.FAST,
+                       level1: bool = False, return_sim: bool = False):
+    """Drop-in for ``run_navierstokes3D`` (M:287): same keywords, same return value.
+
+    Under ``torchrun`` (WORLD_SIZE > 1, torch.distributed initialised by the caller) the domain is
+    split into z-slabs, one rank per GPU, with the script's local ``nx, ny, nz`` per rank.
+    ``do_vis`` is accepted and ignored (plotting is out of scope); ``do_save`` writes the
+    script's Float32 ``out_save/out_*_v_%04d.bin`` dumps of the returned arrays on rank 0.
+    """
+    rank, world, local = _dist_env()
+    s = setup_multi_gpu(nx, ny=ny, nz=nz, rank=rank, nranks=world)
+    ctx = native.Context(local, mode)
+    attach_communicator(ctx, rank, world)
+    sim = Simulation(s, ctx)
+    for it in range(1, nt + 1):
+        if rank == 0 and do_print:
+            print(f"#it = {it}")                                         # M:456
+        iters, hist = sim.step_level1() if level1 else sim.step()
+        if rank == 0 and do_print:
+            for c, err in enumerate(hist, 1):
+                print("  #iter = %d, err = %1.3e" % (min(c * s.nchk, iters), err))   # M:468
+    out = tuple(gather_interior(sim, name) for name in ("C", "Pr", "Vx", "Vy", "Vz"))   # M:528-535
+    if do_save and rank == 0:
+        os.makedirs("out_save", exist_ok=True)
+        for name, arr in zip(("C", "Pr", "Vx", "Vy", "Vz"), out):
+            np.asfortranarray(arr, dtype=np.float32).ravel(order="F").tofile(f"out_save/out_{name}_v_{nt:04d}.bin")
+    if return_sim:
+        return out, sim
+    ctx.close()
+    return out
+
+
+def gather_interior(sim: Simulation, name: str) -> np.ndarray | None:
+    """``gather!(A_inn, A_v)`` (M:399-403): interior blocks concatenated along z on rank 0.
+
+    The reference's own multi-rank gather of the staggered fields is shape-inconsistent
+    (SURVEY.md quirk 10); here each rank contributes its interior planes and, for the field
+    staggered along the split dimension (Vz), the last rank contributes the extra plane.
+    """
+    s = sim.s
+    a = sim.interior(name)
+    world, rank = s.grid.nranks, s.grid.rank
+    if world == 1:
+        return a
+    if name == "Vz" and rank < world - 1:
+        a = a[:, :, : s.nz - 2]
+    import torch
+    import torch.distributed as dist
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(np.ascontiguousarray(a), parts, dst=0)
+    if rank != 0:
+        return None
+    return np.asfortranarray(np.concatenate(parts, axis=2))
+
+
+def runme(*, do_vis: bool = True, do_save: bool = False, nx: int = 255, nt: int = 10000, mode: int = native.FAST,
+          do_print: bool = True, return_sim: bool = False):
+    """Drop-in for ``runme`` of the single-GPU script (G:12); ``nx``/``nt`` are literals there (G:44,51)."""
+    s = setup_gpu(nx)
+    sim = Simulation(s, native.Context(_dist_env()[2], mode))
+    for it in range(1, nt + 1):
+        if do_print:
+            print(f"#it = {it}")                                         # G:125
+        iters, hist = sim.step()
+        if do_print:
+            for c, err in enumerate(hist, 1):
+                print("  #iter = %d, err = %1.3e" % (min(c * s.nchk, iters), err))   # G:134
+        if do_save and it % 10 == 0:                                     # G:168-170 (npz instead of .mat)
+            os.makedirs("out_save", exist_ok=True)
+            np.savez(f"out_save/step_{it}.npz", **{k: sim.host(k) for k in ("Pr", "Vx", "Vy", "Vz", "C")},
+                     dx=s.dx, dy=s.dy, dz=s.dz)
+    if return_sim:
+        return sim
+    sim.ctx.close()
+    return None

@@ -1,0 +1,313 @@
+"""ctypes binding of libns3d.so -- one Python function per entry point of include/ns3d.h.
+
+This is the executable stand-in for the Julia ``ccall`` shim (julia/NS3DNative.jl): same
+symbols, same argument order.  There is no fallback of any kind: if the shared object is
+missing or a call fails, an exception is raised (``NS3DError``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+PARITY, FAST, FASTEST = 0, 1, 2
+VARIANT_M, VARIANT_G = 0, 1
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+
+
+class NS3DError(RuntimeError):
+    pass
+
+
+class PtParams(C.Structure):
+    """``ns3d_pt_params`` (include/ns3d.h)."""
+    _fields_ = [
+        ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("variant", C.c_int),
+        ("rho", C.c_double), ("dt", C.c_double), ("dtau", C.c_double), ("damp", C.c_double),
+        ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double),
+        ("eps_it", C.c_double), ("err_num", C.c_double), ("err_den", C.c_double),
+        ("niter", C.c_int), ("nchk", C.c_int), ("outlet_guard", C.c_int),
+        ("outlet_val", C.c_double), ("g", C.c_double),
+        ("zchunk", C.c_int), ("reserved", C.c_int),
+    ]
+
+
+FIELD_NAMES = ["Pr", "dPrdtau", "C", "C_o", "txx", "tyy", "tzz", "txy", "txz", "tyz",
+               "Vx", "Vy", "Vz", "Vx_o", "Vy_o", "Vz_o", "divV", "Rp"]
+
+
+class Fields(C.Structure):
+    """``ns3d_fields``: 18 device pointers in the reference's allocation order (M:343-360)."""
+    _fields_ = [(n, C.c_void_p) for n in FIELD_NAMES]
+
+
+class StepParams(C.Structure):
+    """``ns3d_step_params``."""
+    _fields_ = [
+        ("pt", PtParams),
+        ("mu", C.c_double), ("vin", C.c_double),
+        ("a2", C.c_double), ("b2", C.c_double), ("ox", C.c_double), ("oy", C.c_double),
+        ("sinb", C.c_double), ("cosb", C.c_double),
+        ("xco_g", C.c_double), ("yco_g", C.c_double), ("lx", C.c_double), ("ly", C.c_double),
+        ("inlet_guard", C.c_int), ("reserved", C.c_int),
+    ]
+
+
+# name -> (restype, argtypes); the single source of truth for the symbols the header declares.
+_D, _I, _P, _Z = C.c_double, C.c_int, C.c_void_p, C.c_size_t
+SIGNATURES = {
+    "ns3d_create": (_I, [_I, C.POINTER(_P)]),
+    "ns3d_destroy": (_I, [_P]),
+    "ns3d_version": (C.c_char_p, []),
+    "ns3d_last_error": (C.c_char_p, [_P]),
+    "ns3d_set_mode": (_I, [_P, _I]),
+    "ns3d_get_mode": (_I, [_P]),
+    "ns3d_sync": (_I, [_P]),
+    "ns3d_launch_count": (C.c_longlong, [_P]),
+    "ns3d_stream": (_P, [_P]),
+    "ns3d_zeros": (_I, [_P, _I, _I, _I, C.POINTER(_P)]),
+    "ns3d_free": (_I, [_P, _P]),
+    "ns3d_h2d": (_I, [_P, _P, _P, _Z]),
+    "ns3d_d2h": (_I, [_P, _P, _P, _Z]),
+    "ns3d_copy": (_I, [_P, _P, _P, _Z]),
+    "ns3d_fill": (_I, [_P, _P, _D, _Z]),
+    "ns3d_bytes_allocated": (_Z, [_P]),
+    "ns3d_update_tau": (_I, [_P] + [_P] * 9 + [_D] * 4 + [_I] * 3),
+    "ns3d_predict_V": (_I, [_P] + [_P] * 9 + [_D] * 6 + [_I] * 3),
+    "ns3d_update_divV": (_I, [_P] + [_P] * 4 + [_D] * 3 + [_I] * 3),
+    "ns3d_update_dPrdtau": (_I, [_P] + [_P] * 3 + [_D] * 7 + [_I] * 3),
+    "ns3d_update_Pr": (_I, [_P, _P, _P, _D, _I, _I, _I]),
+    "ns3d_compute_res": (_I, [_P] + [_P] * 3 + [_D] * 5 + [_I] * 3),
+    "ns3d_max_abs": (_I, [_P, _P, _Z, c_double_p]),
+    "ns3d_correct_V": (_I, [_P] + [_P] * 4 + [_D] * 5 + [_I] * 3),
+    "ns3d_bc_x": (_I, [_P, _P, _I, _I, _I]),
+    "ns3d_bc_y": (_I, [_P, _P, _I, _I, _I]),
+    "ns3d_bc_z": (_I, [_P, _P, _I, _I, _I]),
+    "ns3d_bc_x_Vx": (_I, [_P, _P, _D, _I, _I, _I]),
+    "ns3d_bc_x_Pr": (_I, [_P, _P, _D, _I, _I, _I]),
+    "ns3d_bc_zV": (_I, [_P, _P, _I, _I, _I]),
+    "ns3d_bc_xhydstatic": (_I, [_P, _P, _D, _I, _D, _D, _I, _I, _I]),
+    "ns3d_set_bc_Vel_M": (_I, [_P, _P, _P, _P, _I, _D, _I, _I, _I]),
+    "ns3d_set_bc_Vel_G": (_I, [_P, _P, _P, _P, _I, _I, _I]),
+    "ns3d_set_bc_Pr_M": (_I, [_P, _P, _I, _D, _I, _I, _I]),
+    "ns3d_set_bc_Pr_G": (_I, [_P, _P, _D, _I, _D, _D, _I, _I, _I]),
+    "ns3d_advect": (_I, [_P] + [_P] * 8 + [_D] * 4 + [_I] * 3),
+    "ns3d_set_cylinder_M": (_I, [_P] + [_P] * 4 + [_D] * 10 + [_I] * 3),
+    "ns3d_set_cylinder_G": (_I, [_P] + [_P] * 4 + [_D] * 10 + [_I] * 3),
+    "ns3d_comm_unique_id": (_I, [C.c_char_p]),
+    "ns3d_comm_init": (_I, [_P, _I, _I, C.c_char_p]),
+    "ns3d_comm_rank": (_I, [_P]),
+    "ns3d_comm_size": (_I, [_P]),
+    "ns3d_update_halo": (_I, [_P, C.POINTER(_P), c_int_p, c_int_p, c_int_p, _I, _I]),
+    "ns3d_allreduce_max": (_I, [_P, c_double_p]),
+    "ns3d_pt_solve": (_I, [_P, _P, _P, _P, C.POINTER(PtParams), c_int_p, c_double_p, _I, c_int_p]),
+    "ns3d_pt_iterate": (_I, [_P, _P, _P, _P, C.POINTER(PtParams), _I]),
+    "ns3d_step": (_I, [_P, C.POINTER(Fields), C.POINTER(StepParams), c_int_p, c_double_p, _I, c_int_p]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """dlopen libns3d.so and type every symbol of include/ns3d.h.  Raises if it cannot."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if build_if_missing and _build.needs_build():
+        try:
+            _build.build()
+        except Exception as exc:  # noqa: BLE001
+            if not os.path.exists(path):
+                raise NS3DError(f"libns3d.so is missing and cannot be built: {exc}") from exc
+    if not os.path.exists(path):
+        raise NS3DError(f"{path} not found: build it with `python -m navierstokes3d_b200.build` "
+                        "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class DeviceArray:
+    """A dense column-major float64 device array of the reference's shape, owned by a Context."""
+
+    __slots__ = ("ctx", "ptr", "shape")
+
+    def __init__(self, ctx: "Context", ptr: int, shape):
+        self.ctx, self.ptr, self.shape = ctx, ptr, tuple(shape)
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.shape))
+
+    def to_host(self) -> np.ndarray:
+        """``Array(A)`` (M:399)."""
+        out = np.empty(self.shape, dtype=np.float64, order="F")
+        self.ctx.d2h(out, self)
+        return out
+
+    def set(self, host: np.ndarray) -> "DeviceArray":
+        """``A = Data.Array(host)`` (M:370)."""
+        self.ctx.h2d(self, host)
+        return self
+
+
+def _ptr(a) -> int:
+    return a.ptr if isinstance(a, DeviceArray) else (0 if a is None else int(a))
+
+
+class Context:
+    """``ns3d_ctx``: one GPU, one stream, its field allocator and (optionally) a z-slab communicator."""
+
+    def __init__(self, device: int = 0, mode: int = PARITY):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.ns3d_create(device, C.byref(h))
+        if rc != 0:
+            raise NS3DError(f"ns3d_create({device}) failed ({rc}): {self.lib.ns3d_last_error(None).decode()}")
+        self.h = h
+        self.device = device
+        self.set_mode(mode)
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _ck(self, rc: int, what: str):
+        if rc != 0:
+            raise NS3DError(f"{what} failed ({rc}): {self.lib.ns3d_last_error(self.h).decode()}")
+
+    def call(self, name: str, *args):
+        """Call entry point ``name`` with the context prepended; DeviceArrays become pointers."""
+        conv = [_ptr(a) if isinstance(a, DeviceArray) or a is None else a for a in args]
+        self._ck(getattr(self.lib, name)(self.h, *conv), name)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ns3d_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def set_mode(self, mode: int):
+        self._ck(self.lib.ns3d_set_mode(self.h, mode), "ns3d_set_mode")
+
+    @property
+    def mode(self) -> int:
+        return self.lib.ns3d_get_mode(self.h)
+
+    def sync(self):
+        self._ck(self.lib.ns3d_sync(self.h), "ns3d_sync")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.ns3d_launch_count(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.ns3d_stream(self.h) or 0)
+
+    @property
+    def bytes_allocated(self) -> int:
+        return int(self.lib.ns3d_bytes_allocated(self.h))
+
+    # -- allocator -----------------------------------------------------------------------------
+    def zeros(self, *shape) -> DeviceArray:
+        """``@zeros(sx,sy,sz)`` (M:343-360)."""
+        p = C.c_void_p()
+        self._ck(self.lib.ns3d_zeros(self.h, shape[0], shape[1], shape[2], C.byref(p)), "ns3d_zeros")
+        return DeviceArray(self, p.value, shape)
+
+    def free(self, a: DeviceArray):
+        self._ck(self.lib.ns3d_free(self.h, a.ptr), "ns3d_free")
+        a.ptr = 0
+
+    def h2d(self, dst: DeviceArray, host: np.ndarray):
+        host = np.asfortranarray(host, dtype=np.float64)
+        if host.shape != dst.shape:
+            raise NS3DError(f"h2d: shape {host.shape} != {dst.shape}")
+        self._ck(self.lib.ns3d_h2d(self.h, dst.ptr, host.ctypes.data, host.size), "ns3d_h2d")
+
+    def h2d_raw(self, dst_ptr: int, host_ptr: int, count: int):
+        self._ck(self.lib.ns3d_h2d(self.h, dst_ptr, host_ptr, count), "ns3d_h2d")
+
+    def d2h(self, host: np.ndarray, src: DeviceArray):
+        assert host.dtype == np.float64 and host.flags.f_contiguous and host.shape == src.shape
+        self._ck(self.lib.ns3d_d2h(self.h, host.ctypes.data, src.ptr, host.size), "ns3d_d2h")
+
+    def d2h_raw(self, host_ptr: int, src_ptr: int, count: int):
+        self._ck(self.lib.ns3d_d2h(self.h, host_ptr, src_ptr, count), "ns3d_d2h")
+
+    def from_host(self, host: np.ndarray) -> DeviceArray:
+        return self.zeros(*host.shape).set(host)
+
+    def copy(self, dst: DeviceArray, src: DeviceArray):
+        self.call("ns3d_copy", dst, src, src.size)
+
+    def max_abs(self, a: DeviceArray) -> float:
+        """``max_g(abs.(A))`` (M:21,466)."""
+        out = C.c_double()
+        self._ck(self.lib.ns3d_max_abs(self.h, a.ptr, a.size, C.byref(out)), "ns3d_max_abs")
+        return out.value
+
+    # -- communicator --------------------------------------------------------------------------
+    def unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = self.lib.ns3d_comm_unique_id(buf)
+        if rc != 0:
+            raise NS3DError(f"ns3d_comm_unique_id failed ({rc}): {self.lib.ns3d_last_error(None).decode()}")
+        return buf.raw
+
+    def comm_init(self, rank: int, nranks: int, uid: bytes):
+        self._ck(self.lib.ns3d_comm_init(self.h, rank, nranks, uid), "ns3d_comm_init")
+
+    def update_halo(self, fields, nz: int):
+        """``update_halo!(A...)`` for z-slabs."""
+        n = len(fields)
+        ptrs = (C.c_void_p * n)(*[f.ptr for f in fields])
+        sx = (C.c_int * n)(*[f.shape[0] for f in fields])
+        sy = (C.c_int * n)(*[f.shape[1] for f in fields])
+        sz = (C.c_int * n)(*[f.shape[2] for f in fields])
+        self._ck(self.lib.ns3d_update_halo(self.h, ptrs, sx, sy, sz, n, nz), "ns3d_update_halo")
+
+    def allreduce_max(self, x: float) -> float:
+        v = C.c_double(x)
+        self._ck(self.lib.ns3d_allreduce_max(self.h, C.byref(v)), "ns3d_allreduce_max")
+        return v.value
+
+    # -- level 2 -------------------------------------------------------------------------------
+    def pt_solve(self, Pr, dPrdtau, divV, p: PtParams):
+        """PT loop (M:458-471) -> (iterations, [err at each check])."""
+        cap = max(p.niter // max(p.nchk, 1) + 2, 2)
+        hist = (C.c_double * cap)()
+        iters, nchecks = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.ns3d_pt_solve(self.h, _ptr(Pr), _ptr(dPrdtau), _ptr(divV), C.byref(p), C.byref(iters),
+                                        hist, cap, C.byref(nchecks)), "ns3d_pt_solve")
+        return iters.value, [hist[i] for i in range(min(nchecks.value, cap))]
+
+    def pt_iterate(self, Pr, dPrdtau, divV, p: PtParams, n: int):
+        self._ck(self.lib.ns3d_pt_iterate(self.h, _ptr(Pr), _ptr(dPrdtau), _ptr(divV), C.byref(p), n),
+                 "ns3d_pt_iterate")
+
+    def step(self, fields: Fields, sp: StepParams):
+        """One time step (M:449-477) -> (iterations, [err at each check])."""
+        cap = max(sp.pt.niter // max(sp.pt.nchk, 1) + 2, 2)
+        hist = (C.c_double * cap)()
+        iters, nchecks = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.ns3d_step(self.h, C.byref(fields), C.byref(sp), C.byref(iters), hist, cap,
+                                    C.byref(nchecks)), "ns3d_step")
+        return iters.value, [hist[i] for i in range(min(nchecks.value, cap))]

@@ -1,0 +1,596 @@
+/*
+ * ns3d_oracle.c -- CPU ORACLE for the NavierStokes3D per-timestep hot path.
+ *
+ * THIS FILE IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, the
+ * smoke() check in __graft_entry__.py and the cpu_baseline / --impl reference
+ * legs of bench.py may build, load or call it.  The product path
+ * (navierstokes3d_b200/, libns3d.so) never links or imports anything here.
+ *
+ * PARITY STATUS: **parity unpinned by the reference's own tests.**
+ * The reference (mattbuergler/NavierStokes3D) is two Julia scripts on top of
+ * the un-vendored, un-pinned packages ParallelStencil.jl (FiniteDifferences3D
+ * macros, @parallel bounds guards) and ImplicitGlobalGrid.jl (update_halo!,
+ * x_g/nx_g).  Julia is not installed in the build container, so the reference
+ * cannot be executed here; its single golden vector (test/test3D.jl:12-27) is
+ * stale (the shipped script yields Pr == 0 after nt=1).
+ * What pins this oracle instead (tests/test_oracle_*.py):
+ *   - an independently written numpy restatement (oracle/np_restatement.py)
+ *     agreeing bit-for-bit on small grids,
+ *   - the survey-session probe numbers (PT iteration
+ *     counts per step and field sums),
+ *   - analytic invariants (step 1 of variant M has Pr == 0 and exits at the
+ *     first residual check; advect with V == 0 is the identity; ...).
+ *
+ * Arithmetic contract: this is a LITERAL, UNFUSED restatement, one loop nest
+ * per reference kernel, in the reference's operation order (Julia evaluates
+ * a+b+c as (a+b)+c, a/b/c as (a/b)/c, dt/rho*x as (dt/rho)*x, x^2 as x*x; no
+ * FMA contraction, no fast-math).  Compile with -O2 -ffp-contract=off.
+ * Indices are 1-based through the A3() accessor, arrays are column-major with
+ * x fastest, exactly like Julia Array{Float64,3}.
+ *
+ * Citations: M:n = scripts/NavierStokes3D_multi_gpu.jl line n,
+ *            G:n = scripts/NavierStokes3D_gpu.jl line n   (under /root/reference).
+ * ParallelStencil macro semantics restated:
+ *   @all(A)=A[ix,iy,iz] guarded by ix<=size(A,1)...; @inn(A)=A[ix+1,iy+1,iz+1]
+ *   guarded by ix<=size(A,1)-2...; @d_xa(A)=A[ix+1,iy,iz]-A[ix,iy,iz];
+ *   @d_xi(A)=A[ix+1,iy+1,iz+1]-A[ix,iy+1,iz+1];
+ *   @d2_xi(A)=(A[ix+2,iy+1,iz+1]-A[ix+1,iy+1,iz+1])-(A[ix+1,iy+1,iz+1]-A[ix,iy+1,iz+1]).
+ */
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define EXPORT __attribute__((visibility("default")))
+
+/* 1-based column-major accessor: array a of leading sizes (sx, sy). */
+#define A3(a, sx, sy, i, j, k) \
+    (a)[(size_t)((i)-1) + (size_t)(sx) * ((size_t)((j)-1) + (size_t)(sy) * (size_t)((k)-1))]
+
+EXPORT int ns3d_oracle_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+EXPORT void ns3d_oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+/* ------------------------------------------------------------------------- */
+/* K1  update_tau!   M:36-44  (= G:177-185)                                   */
+/* ------------------------------------------------------------------------- */
+EXPORT void oracle_update_tau(double *txx, double *tyy, double *tzz, double *txy, double *txz,
+                              double *tyz, const double *Vx, const double *Vy, const double *Vz,
+                              double mu, double dx, double dy, double dz, int nx, int ny, int nz)
+{
+    const double twomu = 2 * mu; /* `2μ` is 2*μ */
+    /* @all(τxx), @all(τyy), @all(τzz): (nx,ny,nz) arrays, macro @∇V() M:15 */
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= nz; ++k)
+        for (int j = 1; j <= ny; ++j)
+            for (int i = 1; i <= nx; ++i) {
+                double dxa = A3(Vx, nx + 1, ny, i + 1, j, k) - A3(Vx, nx + 1, ny, i, j, k);
+                double dya = A3(Vy, nx, ny + 1, i, j + 1, k) - A3(Vy, nx, ny + 1, i, j, k);
+                double dza = A3(Vz, nx, ny, i, j, k + 1) - A3(Vz, nx, ny, i, j, k);
+                double divv = (dxa / dx + dya / dy) + dza / dz;
+                A3(txx, nx, ny, i, j, k) = twomu * (dxa / dx - divv / 3.0);
+                A3(tyy, nx, ny, i, j, k) = twomu * (dya / dy - divv / 3.0);
+                A3(tzz, nx, ny, i, j, k) = twomu * (dza / dz - divv / 3.0);
+            }
+    /* @all(τxy), @all(τxz), @all(τyz): (nx-1,ny-1,nz-1) arrays, inner differences */
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= nz - 1; ++k)
+        for (int j = 1; j <= ny - 1; ++j)
+            for (int i = 1; i <= nx - 1; ++i) {
+                double dyiVx = A3(Vx, nx + 1, ny, i + 1, j + 1, k + 1) - A3(Vx, nx + 1, ny, i + 1, j, k + 1);
+                double dxiVy = A3(Vy, nx, ny + 1, i + 1, j + 1, k + 1) - A3(Vy, nx, ny + 1, i, j + 1, k + 1);
+                double dziVx = A3(Vx, nx + 1, ny, i + 1, j + 1, k + 1) - A3(Vx, nx + 1, ny, i + 1, j + 1, k);
+                double dxiVz = A3(Vz, nx, ny, i + 1, j + 1, k + 1) - A3(Vz, nx, ny, i, j + 1, k + 1);
+                double dziVy = A3(Vy, nx, ny + 1, i + 1, j + 1, k + 1) - A3(Vy, nx, ny + 1, i + 1, j + 1, k);
+                double dyiVz = A3(Vz, nx, ny, i + 1, j + 1, k + 1) - A3(Vz, nx, ny, i + 1, j, k + 1);
+                A3(txy, nx - 1, ny - 1, i, j, k) = mu * (dyiVx / dy + dxiVy / dx);
+                A3(txz, nx - 1, ny - 1, i, j, k) = mu * (dziVx / dz + dxiVz / dx);
+                A3(tyz, nx - 1, ny - 1, i, j, k) = mu * (dziVy / dz + dyiVz / dy);
+            }
+}
+
+/* ------------------------------------------------------------------------- */
+/* K2  predict_V!   M:50-55  (= G:187-192)                                    */
+/* ------------------------------------------------------------------------- */
+EXPORT void oracle_predict_V(double *Vx, double *Vy, double *Vz, const double *txx, const double *tyy,
+                             const double *tzz, const double *txy, const double *txz, const double *tyz,
+                             double rho, double g, double dt, double dx, double dy, double dz, int nx,
+                             int ny, int nz)
+{
+    const double dtr = dt / rho;
+    const double rg = rho * g;
+    /* @inn(Vx): size(Vx)-2 = (nx-1, ny-2, nz-2) */
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= nz - 2; ++k)
+        for (int j = 1; j <= ny - 2; ++j)
+            for (int i = 1; i <= nx - 1; ++i) {
+                double a = A3(txx, nx, ny, i + 1, j + 1, k + 1) - A3(txx, nx, ny, i, j + 1, k + 1);
+                double b = A3(txy, nx - 1, ny - 1, i, j + 1, k) - A3(txy, nx - 1, ny - 1, i, j, k);
+                double c = A3(txz, nx - 1, ny - 1, i, j, k + 1) - A3(txz, nx - 1, ny - 1, i, j, k);
+                double *v = &A3(Vx, nx + 1, ny, i + 1, j + 1, k + 1);
+                *v = *v + dtr * ((a / dx + b / dy) + c / dz);
+            }
+    /* @inn(Vy): (nx-2, ny-1, nz-2) */
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= nz - 2; ++k)
+        for (int j = 1; j <= ny - 1; ++j)
+            for (int i = 1; i <= nx - 2; ++i) {
+                double a = A3(tyy, nx, ny, i + 1, j + 1, k + 1) - A3(tyy, nx, ny, i + 1, j, k + 1);
+                double b = A3(txy, nx - 1, ny - 1, i + 1, j, k) - A3(txy, nx - 1, ny - 1, i, j, k);
+                double c = A3(tyz, nx - 1, ny - 1, i, j, k + 1) - A3(tyz, nx - 1, ny - 1, i, j, k);
+                double *v = &A3(Vy, nx, ny + 1, i + 1, j + 1, k + 1);
+                *v = *v + dtr * ((a / dy + b / dx) + c / dz);
+            }
+    /* @inn(Vz): (nx-2, ny-2, nz-1); body force term - ρ*g (M:53) */
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= nz - 1; ++k)
+        for (int j = 1; j <= ny - 2; ++j)
+            for (int i = 1; i <= nx - 2; ++i) {
+                double a = A3(tzz, nx, ny, i + 1, j + 1, k + 1) - A3(tzz, nx, ny, i + 1, j + 1, k);
+                double b = A3(txz, nx - 1, ny - 1, i + 1, j, k) - A3(txz, nx - 1, ny - 1, i, j, k);
+                double c = A3(tyz, nx - 1, ny - 1, i, j + 1, k) - A3(tyz, nx - 1, ny - 1, i, j, k);
+                double *v = &A3(Vz, nx, ny, i + 1, j + 1, k + 1);
+                *v = *v + dtr * (((a / dz + b / dx) + c / dy) - rg);
+            }
+}
+
+/* ------------------------------------------------------------------------- */
+/* K4  update_∇V!   M:61-64                                                   */
+/* ------------------------------------------------------------------------- */
+EXPORT void oracle_update_divV(double *divV, const double *Vx, const double *Vy, const double *Vz,
+                               double dx, double dy, double dz, int nx, int ny, int nz)
+{
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= nz; ++k)
+        for (int j = 1; j <= ny; ++j)
+            for (int i = 1; i <= nx; ++i) {
+                double dxa = A3(Vx, nx + 1, ny, i + 1, j, k) - A3(Vx, nx + 1, ny, i, j, k);
+                double dya = A3(Vy, nx, ny + 1, i, j + 1, k) - A3(Vy, nx, ny + 1, i, j, k);
+                double dza = A3(Vz, nx, ny, i, j, k + 1) - A3(Vz, nx, ny, i, j, k);
+                A3(divV, nx, ny, i, j, k) = (dxa / dx + dya / dy) + dza / dz;
+            }
+}
+
+/* The bracket shared by update_dPrdτ! (M:71) and compute_res! (M:89). */
+static inline double pt_bracket(const double *Pr, const double *divV, double rdt, double dx, double dy,
+                                double dz, int nx, int ny, int i, int j, int k)
+{
+    double c = A3(Pr, nx, ny, i + 1, j + 1, k + 1);
+    double d2x = (A3(Pr, nx, ny, i + 2, j + 1, k + 1) - c) - (c - A3(Pr, nx, ny, i, j + 1, k + 1));
+    double d2y = (A3(Pr, nx, ny, i + 1, j + 2, k + 1) - c) - (c - A3(Pr, nx, ny, i + 1, j, k + 1));
+    double d2z = (A3(Pr, nx, ny, i + 1, j + 1, k + 2) - c) - (c - A3(Pr, nx, ny, i + 1, j + 1, k));
+    return ((d2x / dx / dx + d2y / dy / dy) + d2z / dz / dz) - rdt * A3(divV, nx, ny, i + 1, j + 1, k + 1);
+}
+
+/* K5  update_dPrdτ!   M:70-73 */
+EXPORT void oracle_update_dPrdtau(const double *Pr, double *dPrdtau, const double *divV, double rho,
+                                  double dt, double dtau, double damp, double dx, double dy, double dz,
+                                  int nx, int ny, int nz)
+{
+    const double rdt = rho / dt;
+    const double omd = 1.0 - damp;
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= nz - 2; ++k)
+        for (int j = 1; j <= ny - 2; ++j)
+            for (int i = 1; i <= nx - 2; ++i) {
+                double *d = &A3(dPrdtau, nx - 2, ny - 2, i, j, k);
+                *d = *d * omd + dtau * pt_bracket(Pr, divV, rdt, dx, dy, dz, nx, ny, i, j, k);
+            }
+}
+
+/* K6  update_Pr!   M:79-82 */
+EXPORT void oracle_update_Pr(double *Pr, const double *dPrdtau, double dtau, int nx, int ny, int nz)
+{
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= nz - 2; ++k)
+        for (int j = 1; j <= ny - 2; ++j)
+            for (int i = 1; i <= nx - 2; ++i) {
+                double *p = &A3(Pr, nx, ny, i + 1, j + 1, k + 1);
+                *p = *p + dtau * A3(dPrdtau, nx - 2, ny - 2, i, j, k);
+            }
+}
+
+/* K8  compute_res!   M:88-91 */
+EXPORT void oracle_compute_res(double *Rp, const double *Pr, const double *divV, double rho, double dt,
+                               double dx, double dy, double dz, int nx, int ny, int nz)
+{
+    const double rdt = rho / dt;
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= nz - 2; ++k)
+        for (int j = 1; j <= ny - 2; ++j)
+            for (int i = 1; i <= nx - 2; ++i)
+                A3(Rp, nx - 2, ny - 2, i, j, k) = pt_bracket(Pr, divV, rdt, dx, dy, dz, nx, ny, i, j, k);
+}
+
+/* K8' maximum(abs.(Rp))  M:466 / G:132.  `abs.(Rp)` materialises a temporary
+ * (tmp may be NULL to skip materialising; the value is identical).  Julia's
+ * `maximum` propagates NaN. */
+EXPORT double oracle_max_abs(const double *A, double *tmp, size_t n)
+{
+    double m = 0.0; /* abs values are >= 0; n > 0 always here */
+    int has_nan = 0;
+    if (tmp) {
+#pragma omp parallel for schedule(static)
+        for (size_t q = 0; q < n; ++q) tmp[q] = fabs(A[q]);
+        A = tmp;
+    }
+#pragma omp parallel for schedule(static) reduction(max : m) reduction(| : has_nan)
+    for (size_t q = 0; q < n; ++q) {
+        double v = fabs(A[q]);
+        if (v != v) has_nan |= 1;
+        else if (v > m) m = v;
+    }
+    return has_nan ? NAN : m;
+}
+
+/* K9  correct_V!   M:97-102 */
+EXPORT void oracle_correct_V(double *Vx, double *Vy, double *Vz, const double *Pr, double dt, double rho,
+                             double dx, double dy, double dz, int nx, int ny, int nz)
+{
+    const double dtr = dt / rho;
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= nz - 2; ++k)
+        for (int j = 1; j <= ny - 2; ++j)
+            for (int i = 1; i <= nx - 1; ++i) {
+                double d = A3(Pr, nx, ny, i + 1, j + 1, k + 1) - A3(Pr, nx, ny, i, j + 1, k + 1);
+                double *v = &A3(Vx, nx + 1, ny, i + 1, j + 1, k + 1);
+                *v = *v - dtr * d / dx;
+            }
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= nz - 2; ++k)
+        for (int j = 1; j <= ny - 1; ++j)
+            for (int i = 1; i <= nx - 2; ++i) {
+                double d = A3(Pr, nx, ny, i + 1, j + 1, k + 1) - A3(Pr, nx, ny, i + 1, j, k + 1);
+                double *v = &A3(Vy, nx, ny + 1, i + 1, j + 1, k + 1);
+                *v = *v - dtr * d / dy;
+            }
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= nz - 1; ++k)
+        for (int j = 1; j <= ny - 2; ++j)
+            for (int i = 1; i <= nx - 2; ++i) {
+                double d = A3(Pr, nx, ny, i + 1, j + 1, k + 1) - A3(Pr, nx, ny, i + 1, j + 1, k);
+                double *v = &A3(Vz, nx, ny, i + 1, j + 1, k + 1);
+                *v = *v - dtr * d / dz;
+            }
+}
+
+/* ------------------------------------------------------------------------- */
+/* K7  boundary-condition kernels on an array of shape (sx,sy,sz)             */
+/* ------------------------------------------------------------------------- */
+/* bc_x!  M:108-112 (launch range 1:size(A,2), 1:size(A,3)) */
+EXPORT void oracle_bc_x(double *A, int sx, int sy, int sz)
+{
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= sz; ++k)
+        for (int j = 1; j <= sy; ++j) {
+            A3(A, sx, sy, 1, j, k) = A3(A, sx, sy, 2, j, k);
+            A3(A, sx, sy, sx, j, k) = A3(A, sx, sy, sx - 1, j, k);
+        }
+}
+/* bc_y!  M:118-122 */
+EXPORT void oracle_bc_y(double *A, int sx, int sy, int sz)
+{
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k <= sz; ++k)
+        for (int i = 1; i <= sx; ++i) {
+            A3(A, sx, sy, i, 1, k) = A3(A, sx, sy, i, 2, k);
+            A3(A, sx, sy, i, sy, k) = A3(A, sx, sy, i, sy - 1, k);
+        }
+}
+/* bc_z!  M:128-132 */
+EXPORT void oracle_bc_z(double *A, int sx, int sy, int sz)
+{
+#pragma omp parallel for schedule(static)
+    for (int j = 1; j <= sy; ++j)
+        for (int i = 1; i <= sx; ++i) {
+            A3(A, sx, sy, i, j, 1) = A3(A, sx, sy, i, j, 2);
+            A3(A, sx, sy, i, j, sz) = A3(A, sx, sy, i, j, sz - 1);
+        }
+}
+/* bc_x_Vx!  M:138-141 */
+EXPORT void oracle_bc_x_Vx(double *A, double V, int sx, int sy, int sz)
+{
+    for (int k = 1; k <= sz; ++k)
+        for (int j = 1; j <= sy; ++j) A3(A, sx, sy, 1, j, k) = V;
+}
+/* bc_x_Pr!  M:147-150 */
+EXPORT void oracle_bc_x_Pr(double *A, double val, int sx, int sy, int sz)
+{
+    for (int k = 1; k <= sz; ++k)
+        for (int j = 1; j <= sy; ++j) A3(A, sx, sy, sx, j, k) = val;
+}
+/* bc_zV!  G:239-243 */
+EXPORT void oracle_bc_zV(double *A, int sx, int sy, int sz)
+{
+    for (int j = 1; j <= sy; ++j)
+        for (int i = 1; i <= sx; ++i) {
+            A3(A, sx, sy, i, j, 1) = 0.0;
+            A3(A, sx, sy, i, j, sz) = A3(A, sx, sy, i, j, sz - 1);
+        }
+}
+/* bc_xhydstatic!  G:257-261 : ρ*g*(nz-iz + 0.5)*dz (+ 100 at the inlet) */
+EXPORT void oracle_bc_xhydstatic(double *A, double dz, int nz, double g, double rho, int sx, int sy, int sz)
+{
+    for (int k = 1; k <= sz; ++k)
+        for (int j = 1; j <= sy; ++j) {
+            double h = rho * g * ((double)(nz - k) + 0.5) * dz;
+            A3(A, sx, sy, 1, j, k) = h + 100;
+            A3(A, sx, sy, sx, j, k) = h;
+        }
+}
+
+/* set_bc_Vel!  variant M  M:156-169 (update_halo! is the caller's business) */
+EXPORT void oracle_set_bc_Vel_M(double *Vx, double *Vy, double *Vz, int inlet, double vin, int nx, int ny,
+                                int nz)
+{
+    oracle_bc_x(Vx, nx + 1, ny, nz);
+    oracle_bc_y(Vx, nx + 1, ny, nz);
+    oracle_bc_z(Vx, nx + 1, ny, nz);
+    oracle_bc_x(Vy, nx, ny + 1, nz);
+    oracle_bc_z(Vy, nx, ny + 1, nz);
+    oracle_bc_x(Vz, nx, ny, nz + 1);
+    oracle_bc_y(Vz, nx, ny, nz + 1);
+    if (inlet) oracle_bc_x_Vx(Vx, vin, nx + 1, ny, nz); /* guard xvo_g == -lx/2, M:164 */
+}
+/* set_bc_Vel!  variant G  G:264-279 (Vprof unused) */
+EXPORT void oracle_set_bc_Vel_G(double *Vx, double *Vy, double *Vz, int nx, int ny, int nz)
+{
+    oracle_bc_x(Vx, nx + 1, ny, nz);
+    oracle_bc_y(Vx, nx + 1, ny, nz);
+    oracle_bc_zV(Vx, nx + 1, ny, nz);
+    oracle_bc_x(Vy, nx, ny + 1, nz);
+    oracle_bc_y(Vy, nx, ny + 1, nz);
+    oracle_bc_zV(Vy, nx, ny + 1, nz);
+    oracle_bc_x(Vz, nx, ny, nz + 1);
+    oracle_bc_y(Vz, nx, ny, nz + 1);
+    oracle_bc_zV(Vz, nx, ny, nz + 1);
+}
+/* set_bc_Pr!  variant M  M:175-184 */
+EXPORT void oracle_set_bc_Pr_M(double *Pr, int outlet, double val, int nx, int ny, int nz)
+{
+    oracle_bc_x(Pr, nx, ny, nz);
+    oracle_bc_y(Pr, nx, ny, nz);
+    oracle_bc_z(Pr, nx, ny, nz);
+    if (outlet) oracle_bc_x_Pr(Pr, val, nx, ny, nz); /* guard xve_g == lx/2, M:179 */
+}
+/* set_bc_Pr!  variant G  G:281-286 */
+EXPORT void oracle_set_bc_Pr_G(double *Pr, double dz, int nzarg, double g, double rho, int nx, int ny, int nz)
+{
+    oracle_bc_y(Pr, nx, ny, nz);
+    oracle_bc_z(Pr, nx, ny, nz);
+    oracle_bc_xhydstatic(Pr, dz, nzarg, g, rho, nx, ny, nz);
+}
+
+/* ------------------------------------------------------------------------- */
+/* K11  advect! + backtrack! + lerp   M:190-243 (= G:288-334)                 */
+/* ------------------------------------------------------------------------- */
+static inline double lerp_(double a, double b, double t) { return b * t + a * (1 - t); } /* M:211 */
+
+static inline long clampl(long v, long lo, long hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* backtrack!  M:190-205; (sx,sy,sz) = size(A) */
+static inline void backtrack(double *A, const double *Ao, double vxc, double vyc, double vzc, double dt,
+                             double dx, double dy, double dz, int ix, int iy, int iz, int sx, int sy, int sz)
+{
+    double ddx = dt * vxc / dx, ddy = dt * vyc / dy, ddz = dt * vzc / dz;
+    long ix1 = clampl((long)floor((double)ix - ddx), 1, sx);
+    long iy1 = clampl((long)floor((double)iy - ddy), 1, sy);
+    long iz1 = clampl((long)floor((double)iz - ddz), 1, sz);
+    long ix2 = clampl(ix1 + 1, 1, sx), iy2 = clampl(iy1 + 1, 1, sy), iz2 = clampl(iz1 + 1, 1, sz);
+    ddx = (ddx > 0 ? 1.0 : 0.0) - fmod(ddx, 1.0);
+    ddy = (ddy > 0 ? 1.0 : 0.0) - fmod(ddy, 1.0);
+    ddz = (ddz > 0 ? 1.0 : 0.0) - fmod(ddz, 1.0);
+    double fy1z1 = lerp_(A3(Ao, sx, sy, ix1, iy1, iz1), A3(Ao, sx, sy, ix2, iy1, iz1), ddx);
+    double fy1z2 = lerp_(A3(Ao, sx, sy, ix1, iy1, iz2), A3(Ao, sx, sy, ix2, iy1, iz2), ddx);
+    double fy2z1 = lerp_(A3(Ao, sx, sy, ix1, iy2, iz1), A3(Ao, sx, sy, ix2, iy2, iz1), ddx);
+    double fy2z2 = lerp_(A3(Ao, sx, sy, ix1, iy2, iz2), A3(Ao, sx, sy, ix2, iy2, iz2), ddx);
+    double fz1 = lerp_(fy1z1, fy2z1, ddy);
+    double fz2 = lerp_(fy1z2, fy2z2, ddy);
+    A3(A, sx, sy, ix, iy, iz) = lerp_(fz1, fz2, ddz);
+}
+
+#define VXO(i, j, k) A3(Vx_o, nx + 1, ny, i, j, k)
+#define VYO(i, j, k) A3(Vy_o, nx, ny + 1, i, j, k)
+#define VZO(i, j, k) A3(Vz_o, nx, ny, i, j, k)
+
+/* advect!  M:217-243.  NOTE the reference's third branch calls
+ * backtrack!(Vy,Vy_o,...) (M:234): Vz is never advected and Vy is written twice
+ * by the same (ix,iy,iz) "thread", branch 3 last.  Reproduced literally. */
+EXPORT void oracle_advect(double *Vx, const double *Vx_o, double *Vy, const double *Vy_o, double *Vz,
+                          const double *Vz_o, double *C, const double *C_o, double dt, double dx, double dy,
+                          double dz, int nx, int ny, int nz)
+{
+    (void)Vz;
+#pragma omp parallel for schedule(static)
+    for (int iz = 1; iz <= nz + 1; ++iz)
+        for (int iy = 1; iy <= ny + 1; ++iy)
+            for (int ix = 1; ix <= nx + 1; ++ix) {
+                if (ix > 1 && ix < nx + 1 && iy <= ny && iz <= nz) {
+                    double vxc = VXO(ix, iy, iz);
+                    double vyc = 0.25 * (((VYO(ix - 1, iy, iz) + VYO(ix - 1, iy + 1, iz)) + VYO(ix, iy, iz)) + VYO(ix, iy + 1, iz));
+                    double vzc = 0.25 * (((VZO(ix - 1, iy, iz) + VZO(ix - 1, iy, iz + 1)) + VZO(ix, iy, iz)) + VZO(ix, iy, iz + 1));
+                    backtrack(Vx, Vx_o, vxc, vyc, vzc, dt, dx, dy, dz, ix, iy, iz, nx + 1, ny, nz);
+                }
+                if (iy > 1 && iy < ny + 1 && ix <= nx && iz <= nz) {
+                    double vxc = 0.25 * (((VXO(ix, iy - 1, iz) + VXO(ix + 1, iy - 1, iz)) + VXO(ix, iy, iz)) + VXO(ix + 1, iy, iz));
+                    double vyc = VYO(ix, iy, iz);
+                    double vzc = 0.25 * (((VZO(ix, iy - 1, iz) + VZO(ix, iy - 1, iz + 1)) + VZO(ix, iy, iz)) + VZO(ix, iy, iz + 1));
+                    backtrack(Vy, Vy_o, vxc, vyc, vzc, dt, dx, dy, dz, ix, iy, iz, nx, ny + 1, nz);
+                }
+                if (iz > 1 && iz < nz + 1 && ix <= nx && iy <= ny) {
+                    double vxc = 0.25 * (((VXO(ix, iy, iz - 1) + VXO(ix + 1, iy, iz - 1)) + VXO(ix, iy, iz)) + VXO(ix + 1, iy, iz));
+                    double vyc = 0.25 * (((VYO(ix, iy, iz - 1) + VYO(ix, iy + 1, iz - 1)) + VYO(ix, iy, iz)) + VYO(ix, iy + 1, iz));
+                    double vzc = VZO(ix, iy, iz);
+                    backtrack(Vy, Vy_o, vxc, vyc, vzc, dt, dx, dy, dz, ix, iy, iz, nx, ny + 1, nz); /* sic, M:234 */
+                }
+                if (ix <= nx && iy <= ny && iz <= nz) {
+                    double vxc = 0.5 * (VXO(ix, iy, iz) + VXO(ix + 1, iy, iz));
+                    double vyc = 0.5 * (VYO(ix, iy, iz) + VYO(ix, iy + 1, iz));
+                    double vzc = 0.5 * (VZO(ix, iy, iz) + VZO(ix, iy, iz + 1));
+                    backtrack(C, C_o, vxc, vyc, vzc, dt, dx, dy, dz, ix, iy, iz, nx, ny, nz);
+                }
+            }
+}
+
+/* ------------------------------------------------------------------------- */
+/* K3  set_cylinder!                                                          */
+/* ------------------------------------------------------------------------- */
+static inline int in_ellipse(double X, double Y, double ox, double oy, double sinb, double cosb, double a2,
+                             double b2, double thr)
+{
+    double xr = (X - ox) * cosb - (Y - oy) * sinb;
+    double yr = (X - ox) * sinb + (Y - oy) * cosb;
+    return xr * xr / a2 + yr * yr / b2 < thr;
+}
+
+/* variant selects the coordinate formulas: 0 = M (M:250-251), 1 = G (G:337-338) */
+static void set_cylinder(int variant, double *C, double *Vx, double *Vy, double *Vz, double a2, double b2,
+                         double ox, double oy, double sinb, double cosb, double xco_g, double yco_g,
+                         double lx, double ly, double dx, double dy, int nx, int ny, int nz)
+{
+#pragma omp parallel for schedule(static)
+    for (int iz = 1; iz <= nz + 1; ++iz)
+        for (int iy = 1; iy <= ny + 1; ++iy)
+            for (int ix = 1; ix <= nx + 1; ++ix) {
+                double xc, yc, xv, yv;
+                if (variant == 0) {
+                    xc = xco_g + (ix - 1) * dx;
+                    yc = yco_g + (iy - 1) * dy;
+                    xv = xc - dx / 2;
+                    yv = yc - dy / 2;
+                } else {
+                    xv = (ix - 1) * dx - lx / 2;
+                    yv = (iy - 1) * dy - ly / 2;
+                    xc = xv + dx / 2;
+                    yc = yv + dx / 2; /* sic: dx, G:338 */
+                }
+                if (ix <= nx && iy <= ny && iz <= nz)
+                    if (in_ellipse(xc, yc, ox, oy, sinb, cosb, a2, b2, 1.05)) A3(C, nx, ny, ix, iy, iz) = 1.0;
+                if (ix <= nx + 1 && iy <= ny && iz <= nz)
+                    if (in_ellipse(xv, yc, ox, oy, sinb, cosb, a2, b2, 1.0)) A3(Vx, nx + 1, ny, ix, iy, iz) = 0.0;
+                if (ix <= nx && iy <= ny + 1 && iz <= nz)
+                    if (in_ellipse(xc, yv, ox, oy, sinb, cosb, a2, b2, 1.0)) A3(Vy, nx, ny + 1, ix, iy, iz) = 0.0;
+                if (ix <= nx && iy <= ny && iz <= nz + 1)
+                    if (in_ellipse(xc, yc, ox, oy, sinb, cosb, a2, b2, 1.0)) A3(Vz, nx, ny, ix, iy, iz) = 0.0;
+            }
+}
+
+/* set_cylinder!  variant M  M:249-281 (zco_g, lx, ly, lz, dz are unused by the reference) */
+EXPORT void oracle_set_cylinder_M(double *C, double *Vx, double *Vy, double *Vz, double a2, double b2,
+                                  double ox, double oy, double sinb, double cosb, double xco_g, double yco_g,
+                                  double dx, double dy, int nx, int ny, int nz)
+{
+    set_cylinder(0, C, Vx, Vy, Vz, a2, b2, ox, oy, sinb, cosb, xco_g, yco_g, 0.0, 0.0, dx, dy, nx, ny, nz);
+}
+/* set_cylinder!  variant G  G:336-368 */
+EXPORT void oracle_set_cylinder_G(double *C, double *Vx, double *Vy, double *Vz, double a2, double b2,
+                                  double ox, double oy, double sinb, double cosb, double lx, double ly,
+                                  double dx, double dy, int nx, int ny, int nz)
+{
+    set_cylinder(1, C, Vx, Vy, Vz, a2, b2, ox, oy, sinb, cosb, 0.0, 0.0, lx, ly, dx, dy, nx, ny, nz);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Whole time steps, reference-shaped (all 18 arrays, no fusion).             */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    /* grid (local = global: single rank) */
+    int nx, ny, nz;
+    int variant; /* 0 = M (multi_gpu.jl, one rank), 1 = G (gpu.jl) */
+    /* scalars, named as in the scripts */
+    double lx, ly, lz, dx, dy, dz, dt, dtau, damp, rho, mu, g, vin, psc;
+    double a2, b2, ox, oy, sinb, cosb, xco_g, yco_g;
+    double eps_it;
+    int niter, nchk;
+    int inlet_guard, outlet_guard; /* M:164 / M:179 evaluated by the caller */
+} oracle_params;
+
+typedef struct {
+    double *Pr, *dPrdtau, *C, *C_o, *txx, *tyy, *tzz, *txy, *txz, *tyz;
+    double *Vx, *Vy, *Vz, *Vx_o, *Vy_o, *Vz_o, *divV, *Rp;
+    double *absRp; /* the abs.(Rp) temporary */
+} oracle_fields;
+
+static void set_bc_Pr(const oracle_params *p, double *Pr)
+{
+    if (p->variant == 0)
+        oracle_set_bc_Pr_M(Pr, p->outlet_guard, 0.0, p->nx, p->ny, p->nz);
+    else
+        oracle_set_bc_Pr_G(Pr, p->dz, p->nz, p->g, p->rho, p->nx, p->ny, p->nz);
+}
+
+static void set_cyl(const oracle_params *p, oracle_fields *f)
+{
+    set_cylinder(p->variant, f->C, f->Vx, f->Vy, f->Vz, p->a2, p->b2, p->ox, p->oy, p->sinb, p->cosb,
+                 p->xco_g, p->yco_g, p->lx, p->ly, p->dx, p->dy, p->nx, p->ny, p->nz);
+}
+
+/* PT loop  M:458-471 / G:126-137.  Returns the number of iterations done;
+ * err_hist (capacity cap) receives err at every residual check. */
+EXPORT int oracle_pt_solve(const oracle_params *p, oracle_fields *f, double *err_hist, int cap, int *nchecks)
+{
+    const int nx = p->nx, ny = p->ny, nz = p->nz;
+    int iters = 0, nc = 0;
+    for (int iter = 1; iter <= p->niter; ++iter) {
+        oracle_update_dPrdtau(f->Pr, f->dPrdtau, f->divV, p->rho, p->dt, p->dtau, p->damp, p->dx, p->dy, p->dz, nx, ny, nz);
+        oracle_update_Pr(f->Pr, f->dPrdtau, p->dtau, nx, ny, nz);
+        set_bc_Pr(p, f->Pr);
+        iters = iter;
+        if (iter % p->nchk == 0) {
+            oracle_compute_res(f->Rp, f->Pr, f->divV, p->rho, p->dt, p->dx, p->dy, p->dz, nx, ny, nz);
+            double m = oracle_max_abs(f->Rp, f->absRp, (size_t)(nx - 2) * (ny - 2) * (nz - 2));
+            double err = m * (p->ly * p->ly) / p->psc; /* max*ly^2/psc, M:466 */
+            if (err_hist && nc < cap) err_hist[nc] = err;
+            ++nc;
+            if (err < p->eps_it || !isfinite(err)) break;
+        }
+    }
+    if (nchecks) *nchecks = nc;
+    return iters;
+}
+
+/* One time step  M:449-477 (single rank: every update_halo! is a no-op) / G:121-142. */
+EXPORT int oracle_step(const oracle_params *p, oracle_fields *f, double *err_hist, int cap, int *nchecks)
+{
+    const int nx = p->nx, ny = p->ny, nz = p->nz;
+    oracle_update_tau(f->txx, f->tyy, f->tzz, f->txy, f->txz, f->tyz, f->Vx, f->Vy, f->Vz, p->mu, p->dx, p->dy, p->dz, nx, ny, nz);
+    oracle_predict_V(f->Vx, f->Vy, f->Vz, f->txx, f->tyy, f->tzz, f->txy, f->txz, f->tyz, p->rho, p->g, p->dt, p->dx, p->dy, p->dz, nx, ny, nz);
+    set_cyl(p, f);
+    oracle_update_divV(f->divV, f->Vx, f->Vy, f->Vz, p->dx, p->dy, p->dz, nx, ny, nz);
+    int iters = oracle_pt_solve(p, f, err_hist, cap, nchecks);
+    oracle_correct_V(f->Vx, f->Vy, f->Vz, f->Pr, p->dt, p->rho, p->dx, p->dy, p->dz, nx, ny, nz);
+    set_cyl(p, f);
+    if (p->variant == 0)
+        oracle_set_bc_Vel_M(f->Vx, f->Vy, f->Vz, p->inlet_guard, p->vin, nx, ny, nz);
+    else
+        oracle_set_bc_Vel_G(f->Vx, f->Vy, f->Vz, nx, ny, nz);
+    /* Vx_o .= Vx; ... C_o .= C   M:475 */
+    memcpy(f->Vx_o, f->Vx, sizeof(double) * (size_t)(nx + 1) * ny * nz);
+    memcpy(f->Vy_o, f->Vy, sizeof(double) * (size_t)nx * (ny + 1) * nz);
+    memcpy(f->Vz_o, f->Vz, sizeof(double) * (size_t)nx * ny * (nz + 1));
+    memcpy(f->C_o, f->C, sizeof(double) * (size_t)nx * ny * nz);
+    oracle_advect(f->Vx, f->Vx_o, f->Vy, f->Vy_o, f->Vz, f->Vz_o, f->C, f->C_o, p->dt, p->dx, p->dy, p->dz, nx, ny, nz);
+    return iters;
+}
+
+EXPORT size_t oracle_sizeof_params(void) { return sizeof(oracle_params); }
+EXPORT size_t oracle_sizeof_fields(void) { return sizeof(oracle_fields); }
