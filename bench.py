@@ -110,7 +110,7 @@ def oracle_sample(variant: str, nx: int, ny, nz, budget_s: float = 12.0):
     for _ in range(2):
         O.update_dPrdtau(p, f); O.update_Pr(p, f); O.set_bc_Pr(p, f)
     t_it = (time.perf_counter() - t0) / 2
-    n_it = int(max(4, min(p.nchk, budget_s / max(t_it, 1e-6))))
+    n_it = int(max(4, min(20 * p.nchk, budget_s / max(t_it, 1e-6))))
     f = O.initial_fields(p)
     p.niter, p.nchk = n_it, n_it
     t0 = time.perf_counter()

@@ -387,14 +387,27 @@ static inline double lerp_(double a, double b, double t) { return b * t + a * (1
 
 static inline long clampl(long v, long lo, long hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+/* floor(Int, x).  Julia throws InexactError when x is NaN or outside Int64 (only reachable
+ * after the run has blown up, e.g. the unstable 31x19x19 grid at step 4); a C cast would be
+ * undefined there.  Oracle and CUDA kernel both SATURATE instead (NaN -> INT64_MIN, the
+ * behaviour of CUDA's __double2ll_rd), so that they agree even on diverged states. */
+static inline long floor_to_long(double x)
+{
+    double fl = floor(x);
+    if (!(fl == fl)) return INT64_MIN;
+    if (fl >= 9223372036854775807.0) return INT64_MAX;
+    if (fl <= -9223372036854775808.0) return INT64_MIN;
+    return (long)fl;
+}
+
 /* backtrack!  M:190-205; (sx,sy,sz) = size(A) */
 static inline void backtrack(double *A, const double *Ao, double vxc, double vyc, double vzc, double dt,
                              double dx, double dy, double dz, int ix, int iy, int iz, int sx, int sy, int sz)
 {
     double ddx = dt * vxc / dx, ddy = dt * vyc / dy, ddz = dt * vzc / dz;
-    long ix1 = clampl((long)floor((double)ix - ddx), 1, sx);
-    long iy1 = clampl((long)floor((double)iy - ddy), 1, sy);
-    long iz1 = clampl((long)floor((double)iz - ddz), 1, sz);
+    long ix1 = clampl(floor_to_long((double)ix - ddx), 1, sx);
+    long iy1 = clampl(floor_to_long((double)iy - ddy), 1, sy);
+    long iz1 = clampl(floor_to_long((double)iz - ddz), 1, sz);
     long ix2 = clampl(ix1 + 1, 1, sx), iy2 = clampl(iy1 + 1, 1, sy), iz2 = clampl(iz1 + 1, 1, sz);
     ddx = (ddx > 0 ? 1.0 : 0.0) - fmod(ddx, 1.0);
     ddy = (ddy > 0 ? 1.0 : 0.0) - fmod(ddy, 1.0);

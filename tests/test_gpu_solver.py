@@ -109,12 +109,17 @@ def test_pt_solve_nonfinite_breaks(O, ns, ctx):
     assert len(hist_g) == 1 and np.isnan(hist_g[0]) and np.isnan(hist_o[0])
 
 
-@pytest.mark.parametrize("variant,nx,nt", [("M", 63, 6), ("G", 63, 3), ("M", 31, 4)])
+@pytest.mark.parametrize("variant,nx,nt", [("M", 63, 6), ("G", 63, 3), ("M", 40, 4), ("G", 40, 2), ("M", 31, 6)])
 @pytest.mark.parametrize("level1", [False, True])
 def test_time_steps_parity_mode(O, ns, variant, nx, nt, level1):
-    """Config A (test/test3D.jl's grid, nt extended: step 1 of variant M is degenerate) end to end."""
-    if level1 and (variant, nx) != ("M", 31):
-        pytest.skip("the call-by-call level-1 loop is exercised on the small grid only (launch bound)")
+    """Config A (test/test3D.jl's grid, nt extended: step 1 of variant M is degenerate) end to end.
+
+    40x24x24 (dx=dy=dz) is a second stable grid.  31x19x19 is UNSTABLE in the reference's own
+    numerics (the PT loop hits niter at step 4 and the fields overflow to Inf/NaN by step 5):
+    it is kept to pin that kernel and oracle agree bit-for-bit even on a diverged state
+    (saturating floor(Int, .) in backtrack!, NaN-propagating maximum)."""
+    if level1 and nx == 63:
+        pytest.skip("the call-by-call level-1 loop is exercised on the small grids only (launch bound)")
     p = oracle_params(O, variant, nx)
     f, iters_o, errs_o = O.run(p, nt)
     s = setup_for(ns, variant, nx)
@@ -122,10 +127,13 @@ def test_time_steps_parity_mode(O, ns, variant, nx, nt, level1):
     for _ in range(nt):
         sim.step_level1() if level1 else sim.step()
     assert sim.iters == iters_o
-    assert sim.err_hist == errs_o
+    assert np.array_equal(np.concatenate(sim.err_hist), np.concatenate(errs_o), equal_nan=True)
     for name in ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C", "divV"):
         got = sim.host(name)
-        assert (got == f[name]).all(), f"{name}: {(got != f[name]).sum()} values differ"
+        same = (got == f[name]) | (np.isnan(got) & np.isnan(f[name]))
+        assert same.all(), f"{name}: {(~same).sum()} values differ"
+    if nx != 31:
+        assert all(np.isfinite(f[v]).all() for v in ("Pr", "Vx", "Vy", "Vz", "C"))
     if variant == "M":
         assert iters_o[0] == p.nchk and errs_o[0] == [0.0]   # quirk 2: step 1 is degenerate, Pr == 0
     sim.ctx.close()

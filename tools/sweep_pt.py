@@ -1,0 +1,40 @@
+"""Times the fused PT iteration (us/launch, T_eff) over modes / zchunk / grid sizes (tuning aid)."""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import navierstokes3d_b200 as ns
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--grids", default="255x153x153,511x511x511")
+ap.add_argument("--modes", default="PARITY,FAST,FASTEST")
+ap.add_argument("--zchunks", default="0,2,4,8,16,32")
+ap.add_argument("--iters", type=int, default=200)
+ap.add_argument("--variant", default="G")
+args = ap.parse_args()
+rng = np.random.default_rng(0)
+for g in args.grids.split(","):
+    nx, ny, nz = map(int, g.split("x"))
+    s = ns.setup_gpu(nx, ny=ny, nz=nz) if args.variant == "G" else ns.setup_multi_gpu(nx, ny=ny, nz=nz)
+    n = nx * ny * nz
+    for mode in args.modes.split(","):
+        ctx = ns.Context(0, getattr(ns, mode))
+        stream = torch.cuda.ExternalStream(ctx.stream)
+        Pr = ctx.from_host(np.asfortranarray(rng.uniform(-1, 1, size=(nx, ny, nz))))
+        dP = ctx.zeros(nx - 2, ny - 2, nz - 2)
+        dv = ctx.from_host(np.asfortranarray(rng.uniform(-1e-3, 1e-3, size=(nx, ny, nz))))
+        for zc in map(int, args.zchunks.split(",")):
+            pt = s.pt_params(zc)
+            ctx.pt_iterate(Pr, dP, dv, pt, 20)
+            ctx.sync()
+            best = 1e9
+            for rep in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                ctx.pt_iterate(Pr, dP, dv, pt, args.iters)
+                e1.record(stream)
+                ctx.sync()
+                best = min(best, e0.elapsed_time(e1) / args.iters * 1e3)
+            print(json.dumps({"grid": g, "mode": mode, "zchunk": zc, "us_per_iter": round(best, 2),
+                              "T_eff_GBs": round(40.0 * n / best / 1e3, 1)}), flush=True)
+        ctx.close()
