@@ -73,6 +73,9 @@ NS3D_API const char* ns3d_version(void);
 NS3D_API const char* ns3d_last_error(const ns3d_ctx* ctx); /* ctx may be NULL: last create() error */
 NS3D_API int ns3d_set_mode(ns3d_ctx* ctx, int mode);
 NS3D_API int ns3d_get_mode(const ns3d_ctx* ctx);
+/* Tuning / diagnostic knobs that never change results ("pt_minb": CTAs per SM the hot kernel
+ * is compiled for, 3..6). */
+NS3D_API int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value);
 NS3D_API int ns3d_sync(ns3d_ctx* ctx);
 /* Number of kernels this library launched on ctx since creation (bench bookkeeping). */
 NS3D_API long long ns3d_launch_count(const ns3d_ctx* ctx);

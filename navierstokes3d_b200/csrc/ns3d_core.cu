@@ -148,6 +148,18 @@ extern "C" int ns3d_set_mode(ns3d_ctx* ctx, int mode)
     ctx->mode = mode;
     return NS3D_OK;
 }
+extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
+{
+    NS3D_CHECK_CTX(ctx);
+    if (!name) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_set_option: NULL name");
+    if (!strcmp(name, "pt_minb")) {
+        if (value != 0 && (value < 3 || value > 6)) return ns3d_fail(ctx, NS3D_EINVAL, "pt_minb must be 0 (auto) or 3..6");
+        ctx->opt_pt_minb = value;
+        return NS3D_OK;
+    }
+    return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_set_option: unknown option '%s'", name);
+}
+
 extern "C" int ns3d_get_mode(const ns3d_ctx* ctx) { return ctx ? ctx->mode : NS3D_EINVAL; }
 
 extern "C" int ns3d_sync(ns3d_ctx* ctx)

@@ -31,6 +31,8 @@ struct ns3d_ctx {
     // communicator (z-slabs, one rank per GPU)
     void* nccl = nullptr;
     int rank = 0, nranks = 1;
+    // tuning knobs (ns3d_set_option)
+    int opt_pt_minb = 0;  // 0 = per-mode default
 };
 
 int ns3d_fail(ns3d_ctx* ctx, int code, const char* fmt, ...);

@@ -78,32 +78,40 @@ __device__ __forceinline__ double xface(const PtK& p, bool hi, int k, double u)
     return hi ? h : h + p.xlo_val;
 }
 
-// Stores the new value u of interior point (i,j) into plane k of PrN together with its
-// x/y mirror images (k may itself be a z-mirror plane 0 / nz-1).
-__device__ __forceinline__ void store_with_mirrors(const PtK& p, double* __restrict__ PrN, int i, int j, int k,
-                                                   double u)
+// Stores the new value u of the interior point at x index i into row pointers of one plane:
+// `row` is the row j itself, mirrors go to x faces (xl/xh) and to the y-face rows (ylo/yhi,
+// NULL when the point is not next to that face).  k selects the hydrostatic value (variant G).
+__device__ __forceinline__ void store_row(const PtK& p, double* __restrict__ row, int i, int k, double u, bool xl,
+                                          bool xh)
 {
-    const int nx = p.nx, ny = p.ny;
-    const bool xl = (i == 1), xh = (i == nx - 2), yl = (j == 1), yh = (j == ny - 2);
-    double* row = PrN + idx3(0, j, k, nx, ny);
     row[i] = u;
     if (xl) row[0] = xface(p, false, k, u);
-    if (xh) row[nx - 1] = xface(p, true, k, u);
-    if (yl | yh) {
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            if (s == 0 ? !yl : !yh) continue;
-            double* r2 = PrN + idx3(0, s == 0 ? 0 : ny - 1, k, nx, ny);
-            r2[i] = u;
-            if (xl) r2[0] = xface(p, false, k, u);
-            if (xh) r2[nx - 1] = xface(p, true, k, u);
-        }
-    }
+    if (xh) row[p.nx - 1] = xface(p, true, k, u);
+}
+
+__device__ __forceinline__ void store_plane(const PtK& p, double* __restrict__ plane, int i, int j, int k, double u,
+                                            bool xl, bool xh, bool yl, bool yh)
+{
+    store_row(p, plane + (size_t)j * p.nx, i, k, u, xl, xh);
+    if (yl) store_row(p, plane, i, k, u, xl, xh);
+    if (yh) store_row(p, plane + (size_t)(p.ny - 1) * p.nx, i, k, u, xl, xh);
 }
 
 // One fused PT iteration: K5 + K6 + set_bc_Pr!.
-template <int MODE>
-__global__ void __launch_bounds__(256) pt_iter_kernel(const double* __restrict__ Pr, double* __restrict__ PrN,
+//
+// Each thread owns one interior column (i,j) and marches planes [kb,ke).  The three streams
+// that come from DRAM/L2 (Pr plane k+1, dPrdτ, ∇V) are software-pipelined: the loop is unrolled
+// by two with two named register sets (A, B), the loads of plane k+1 are issued before the
+// arithmetic of plane k and land in the other set, so no register move waits on them.  The
+// four in-plane neighbours were brought into L1 one step earlier by this and the adjacent
+// warps (as their "plane k+1" loads) and are read just in time.  The z neighbours stay in
+// registers, and the face bookkeeping is hoisted into one per-thread flag.
+struct StreamRegs {
+    double zp, dq, dv;
+};
+
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(256, MINB) pt_iter_kernel(const double* __restrict__ Pr, double* __restrict__ PrN,
                                                       double* __restrict__ dP, const double* __restrict__ divV,
                                                       const PtK p)
 {
@@ -113,33 +121,55 @@ __global__ void __launch_bounds__(256) pt_iter_kernel(const double* __restrict__
     if (i > nx - 2 || j > ny - 2) return;
     const int kb = 1 + blockIdx.z * p.zchunk;
     const int ke = min(kb + p.zchunk, nz - 1);  // interior planes [kb, ke)
-    const size_t sxy = (size_t)nx * ny;
-    const size_t dxy = (size_t)(nx - 2) * (ny - 2);
-    const double* c = Pr + idx3(i, j, kb, nx, ny);
-    const double* dv = divV + idx3(i, j, kb, nx, ny);
-    double* dp = dP + idx3(i - 1, j - 1, kb - 1, nx - 2, ny - 2);
-    double pm = c[-(ptrdiff_t)sxy];
-    double pc = c[0];
-    for (int k = kb; k < ke; ++k) {
-        const double pp = c[sxy];
-        const double L = bracket<MODE>(p, pc, c[-1], c[1], c[-nx], c[nx], pm, pp, dv[0]);
+    const ptrdiff_t sxy = (ptrdiff_t)nx * ny;
+    const ptrdiff_t dxy = (ptrdiff_t)(nx - 2) * (ny - 2);
+    const bool xl = (i == 1), xh = (i == nx - 2), yl = (j == 1), yh = (j == ny - 2);
+    const bool edge = xl | xh | yl | yh;
+    ptrdiff_t off = (ptrdiff_t)idx3(i, j, kb, nx, ny);                      // into Pr, PrN, divV
+    ptrdiff_t dof = (ptrdiff_t)idx3(i - 1, j - 1, kb - 1, nx - 2, ny - 2);  // into dPrdτ
+
+    auto load = [&](StreamRegs& r, ptrdiff_t o, ptrdiff_t d) {
+        r.zp = Pr[o + sxy];
+        r.dq = dP[d];
+        r.dv = divV[o];
+    };
+    double pm = Pr[off - sxy], pc = Pr[off];
+    auto compute = [&](const StreamRegs& r, int k, ptrdiff_t o, ptrdiff_t d) {
+        const double L = bracket<MODE>(p, pc, Pr[o - 1], Pr[o + 1], Pr[o - nx], Pr[o + nx], pm, r.zp, r.dv);
         double dn, u;
         if (MODE == NS3D_FASTEST) {
-            dn = fma(p.dtau, L, dp[0] * p.omd);
+            dn = fma(p.dtau, L, r.dq * p.omd);
             u = fma(p.dtau, dn, pc);
         } else {
-            dn = dp[0] * p.omd + p.dtau * L;  // M:71
-            u = pc + p.dtau * dn;             // M:80
+            dn = r.dq * p.omd + p.dtau * L;  // M:71
+            u = pc + p.dtau * dn;            // M:80
         }
-        dp[0] = dn;
-        store_with_mirrors(p, PrN, i, j, k, u);
-        if (k == 1 && !p.zlo_halo) store_with_mirrors(p, PrN, i, j, 0, u);            // bc_z! M:129
-        if (k == nz - 2 && !p.zhi_halo) store_with_mirrors(p, PrN, i, j, nz - 1, u);  // bc_z! M:130
+        dP[d] = dn;
+        PrN[o] = u;
+        if (edge) {  // x/y mirror images in this plane (bc_x!, bc_y!; outlet / hydrostatic x faces)
+            double* plane = PrN + (o - ((ptrdiff_t)j * nx + i));
+            if (xl) plane[(ptrdiff_t)j * nx] = xface(p, false, k, u);
+            if (xh) plane[(ptrdiff_t)j * nx + nx - 1] = xface(p, true, k, u);
+            if (yl) store_row(p, plane, i, k, u, xl, xh);
+            if (yh) store_row(p, plane + (ptrdiff_t)(ny - 1) * nx, i, k, u, xl, xh);
+        }
+        if (k == 1 && !p.zlo_halo) store_plane(p, PrN, i, j, 0, u, xl, xh, yl, yh);  // bc_z! M:129
+        if (k == nz - 2 && !p.zhi_halo)
+            store_plane(p, PrN + (ptrdiff_t)(nz - 1) * sxy, i, j, nz - 1, u, xl, xh, yl, yh);  // bc_z! M:130
         pm = pc;
-        pc = pp;
-        c += sxy;
-        dv += sxy;
-        dp += dxy;
+        pc = r.zp;
+    };
+
+    StreamRegs A, B;
+    load(A, off, dof);
+    for (int k = kb; k < ke; k += 2) {
+        const bool has1 = k + 1 < ke, has2 = k + 2 < ke;
+        if (has1) load(B, off + sxy, dof + dxy);
+        compute(A, k, off, dof);
+        if (has2) load(A, off + 2 * sxy, dof + 2 * dxy);
+        if (has1) compute(B, k + 1, off + sxy, dof + dxy);
+        off += 2 * sxy;
+        dof += 2 * dxy;
     }
 }
 
@@ -210,7 +240,7 @@ int make_ptk(ns3d_ctx* ctx, const ns3d_pt_params* p, PtK* k)
         // two extra plane loads at the start of every chunk
         const long long xy = (long long)cdiv(p->nx - 2, 32) * cdiv(p->ny - 2, 8);
         zc = 16;
-        while (zc > 4 && xy * cdiv(p->nz - 2, zc) < 8LL * 8 * ctx->num_sms) zc /= 2;
+        while (zc > 4 && xy * cdiv(p->nz - 2, zc) < 2LL * 8 * ctx->num_sms) zc /= 2;  // measured: profiles/r01_*sweep*
     }
     k->zchunk = zc;
     return NS3D_OK;
@@ -239,11 +269,26 @@ inline dim3 pt_grid(const PtK& k) { return dim3(cdiv(k.nx - 2, 32), cdiv(k.ny - 
 
 int launch_iter(ns3d_ctx* ctx, const PtK& k, const double* cur, double* nxt, double* dP, const double* divV)
 {
-    switch (ctx->mode) {
-        case NS3D_PARITY: pt_iter_kernel<NS3D_PARITY><<<pt_grid(k), pt_block(), 0, ctx->stream>>>(cur, nxt, dP, divV, k); break;
-        case NS3D_FAST: pt_iter_kernel<NS3D_FAST><<<pt_grid(k), pt_block(), 0, ctx->stream>>>(cur, nxt, dP, divV, k); break;
-        default: pt_iter_kernel<NS3D_FASTEST><<<pt_grid(k), pt_block(), 0, ctx->stream>>>(cur, nxt, dP, divV, k); break;
+#define PT_LAUNCH(MODE, MINB) pt_iter_kernel<MODE, MINB><<<pt_grid(k), pt_block(), 0, ctx->stream>>>(cur, nxt, dP, divV, k)
+#define PT_LAUNCH_MODE(MINB)                                  \
+    switch (ctx->mode) {                                      \
+        case NS3D_PARITY: PT_LAUNCH(NS3D_PARITY, MINB); break; \
+        case NS3D_FAST: PT_LAUNCH(NS3D_FAST, MINB); break;     \
+        default: PT_LAUNCH(NS3D_FASTEST, MINB); break;         \
     }
+    // CTAs per SM the kernel is compiled for (register cap 65536 / (256 * MINB)); the defaults are
+    // the measured optimum per mode (profiles/r01_v4_sweep_minb.jsonl): the largest occupancy
+    // that does not spill.
+    int minb = ctx->opt_pt_minb;
+    if (minb == 0) minb = ctx->mode == NS3D_FASTEST ? 5 : (ctx->mode == NS3D_FAST ? 4 : 3);
+    switch (minb) {
+        case 3: PT_LAUNCH_MODE(3); break;
+        case 5: PT_LAUNCH_MODE(5); break;
+        case 6: PT_LAUNCH_MODE(6); break;
+        default: PT_LAUNCH_MODE(4); break;
+    }
+#undef PT_LAUNCH_MODE
+#undef PT_LAUNCH
     NS3D_LAUNCH_CHECK(ctx);
     return NS3D_OK;
 }

@@ -67,6 +67,7 @@ SIGNATURES = {
     "ns3d_last_error": (C.c_char_p, [_P]),
     "ns3d_set_mode": (_I, [_P, _I]),
     "ns3d_get_mode": (_I, [_P]),
+    "ns3d_set_option": (_I, [_P, C.c_char_p, _I]),
     "ns3d_sync": (_I, [_P]),
     "ns3d_launch_count": (C.c_longlong, [_P]),
     "ns3d_stream": (_P, [_P]),
@@ -205,6 +206,9 @@ class Context:
 
     def set_mode(self, mode: int):
         self._ck(self.lib.ns3d_set_mode(self.h, mode), "ns3d_set_mode")
+
+    def set_option(self, name: str, value: int):
+        self._ck(self.lib.ns3d_set_option(self.h, name.encode(), value), "ns3d_set_option")
 
     @property
     def mode(self) -> int:
