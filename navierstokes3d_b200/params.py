@@ -57,6 +57,21 @@ class SlabGrid:
         return lo, lo + self.nz
 
 
+def halo_planes(sz: int, nz: int):
+    """Planes ``update_halo!`` moves along a split dimension (IGG, overlap 2, halo width 1).
+
+    For a field with ``sz`` points along the dimension whose local cell count is ``nz`` the overlap
+    is ol = 2 + (sz - nz).  Returns 0-based ``(send_lo, recv_lo, send_hi, recv_hi)``: plane
+    ``send_lo`` goes to the lower neighbour's ``recv_hi``, ``send_hi`` to the upper neighbour's
+    ``recv_lo`` (cell-centred: planes 1 / nz-2; face-staggered sz = nz+1: planes 2 / nz-2).
+    The C library applies the same rule in ``ns3d_update_halo``.
+    """
+    ol = 2 + (sz - nz)
+    if ol < 2:
+        raise ValueError(f"a field with {sz} planes on {nz} cells has overlap {ol} < 2 and cannot be exchanged")
+    return ol - 1, 0, sz - ol, sz - 1
+
+
 @dataclass
 class Setup:
     variant: int                 # native.VARIANT_M | native.VARIANT_G

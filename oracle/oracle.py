@@ -443,3 +443,126 @@ def run(p: Params, nt: int, f: dict | None = None):
 def interior(a: np.ndarray) -> np.ndarray:
     """``A[2:end-1,2:end-1,2:end-1]`` -- what run_navierstokes3D returns (M:528-535)."""
     return a[1:-1, 1:-1, 1:-1]
+
+
+# ----------------------------------------------------------------------------------------------
+# ImplicitGlobalGrid emulation: N virtual ranks in one process (multi-rank truth)
+# ----------------------------------------------------------------------------------------------
+class VirtualRanks:
+    """Runs script M on a dims = (dx,dy,dz) Cartesian process grid, all ranks in this process.
+
+    Restates what the reference does around its kernels when more than one MPI rank runs
+    (IGG source is not in the reference tree; semantics from SURVEY.md section 5 / 3.4):
+    every rank holds local arrays of the script's shapes (overlap 2), ``update_halo!`` is applied
+    at exactly the script's call sites (M:371,373,450,453,455,460,462,182,167,477), dimension
+    by dimension x -> y -> z, sending plane ``ol`` / ``s-ol+1`` (1-based, ol = 2 + s - n) to the
+    lower / upper neighbour's last / first plane; the residual is max-reduced over ranks
+    (``max_g``, M:21).  ``damp`` uses the local nx (M:340), coordinates come from ``x_g`` per rank.
+    """
+
+    def __init__(self, nx, ny, nz, dims, **kw):
+        self.dims = tuple(dims)
+        self.coords = [(cx, cy, cz) for cx in range(dims[0]) for cy in range(dims[1]) for cz in range(dims[2])]
+        self.p = [params_M(nx, ny, nz, dims=dims, coords=c, **kw) for c in self.coords]
+        self.f = []
+        for p in self.p:                              # M:343-373
+            f = alloc_fields(p)
+            init = initial_fields(p)                  # Vy[1,:,:] .= vin on EVERY rank (M:369, sic), Pr, cylinder
+            for k in f:
+                f[k][...] = init[k]
+            self.f.append(f)
+        # initial_fields applied set_cylinder! after the Pr assignment; the halo updates of
+        # M:371 and M:373 follow (update_halo!(Pr) commutes with set_cylinder!, which does not touch Pr)
+        self.update_halo("Pr")
+        self.update_halo("C", "Vx", "Vy", "Vz")
+        self.iters, self.errs = [], []
+
+    def rank_of(self, c):
+        return self.coords.index(tuple(c))
+
+    def update_halo(self, *names):
+        n_loc = (self.p[0].nx, self.p[0].ny, self.p[0].nz)
+        for name in names:
+            for d in range(3):
+                if self.dims[d] == 1:
+                    continue
+                s = self.f[0][name].shape[d]
+                ol = 2 + (s - n_loc[d])
+                assert ol >= 2, f"{name} cannot be exchanged along dim {d}"
+                sends = {}
+                for r, c in enumerate(self.coords):   # pack every send buffer before any unpack
+                    a = self.f[r][name]
+                    sends[r] = (np.take(a, ol - 1, axis=d).copy(), np.take(a, s - ol, axis=d).copy())
+                for r, c in enumerate(self.coords):
+                    a = self.f[r][name]
+                    idx = [slice(None)] * 3
+                    if c[d] > 0:                      # from the lower neighbour: its plane s-ol+1 -> my plane 1
+                        lo = list(c); lo[d] -= 1
+                        idx[d] = 0
+                        a[tuple(idx)] = sends[self.rank_of(lo)][1]
+                    if c[d] < self.dims[d] - 1:       # from the upper neighbour: its plane ol -> my plane s
+                        hi = list(c); hi[d] += 1
+                        idx[d] = s - 1
+                        a[tuple(idx)] = sends[self.rank_of(hi)][0]
+
+    def each(self, fn):
+        for p, f in zip(self.p, self.f):
+            fn(p, f)
+
+    def step(self):
+        p0 = self.p[0]
+        self.each(update_tau)                                         # M:449
+        self.update_halo("txx", "tyy", "tzz")                         # M:450
+        self.each(predict_V)                                          # M:451
+        self.each(set_cylinder)                                       # M:452
+        self.update_halo("C", "Vx", "Vy", "Vz")                       # M:453
+        self.each(update_divV)                                        # M:454
+        self.update_halo("divV")                                      # M:455
+        iters, hist = 0, []
+        for it in range(1, p0.niter + 1):                             # M:458
+            self.each(update_dPrdtau)                                 # M:459
+            self.update_halo("divV")                                  # M:460
+            self.each(update_Pr)                                      # M:461
+            self.update_halo("Pr")                                    # M:462
+            self.each(set_bc_Pr)                                      # M:463 ...
+            self.update_halo("Pr")                                    # ... M:182
+            iters = it
+            if it % p0.nchk == 0:                                     # M:464
+                self.each(compute_res)
+                m = max((max_abs(f["Rp"]) for f in self.f), key=lambda v: (math.isnan(v), v))   # max_g, NaN wins
+                err = m * (p0.ly * p0.ly) / p0.psc
+                hist.append(err)
+                if err < p0.eps_it or not math.isfinite(err):
+                    break
+        self.each(correct_V)                                          # M:472
+        self.each(set_cylinder)                                       # M:473
+        self.each(set_bc_Vel)                                         # M:474 ...
+        self.update_halo("Vx", "Vy", "Vz")                            # ... M:167
+        for f in self.f:                                              # M:475
+            for a in ("Vx", "Vy", "Vz", "C"):
+                f[a + "_o"][...] = f[a]
+        self.each(advect)                                             # M:476
+        self.update_halo("Vx", "Vy", "Vz")                            # M:477
+        self.iters.append(iters)
+        self.errs.append(hist)
+        return iters, hist
+
+    def assemble(self, name):
+        """Global array from the ranks' OWNED planes (local 2..n-1, plus the physical faces).
+
+        Halo planes are skipped: right after advect! (M:476-477) only Vx,Vy,Vz are exchanged, so
+        C's halo planes hold locally clamped values until the next step's M:453."""
+        n_loc = (self.p[0].nx, self.p[0].ny, self.p[0].nz)
+        shp = self.f[0][name].shape
+        gshape = tuple(self.dims[d] * (n_loc[d] - 2) + 2 + (shp[d] - n_loc[d]) for d in range(3))
+        out = np.full(gshape, np.nan, order="F")
+        for c, f in zip(self.coords, self.f):
+            src, dst = [], []
+            for d in range(3):
+                lo = 0 if c[d] == 0 else 1
+                hi = shp[d] if c[d] == self.dims[d] - 1 else n_loc[d] - 1
+                src.append(slice(lo, hi))
+                dst.append(slice(c[d] * (n_loc[d] - 2) + lo, c[d] * (n_loc[d] - 2) + hi))
+            out[tuple(dst)] = f[name][tuple(src)]
+        assert not np.isnan(out).any() or np.isnan(f[name]).any()
+        return out

@@ -1,0 +1,56 @@
+"""One rank per GPU (torchrun, NCCL): z-slab run of libns3d.so vs the oracle's IGG emulation.
+
+PARITY mode: every rank's local arrays must equal the emulation's arrays for that rank bit for bit
+(halo planes included) and the PT iteration counts must be identical.  Launched by
+tests/test_gpu_multi.py when the box has >= 2 GPUs.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import navierstokes3d_b200 as ns  # noqa: E402
+from navierstokes3d_b200.driver import attach_communicator, gather_interior  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+
+def main():
+    nx, ny, nz, nt = (int(v) for v in sys.argv[1:5])
+    lz = float(sys.argv[5]) if len(sys.argv) > 5 and sys.argv[5] != "None" else None
+    level1 = len(sys.argv) > 6 and sys.argv[6] == "level1"
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    s = ns.setup_multi_gpu(nx, ny=ny, nz=nz, rank=rank, nranks=world, lz=lz)
+    ctx = ns.Context(local, ns.PARITY)
+    attach_communicator(ctx, rank, world)
+    sim = ns.Simulation(s, ctx)
+    for _ in range(nt):
+        sim.step_level1() if level1 else sim.step()
+    truth = O.VirtualRanks(nx, ny, nz, (1, 1, world), lz=lz)
+    for _ in range(nt):
+        truth.step()
+    assert sim.iters == truth.iters, (sim.iters, truth.iters)
+    for name in ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C", "divV"):
+        got = sim.host(name)
+        assert np.isfinite(got).all()
+        bad = (got != truth.f[rank][name])
+        assert not bad.any(), f"rank {rank}: {name}: {bad.sum()} values differ (planes {sorted(set(np.argwhere(bad)[:, 2].tolist()))})"
+    # gather!(A_inn, A_v): interior of the global field on rank 0
+    for name in ("Pr", "Vz", "C"):
+        g = gather_interior(sim, name)
+        if rank == 0:
+            want = truth.assemble(name)[1:-1, 1:-1, 1:-1]
+            assert g.shape == want.shape and np.array_equal(g, want), name
+    if rank == 0:
+        print(f"MULTI_GPU_OK world={world} level1={level1} iters={sim.iters} launches={ctx.launch_count}")
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

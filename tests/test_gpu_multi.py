@@ -1,0 +1,37 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): torchrun, one rank per GPU."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:  # noqa: BLE001
+        return 0
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world,grid,nt,lz,level", [(2, (40, 24, 13), 4, None, "fused"), (2, (40, 24, 13), 2, None, "level1"),
+                                                     (4, (40, 24, 10), 3, 34 / 40, "fused"), (8, (40, 24, 6), 3, 34 / 40, "fused")])
+def test_slabs_match_igg_emulation(world, grid, nt, lz, level):
+    if gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
+           os.path.join(ROOT, "tests", "multi_gpu_worker.py"), *map(str, grid), str(nt), repr(lz), level]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert f"MULTI_GPU_OK world={world}" in res.stdout
