@@ -203,6 +203,11 @@ def main():
     if variant == "G":
         s = ns.setup_gpu(nx, ny=ny, nz=nz, **kw)
     else:
+        # weak scaling: the domain grows in z with the number of slabs so
+        # that dz stays equal to dx and every GPU does the same work; the cylinder is z-invariant.
+        probe = ns.setup_multi_gpu(nx, ny=ny, nz=nz, rank=rank, nranks=world, **kw)
+        if world > 1 or (ny is not None):
+            kw = dict(kw, ly=probe.ny * probe.dx, lz=probe.grid.nz_g * probe.dx)
         s = ns.setup_multi_gpu(nx, ny=ny, nz=nz, rank=rank, nranks=world, **kw)
     ctx = ns.Context(local, getattr(ns, args.mode))
     attach_communicator(ctx, rank, world)

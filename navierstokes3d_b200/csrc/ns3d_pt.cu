@@ -38,6 +38,9 @@ struct PtK {
     int hyd_nz;
     int zlo_halo, zhi_halo;   // z faces that are slab interfaces: left to the halo exchange
     int zchunk;
+    // planes this launch updates: [kbeg, kend) in chunks of zchunk, or -- when `faces` is set --
+    // only the two outermost interior planes 1 and nz-2 (the ones a slab sends to its neighbours)
+    int kbeg, kend, faces;
 };
 
 // a / b with y = RN(1/b): one multiply + two FMAs (Markstein's correction step).
@@ -119,8 +122,8 @@ __global__ void __launch_bounds__(256, MINB) pt_iter_kernel(const double* __rest
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
     if (i > nx - 2 || j > ny - 2) return;
-    const int kb = 1 + blockIdx.z * p.zchunk;
-    const int ke = min(kb + p.zchunk, nz - 1);  // interior planes [kb, ke)
+    const int kb = p.faces ? (blockIdx.z == 0 ? 1 : nz - 2) : p.kbeg + blockIdx.z * p.zchunk;
+    const int ke = p.faces ? kb + 1 : min(kb + p.zchunk, p.kend);  // interior planes [kb, ke)
     const ptrdiff_t sxy = (ptrdiff_t)nx * ny;
     const ptrdiff_t dxy = (ptrdiff_t)(nx - 2) * (ny - 2);
     const bool xl = (i == 1), xh = (i == nx - 2), yl = (j == 1), yh = (j == ny - 2);
@@ -185,8 +188,8 @@ __global__ void __launch_bounds__(256) pt_residual_kernel(const double* __restri
     const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
     unsigned long long m = 0ULL;
     if (i <= nx - 2 && j <= ny - 2) {
-        const int kb = 1 + blockIdx.z * p.zchunk;
-        const int ke = min(kb + p.zchunk, nz - 1);
+        const int kb = p.kbeg + blockIdx.z * p.zchunk;
+        const int ke = min(kb + p.zchunk, p.kend);
         const size_t sxy = (size_t)nx * ny;
         const double* c = Pr + idx3(i, j, kb, nx, ny);
         const double* dv = divV + idx3(i, j, kb, nx, ny);
@@ -243,6 +246,9 @@ int make_ptk(ns3d_ctx* ctx, const ns3d_pt_params* p, PtK* k)
         while (zc > 4 && xy * cdiv(p->nz - 2, zc) < 2LL * 8 * ctx->num_sms) zc /= 2;  // measured: profiles/r01_*sweep*
     }
     k->zchunk = zc;
+    k->kbeg = 1;
+    k->kend = p->nz - 1;
+    k->faces = 0;
     return NS3D_OK;
 }
 
@@ -265,11 +271,16 @@ int ensure_shadow(ns3d_ctx* ctx, size_t count)
 }
 
 inline dim3 pt_block() { return dim3(32, 8, 1); }
-inline dim3 pt_grid(const PtK& k) { return dim3(cdiv(k.nx - 2, 32), cdiv(k.ny - 2, 8), cdiv(k.nz - 2, k.zchunk)); }
-
-int launch_iter(ns3d_ctx* ctx, const PtK& k, const double* cur, double* nxt, double* dP, const double* divV)
+inline dim3 pt_grid(const PtK& k)
 {
-#define PT_LAUNCH(MODE, MINB) pt_iter_kernel<MODE, MINB><<<pt_grid(k), pt_block(), 0, ctx->stream>>>(cur, nxt, dP, divV, k)
+    const unsigned gz = k.faces ? (k.nz > 3 ? 2u : 1u) : cdiv(k.kend - k.kbeg, k.zchunk);
+    return dim3(cdiv(k.nx - 2, 32), cdiv(k.ny - 2, 8), gz);
+}
+
+int launch_iter(ns3d_ctx* ctx, cudaStream_t st, const PtK& k, const double* cur, double* nxt, double* dP,
+                const double* divV)
+{
+#define PT_LAUNCH(MODE, MINB) pt_iter_kernel<MODE, MINB><<<pt_grid(k), pt_block(), 0, st>>>(cur, nxt, dP, divV, k)
 #define PT_LAUNCH_MODE(MINB)                                  \
     switch (ctx->mode) {                                      \
         case NS3D_PARITY: PT_LAUNCH(NS3D_PARITY, MINB); break; \
@@ -305,13 +316,45 @@ int launch_residual(ns3d_ctx* ctx, const PtK& k, const double* cur, const double
     return NS3D_OK;
 }
 
-// update_halo!(Pr) for the freshly written iterate (replaces M:462 and M:182; the third call,
-// update_halo!(∇V) M:460, is redundant: ∇V does not change inside the loop).
-int halo_pr(ns3d_ctx* ctx, const PtK& k, double* a)
+// One PT iteration cur -> nxt including update_halo!(Pr) (replaces M:462 and M:182; the third
+// call, update_halo!(∇V) M:460, is redundant: ∇V does not change inside the loop).
+//
+// Single rank: one launch.  z-slabs: the two planes a slab sends (1 and nz-2) are updated by a
+// small launch on the high-priority communication stream, followed there by their exchange,
+// while the remaining planes are updated on the main stream; the main stream joins before
+// anything reads the new halos.  Event protocol (ev_a = "main stream finished reading the
+// iterate that is about to be overwritten", ev_b = "faces + halos of the new iterate are in
+// place"):
+//     comm:  wait ev_a(n-1)  faces(n)  exchange(n)  record ev_b(n)
+//     main:  interior(n)     record ev_a(n)         wait ev_b(n)
+// The reference does the same work with three blocking update_halo! calls per iteration and
+// no overlap.
+int pt_begin(ns3d_ctx* ctx)
 {
-    if (ctx->nranks == 1) return NS3D_OK;
-    double* f[1] = {a};
-    return ns3d_internal_halo_z(ctx, ctx->stream, f, &k.nx, &k.ny, &k.nz, 1, k.nz);
+    if (ctx->nranks > 1) NS3D_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    return NS3D_OK;
+}
+
+int pt_iteration(ns3d_ctx* ctx, const PtK& k, const double* cur, double* nxt, double* dP, const double* divV)
+{
+    if (ctx->nranks == 1) return launch_iter(ctx, ctx->stream, k, cur, nxt, dP, divV);
+    double* f[1] = {nxt};
+    if (k.nz < 6) {  // too thin to split: update, then exchange, on one stream
+        NS3D_TRY(launch_iter(ctx, ctx->stream, k, cur, nxt, dP, divV));
+        return ns3d_internal_halo_z(ctx, ctx->stream, f, &k.nx, &k.ny, &k.nz, 1, k.nz);
+    }
+    PtK faces = k, inner = k;
+    faces.faces = 1;
+    inner.kbeg = 2;
+    inner.kend = k.nz - 2;
+    NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_a, 0));
+    NS3D_TRY(launch_iter(ctx, ctx->comm_stream, faces, cur, nxt, dP, divV));
+    NS3D_TRY(ns3d_internal_halo_z(ctx, ctx->comm_stream, f, &k.nx, &k.ny, &k.nz, 1, k.nz));
+    NS3D_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->comm_stream));
+    NS3D_TRY(launch_iter(ctx, ctx->stream, inner, cur, nxt, dP, divV));
+    NS3D_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
+    return NS3D_OK;
 }
 
 }  // namespace
@@ -331,9 +374,9 @@ extern "C" int ns3d_pt_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const d
     double* cur = Pr;
     double* nxt = ctx->pr_shadow;
     int iters = 0, nc = 0;
+    NS3D_TRY(pt_begin(ctx));
     for (int iter = 1; iter <= p->niter; ++iter) {
-        NS3D_TRY(launch_iter(ctx, k, cur, nxt, dPrdtau, divV));
-        NS3D_TRY(halo_pr(ctx, k, nxt));
+        NS3D_TRY(pt_iteration(ctx, k, cur, nxt, dPrdtau, divV));
         double* t = cur; cur = nxt; nxt = t;
         iters = iter;
         if (iter % p->nchk == 0) {
@@ -365,9 +408,9 @@ extern "C" int ns3d_pt_iterate(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const
     NS3D_TRY(ensure_shadow(ctx, n));
     double* cur = Pr;
     double* nxt = ctx->pr_shadow;
+    NS3D_TRY(pt_begin(ctx));
     for (int iter = 0; iter < n_iter; ++iter) {
-        NS3D_TRY(launch_iter(ctx, k, cur, nxt, dPrdtau, divV));
-        NS3D_TRY(halo_pr(ctx, k, nxt));
+        NS3D_TRY(pt_iteration(ctx, k, cur, nxt, dPrdtau, divV));
         double* t = cur; cur = nxt; nxt = t;
     }
     if (cur != Pr) NS3D_CUDA(ctx, cudaMemcpyAsync(Pr, cur, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
