@@ -164,7 +164,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
-    ap.add_argument("--mode", default="FAST", choices=["PARITY", "FAST", "FASTEST"])
+    ap.add_argument("--mode", default="FASTEST", choices=["PARITY", "FAST", "FASTEST"])
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--zchunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -239,6 +240,7 @@ def main():
     launches = ctx.launch_count - l0
     dev_s = ev0.elapsed_time(ev1) / 1e3
     bytes_rank = sum(a_eff_bytes(n_cells, i, c) for i, c in zip(iters, checks))
+    final = {k: sim.host(k) for k in ("Pr", "Vx", "Vy", "Vz", "C")} if not args.no_parity_check else None
 
     # ---- the dominant kernel, live: nchk fused PT iterations between events ----------------------
     n_probe = max(s.nchk, 50)
@@ -285,6 +287,23 @@ def main():
         e_bytes = sum(a_eff_bytes(n_cells, i, c) for i, c in zip(e_iters, e_checks))
         e2e = [e_bytes, e_dev, h2d_b, d2h_b, e_iters]
 
+    # ---- parity of the timed steps: the same K steps again in PARITY mode (bit-equal to the CPU
+    # oracle, tests/test_gpu_solver.py): iteration counts must be identical, fields within 1e-10 ----
+    parity = None
+    if final is not None:
+        for k, v in snapshot.items():
+            sim.f[k].set(v)
+        ctx.set_mode(ns.PARITY)
+        p_iters = [sim.step()[0] for _ in range(args.steps)]
+        ctx.set_mode(getattr(ns, args.mode))
+        ref = {k: sim.host(k) for k in final}
+        vscale = max(float(np.abs(ref[v]).max()) for v in ("Vx", "Vy", "Vz"))
+        diffs = {k: float(np.abs(final[k] - ref[k]).max() / (vscale if k[0] == "V" else max(float(np.abs(ref[k]).max()), 1e-300)))
+                 for k in final}
+        parity = {"against": "the same steps in PARITY mode (IEEE division, no FMA; bit-equal to the CPU oracle in tests/)",
+                  "pt_iters_identical": p_iters == iters, "max_rel_diff": diffs, "tolerance": 1e-10,
+                  "within_tolerance": max(diffs.values()) <= 1e-10}
+
     # ---- reduce over ranks: max time, summed bytes ----------------------------------------------
     t_rank = max(dev_s, wall)
     if world > 1:
@@ -323,6 +342,8 @@ def main():
                          "algorithmic_bytes_per_launch": 40.0 * n_cells,
                          "share_of_step": (sum(iters) / args.steps) * t_launch / (t_all / args.steps)},
         }
+        if parity:
+            line["parity_check"] = parity
         if e2e:
             line["e2e"] = {"value": e_bytes_all / e_t / 1e9, "unit": "GB/s", "h2d_bytes_per_step": e2e[2],
                            "d2h_bytes_per_step": e2e[3], "ms_per_step": e_t / args.steps * 1e3,

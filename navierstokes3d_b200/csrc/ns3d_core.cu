@@ -58,6 +58,9 @@ extern "C" int ns3d_create(int device, ns3d_ctx** out)
     } while (0)
     CREATE_CUDA(cudaSetDevice(device));
     CREATE_CUDA(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device));
+    int l2 = 0;
+    CREATE_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, device));
+    ctx->l2_bytes = (size_t)l2;
     int lo = 0, hi = 0;
     CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CREATE_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, lo));
@@ -155,6 +158,10 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "pt_minb")) {
         if (value != 0 && (value < 3 || value > 6)) return ns3d_fail(ctx, NS3D_EINVAL, "pt_minb must be 0 (auto) or 3..6");
         ctx->opt_pt_minb = value;
+        return NS3D_OK;
+    }
+    if (!strcmp(name, "serpentine")) {
+        ctx->opt_serpentine = value < 0 ? -1 : (value != 0);
         return NS3D_OK;
     }
     return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_set_option: unknown option '%s'", name);

@@ -33,6 +33,8 @@ struct ns3d_ctx {
     int rank = 0, nranks = 1;
     // tuning knobs (ns3d_set_option)
     int opt_pt_minb = 0;  // 0 = per-mode default
+    int opt_serpentine = -1;  // -1 = by working-set size
+    size_t l2_bytes = 0;
 };
 
 int ns3d_fail(ns3d_ctx* ctx, int code, const char* fmt, ...);

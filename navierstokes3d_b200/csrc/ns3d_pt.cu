@@ -41,6 +41,10 @@ struct PtK {
     // planes this launch updates: [kbeg, kend) in chunks of zchunk, or -- when `faces` is set --
     // only the two outermost interior planes 1 and nz-2 (the ones a slab sends to its neighbours)
     int kbeg, kend, faces;
+    // serpentine sweep: odd iterations walk the z-chunks downwards, so an iteration starts on the
+    // planes the previous one touched last and finds them in the 126 MB L2
+    int reverse;
+    int serpentine;  // host-side policy flag (not read by the kernel)
 };
 
 // a / b with y = RN(1/b): one multiply + two FMAs (Markstein's correction step).
@@ -122,7 +126,8 @@ __global__ void __launch_bounds__(256, MINB) pt_iter_kernel(const double* __rest
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
     if (i > nx - 2 || j > ny - 2) return;
-    const int kb = p.faces ? (blockIdx.z == 0 ? 1 : nz - 2) : p.kbeg + blockIdx.z * p.zchunk;
+    const int bz = p.reverse ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
+    const int kb = p.faces ? (bz == 0 ? 1 : nz - 2) : p.kbeg + bz * p.zchunk;
     const int ke = p.faces ? kb + 1 : min(kb + p.zchunk, p.kend);  // interior planes [kb, ke)
     const ptrdiff_t sxy = (ptrdiff_t)nx * ny;
     const ptrdiff_t dxy = (ptrdiff_t)(nx - 2) * (ny - 2);
@@ -249,6 +254,11 @@ int make_ptk(ns3d_ctx* ctx, const ns3d_pt_params* p, PtK* k)
     k->kbeg = 1;
     k->kend = p->nz - 1;
     k->faces = 0;
+    k->reverse = 0;
+    // serpentine pays while a good part of the 4-field working set can stay in L2 (measured:
+    // +5..8 % at 255x153x153, neutral to -1 % at 511^3; profiles/r01_v4_sweep_serpentine.jsonl)
+    k->serpentine = ctx->opt_serpentine < 0 ? (4.0 * 8.0 * p->nx * p->ny * p->nz < 6.0 * ctx->l2_bytes)
+                                            : ctx->opt_serpentine;
     return NS3D_OK;
 }
 
@@ -376,6 +386,7 @@ extern "C" int ns3d_pt_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const d
     int iters = 0, nc = 0;
     NS3D_TRY(pt_begin(ctx));
     for (int iter = 1; iter <= p->niter; ++iter) {
+        k.reverse = k.serpentine && (iter & 1) == 0;
         NS3D_TRY(pt_iteration(ctx, k, cur, nxt, dPrdtau, divV));
         double* t = cur; cur = nxt; nxt = t;
         iters = iter;
@@ -410,6 +421,7 @@ extern "C" int ns3d_pt_iterate(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const
     double* nxt = ctx->pr_shadow;
     NS3D_TRY(pt_begin(ctx));
     for (int iter = 0; iter < n_iter; ++iter) {
+        k.reverse = k.serpentine && (iter & 1);
         NS3D_TRY(pt_iteration(ctx, k, cur, nxt, dPrdtau, divV));
         double* t = cur; cur = nxt; nxt = t;
     }

@@ -11,7 +11,8 @@ ap.add_argument("--modes", default="PARITY,FAST,FASTEST")
 ap.add_argument("--zchunks", default="0,2,4,8,16,32")
 ap.add_argument("--iters", type=int, default=200)
 ap.add_argument("--variant", default="G")
-ap.add_argument("--minb", default="4")
+ap.add_argument("--minb", default="0")
+ap.add_argument("--serp", default="1")
 args = ap.parse_args()
 rng = np.random.default_rng(0)
 for g in args.grids.split(","):
@@ -24,8 +25,9 @@ for g in args.grids.split(","):
         Pr = ctx.from_host(np.asfortranarray(rng.uniform(-1, 1, size=(nx, ny, nz))))
         dP = ctx.zeros(nx - 2, ny - 2, nz - 2)
         dv = ctx.from_host(np.asfortranarray(rng.uniform(-1e-3, 1e-3, size=(nx, ny, nz))))
-        for zc, minb in [(z, m) for m in map(int, args.minb.split(",")) for z in map(int, args.zchunks.split(","))]:
+        for zc, minb, serp in [(z, m, sp) for sp in map(int, args.serp.split(",")) for m in map(int, args.minb.split(",")) for z in map(int, args.zchunks.split(","))]:
             ctx.set_option("pt_minb", minb)
+            ctx.set_option("serpentine", serp)
             pt = s.pt_params(zc)
             ctx.pt_iterate(Pr, dP, dv, pt, 20)
             ctx.sync()
@@ -37,6 +39,6 @@ for g in args.grids.split(","):
                 e1.record(stream)
                 ctx.sync()
                 best = min(best, e0.elapsed_time(e1) / args.iters * 1e3)
-            print(json.dumps({"grid": g, "mode": mode, "zchunk": zc, "minb": minb, "us_per_iter": round(best, 2),
+            print(json.dumps({"grid": g, "mode": mode, "zchunk": zc, "minb": minb, "serp": serp, "us_per_iter": round(best, 2),
                               "T_eff_GBs": round(40.0 * n / best / 1e3, 1)}), flush=True)
         ctx.close()
