@@ -130,6 +130,7 @@ extern "C" int ns3d_destroy(ns3d_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->comm_stream);
+    ns3d_internal_pt_free_graphs(ctx);
     if (ctx->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl);
     for (auto& kv : ctx->allocs) cudaFree(kv.first);
     if (ctx->pr_shadow) cudaFree(ctx->pr_shadow);
@@ -158,6 +159,10 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "pt_minb")) {
         if (value != 0 && (value < 3 || value > 6)) return ns3d_fail(ctx, NS3D_EINVAL, "pt_minb must be 0 (auto) or 3..6");
         ctx->opt_pt_minb = value;
+        return NS3D_OK;
+    }
+    if (!strcmp(name, "graphs")) {
+        ctx->opt_graphs = value != 0;
         return NS3D_OK;
     }
     if (!strcmp(name, "serpentine")) {
@@ -358,6 +363,9 @@ int ns3d_internal_halo_z(ns3d_ctx* ctx, cudaStream_t s, double* const* fields, c
     if (!ctx->nccl) return ns3d_fail(ctx, NS3D_ECOMM, "update_halo: no communicator attached");
     ncclComm_t comm = (ncclComm_t)ctx->nccl;
     const int lo = ctx->rank - 1, hi = ctx->rank + 1;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &cap);
+    if (cap == cudaStreamCaptureStatusNone) ctx->halo_calls++;
     NS3D_NCCL(ctx, g_nccl.GroupStart());
     for (int f = 0; f < nfields; ++f) {
         const int ol = 2 + (sz[f] - nz);

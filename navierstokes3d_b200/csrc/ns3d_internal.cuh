@@ -34,6 +34,9 @@ struct ns3d_ctx {
     // tuning knobs (ns3d_set_option)
     int opt_pt_minb = 0;  // 0 = per-mode default
     int opt_serpentine = -1;  // -1 = by working-set size
+    int opt_graphs = 1;       // replay chunks of PT iterations as CUDA graphs
+    long long halo_calls = 0; // uncaptured halo exchanges so far (NCCL peers connected)
+    void* pt_graphs = nullptr;  // graph cache owned by ns3d_pt.cu
     size_t l2_bytes = 0;
 };
 
@@ -110,6 +113,7 @@ __device__ __forceinline__ void block_max_to_global(unsigned long long v, unsign
 }
 
 // internal cross-TU entry points
+void ns3d_internal_pt_free_graphs(ns3d_ctx* ctx);
 int ns3d_internal_max_abs_async(ns3d_ctx* ctx, const double* A, size_t count);  // result -> ctx->d_maxbits
 int ns3d_internal_read_max(ns3d_ctx* ctx, double* h_out);                       // sync + allreduce
 int ns3d_internal_halo_z(ns3d_ctx* ctx, cudaStream_t s, double* const* fields, const int* sx,
