@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="FASTEST", choices=["PARITY", "FAST", "FASTEST"])
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library tuning option name=value (ns3d_set_option)")
     ap.add_argument("--zchunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -212,6 +213,9 @@ def main():
         s = ns.setup_multi_gpu(nx, ny=ny, nz=nz, rank=rank, nranks=world, **kw)
     ctx = ns.Context(local, getattr(ns, args.mode))
     attach_communicator(ctx, rank, world)
+    for o in args.opt:
+        name, val = o.split("=")
+        ctx.set_option(name, int(val))
     sim = ns.Simulation(s, ctx, zchunk=args.zchunk)
     n_cells = s.nx * s.ny * s.nz
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)

@@ -131,6 +131,13 @@ extern "C" int ns3d_destroy(ns3d_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->comm_stream);
     ns3d_internal_pt_free_graphs(ctx);
+    for (auto& kv : ctx->p2p_map) {
+        if (kv.second.first) cudaIpcCloseMemHandle(kv.second.first);
+        if (kv.second.second) cudaIpcCloseMemHandle(kv.second.second);
+    }
+    for (int q = 0; q < 2; ++q)
+        if (ctx->peer_mbox[q]) cudaIpcCloseMemHandle(ctx->peer_mbox[q]);
+    if (ctx->mbox) cudaFree(ctx->mbox);
     if (ctx->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl);
     for (auto& kv : ctx->allocs) cudaFree(kv.first);
     if (ctx->pr_shadow) cudaFree(ctx->pr_shadow);
@@ -159,6 +166,10 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "pt_minb")) {
         if (value != 0 && (value < 3 || value > 6)) return ns3d_fail(ctx, NS3D_EINVAL, "pt_minb must be 0 (auto) or 3..6");
         ctx->opt_pt_minb = value;
+        return NS3D_OK;
+    }
+    if (!strcmp(name, "p2p_halo")) {
+        ctx->opt_p2p = value != 0;
         return NS3D_OK;
     }
     if (!strcmp(name, "graphs")) {
@@ -346,6 +357,76 @@ extern "C" int ns3d_comm_init(ns3d_ctx* ctx, int rank, int nranks, const char id
     ncclComm_t comm;
     NS3D_NCCL(ctx, g_nccl.CommInitRank(&comm, nranks, uid, rank));
     ctx->nccl = comm;
+    // Peer-memory halo path: every rank owns a mailbox and maps its neighbours' through CUDA IPC.
+    // If IPC is not available the NCCL send/recv path stays in charge (p2p_ready == false).
+    NS3D_CUDA(ctx, cudaMalloc(&ctx->mbox, NS3D_MB_WORDS * sizeof(unsigned long long)));
+    NS3D_CUDA(ctx, cudaMemset(ctx->mbox, 0, NS3D_MB_WORDS * sizeof(unsigned long long)));
+    void *lo = nullptr, *hi = nullptr;
+    const int rc = ns3d_internal_p2p_map(ctx, ctx->mbox, &lo, &hi);
+    ctx->p2p_map.erase(ctx->mbox);
+    ctx->peer_mbox[0] = (unsigned long long*)lo;
+    ctx->peer_mbox[1] = (unsigned long long*)hi;
+    // all ranks must agree on the path: min-reduce the local outcome
+    ctx->h_maxbits[2] = rc == NS3D_OK ? 1ULL : 0ULL;
+    NS3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_maxbits + 2, ctx->h_maxbits + 2, 8, cudaMemcpyHostToDevice, ctx->stream));
+    NS3D_NCCL(ctx, g_nccl.AllReduce(ctx->d_maxbits + 2, ctx->d_maxbits + 2, 1, ncclUint64, ncclMin, comm, ctx->stream));
+    NS3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_maxbits + 2, ctx->d_maxbits + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->p2p_ready = ctx->h_maxbits[2] == 1ULL;
+    ctx->err.clear();
+    return NS3D_OK;
+}
+
+// Exchanges the CUDA IPC handle of `local_base` (the base of a cudaMalloc block) with both slab
+// neighbours and maps theirs.  COLLECTIVE: every rank must call it at the same point with its
+// corresponding buffer.  Cached per local pointer.
+int ns3d_internal_p2p_map(ns3d_ctx* ctx, const void* local_base, void** peer_lo, void** peer_hi)
+{
+    auto it = ctx->p2p_map.find(local_base);
+    if (it != ctx->p2p_map.end()) {
+        *peer_lo = it->second.first;
+        *peer_hi = it->second.second;
+        return NS3D_OK;
+    }
+    *peer_lo = *peer_hi = nullptr;
+    if (!ctx->nccl) return ns3d_fail(ctx, NS3D_ECOMM, "p2p_map: no communicator");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    cudaIpcMemHandle_t mine;
+    NS3D_CUDA(ctx, cudaIpcGetMemHandle(&mine, const_cast<void*>(local_base)));
+    unsigned char* stage = nullptr;  // [0,64) mine, [64,128) from lower, [128,192) from upper
+    NS3D_CUDA(ctx, cudaMalloc(&stage, 192));
+    NS3D_CUDA(ctx, cudaMemcpyAsync(stage, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+    ncclComm_t comm = (ncclComm_t)ctx->nccl;
+    const int lo = ctx->rank - 1, hi = ctx->rank + 1;
+    NS3D_NCCL(ctx, g_nccl.GroupStart());
+    if (lo >= 0) {
+        NS3D_NCCL(ctx, g_nccl.Send(stage, 64, ncclUint8, lo, comm, ctx->stream));
+        NS3D_NCCL(ctx, g_nccl.Recv(stage + 64, 64, ncclUint8, lo, comm, ctx->stream));
+    }
+    if (hi < ctx->nranks) {
+        NS3D_NCCL(ctx, g_nccl.Send(stage, 64, ncclUint8, hi, comm, ctx->stream));
+        NS3D_NCCL(ctx, g_nccl.Recv(stage + 128, 64, ncclUint8, hi, comm, ctx->stream));
+    }
+    NS3D_NCCL(ctx, g_nccl.GroupEnd());
+    cudaIpcMemHandle_t theirs[2];
+    NS3D_CUDA(ctx, cudaMemcpyAsync(theirs, stage + 64, 128, cudaMemcpyDeviceToHost, ctx->stream));
+    NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(stage);
+    ctx->halo_calls++;
+    void* mapped[2] = {nullptr, nullptr};
+    for (int q = 0; q < 2; ++q) {
+        const int nb = q == 0 ? lo : hi;
+        if (nb < 0 || nb >= ctx->nranks) continue;
+        cudaError_t e = cudaIpcOpenMemHandle(&mapped[q], theirs[q], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return ns3d_fail(ctx, NS3D_ECOMM, "cudaIpcOpenMemHandle (rank %d -> %d) failed: %s", ctx->rank, nb,
+                             cudaGetErrorString(e));
+        }
+    }
+    ctx->p2p_map[local_base] = {mapped[0], mapped[1]};
+    *peer_lo = mapped[0];
+    *peer_hi = mapped[1];
     return NS3D_OK;
 }
 

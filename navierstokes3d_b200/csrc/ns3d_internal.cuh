@@ -31,6 +31,13 @@ struct ns3d_ctx {
     // communicator (z-slabs, one rank per GPU)
     void* nccl = nullptr;
     int rank = 0, nranks = 1;
+    // peer-memory halo path: a mailbox of 64-bit words in device memory (see NS3D_MB_*), the
+    // neighbours' mailboxes and field buffers mapped through CUDA IPC
+    unsigned long long* mbox = nullptr;
+    unsigned long long* peer_mbox[2] = {nullptr, nullptr};  // [0] lower, [1] upper neighbour
+    bool p2p_ready = false;
+    std::unordered_map<const void*, std::pair<void*, void*>> p2p_map;  // local base -> (lower, upper) peer base
+    int opt_p2p = 1;
     // tuning knobs (ns3d_set_option)
     int opt_pt_minb = 0;  // 0 = per-mode default
     int opt_serpentine = -1;  // -1 = by working-set size
@@ -112,7 +119,20 @@ __device__ __forceinline__ void block_max_to_global(unsigned long long v, unsign
     }
 }
 
+// mailbox words
+enum {
+    NS3D_MB_FLAG_LO = 0,    // written by the lower neighbour: epochs whose face work it has finished
+    NS3D_MB_FLAG_HI = 1,    // same, upper neighbour
+    NS3D_MB_ARRIVE_LO = 2,  // face CTAs of the running launch that are done (reset by the last one)
+    NS3D_MB_ARRIVE_HI = 3,
+    NS3D_MB_EPOCH_LO = 4,   // launches whose lower-face work is complete on this rank
+    NS3D_MB_EPOCH_HI = 5,
+    NS3D_MB_ERROR = 6,      // set when a spin-wait timed out
+    NS3D_MB_WORDS = 16
+};
+
 // internal cross-TU entry points
+int ns3d_internal_p2p_map(ns3d_ctx* ctx, const void* local_base, void** peer_lo, void** peer_hi);
 void ns3d_internal_pt_free_graphs(ns3d_ctx* ctx);
 int ns3d_internal_max_abs_async(ns3d_ctx* ctx, const double* A, size_t count);  // result -> ctx->d_maxbits
 int ns3d_internal_read_max(ns3d_ctx* ctx, double* h_out);                       // sync + allreduce

@@ -46,6 +46,13 @@ struct PtK {
     // planes the previous one touched last and finds them in the 126 MB L2
     int reverse;
     int serpentine;  // host-side policy flag (not read by the kernel)
+    // peer-memory halo exchange (pt_iter_kernel<.,.,true>): where the planes this slab sends go
+    // in the neighbours' new iterate, the mailboxes, and the number of CTAs per face
+    double* peer_lo_plane;             // lower neighbour's halo plane nz-1 of its Pr'
+    double* peer_hi_plane;             // upper neighbour's halo plane 0 of its Pr'
+    unsigned long long* mbox;          // this rank's mailbox (NS3D_MB_*)
+    unsigned long long* peer_lo_flag;  // lower neighbour's NS3D_MB_FLAG_HI
+    unsigned long long* peer_hi_flag;  // upper neighbour's NS3D_MB_FLAG_LO
 };
 
 // a / b with y = RN(1/b): one multiply + two FMAs (Markstein's correction step).
@@ -118,7 +125,70 @@ struct StreamRegs {
     double zp, dq, dv;
 };
 
-template <int MODE, int MINB>
+// ---- peer-memory halo protocol (device side) --------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long atom_add_acq_rel_gpu(unsigned long long* p, unsigned long long v)
+{
+    unsigned long long old;
+    asm volatile("atom.add.acq_rel.gpu.global.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+    return old;
+}
+
+// Spins until the neighbour on `side` (0 lower, 1 upper) has finished the face work of every
+// launch this rank has finished: then its stores into our halo plane have landed and it no
+// longer reads the halo plane of its own that we are about to overwrite.  Bounded: a
+// neighbour that never answers raises NS3D_MB_ERROR instead of hanging the GPU.
+__device__ __forceinline__ void wait_neighbour(unsigned long long* mbox, int side)
+{
+    const unsigned long long need = ld_acquire_sys(mbox + NS3D_MB_EPOCH_LO + side);
+    const long long t0 = clock64();
+    while (ld_acquire_sys(mbox + NS3D_MB_FLAG_LO + side) < need) {
+        if (clock64() - t0 > 8000000000LL) {  // ~4 s
+            mbox[NS3D_MB_ERROR] = 1ULL + side;
+            break;
+        }
+    }
+}
+
+// Last face CTA of this launch on `side`: close the epoch and tell the neighbour.
+__device__ __forceinline__ void signal_neighbour(unsigned long long* mbox, int side, unsigned long long* peer_flag,
+                                                 unsigned nface)
+{
+    const unsigned long long old = atom_add_acq_rel_gpu(mbox + NS3D_MB_ARRIVE_LO + side, 1ULL);
+    if (old + 1 == nface) {
+        mbox[NS3D_MB_ARRIVE_LO + side] = 0ULL;
+        const unsigned long long e = mbox[NS3D_MB_EPOCH_LO + side] + 1ULL;
+        mbox[NS3D_MB_EPOCH_LO + side] = e;
+        __threadfence_system();
+        st_release_sys(peer_flag, e);
+    }
+}
+
+// After a chunk of launches: the halo planes of the current iterate are complete once both
+// neighbours have signalled the epoch this rank has reached.
+__global__ void pt_halo_wait_kernel(unsigned long long* mbox, int has_lo, int has_hi)
+{
+    if (threadIdx.x == 0) {
+        if (has_lo) wait_neighbour(mbox, 0);
+        if (has_hi) wait_neighbour(mbox, 1);
+    }
+}
+
+// P2P = true: the CTAs that update plane 1 / nz-2 of a slab also store the new values -- with
+// their x/y mirror images -- straight into the neighbour's halo plane over NVLink (mapped peer
+// memory) and the last of them releases a flag in the neighbour's mailbox; the same CTAs of the
+// next launch acquire the neighbour's flag before touching the halos.  One kernel does the
+// update and the halo exchange; there is no separate communication step to overlap.
+template <int MODE, int MINB, bool P2P>
 __global__ void __launch_bounds__(256, MINB) pt_iter_kernel(const double* __restrict__ Pr, double* __restrict__ PrN,
                                                       double* __restrict__ dP, const double* __restrict__ divV,
                                                       const PtK p)
@@ -126,10 +196,28 @@ __global__ void __launch_bounds__(256, MINB) pt_iter_kernel(const double* __rest
     const int nx = p.nx, ny = p.ny, nz = p.nz;
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
     const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
-    if (i > nx - 2 || j > ny - 2) return;
-    const int bz = p.reverse ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
+    const bool active = (i <= nx - 2) && (j <= ny - 2);
+    if (!P2P && !active) return;
+    int bz = blockIdx.z;
+    if (P2P) {  // the two face chunks go first (lowest CTA indices are scheduled first), then the rest
+        const int nc = gridDim.z;
+        if (bz == 1) bz = nc - 1;
+        else if (bz >= 2) bz = p.reverse ? nc - bz : bz - 1;
+    } else if (p.reverse) {
+        bz = gridDim.z - 1 - bz;
+    }
     const int kb = p.faces ? (bz == 0 ? 1 : nz - 2) : p.kbeg + bz * p.zchunk;
     const int ke = p.faces ? kb + 1 : min(kb + p.zchunk, p.kend);  // interior planes [kb, ke)
+    const bool lo_face = P2P && p.zlo_halo && kb == 1;
+    const bool hi_face = P2P && p.zhi_halo && ke == nz - 1;
+    if (P2P && (lo_face | hi_face)) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            if (lo_face) wait_neighbour(p.mbox, 0);
+            if (hi_face) wait_neighbour(p.mbox, 1);
+        }
+        __syncthreads();
+    }
+    if (active) {
     const ptrdiff_t sxy = (ptrdiff_t)nx * ny;
     const ptrdiff_t dxy = (ptrdiff_t)(nx - 2) * (ny - 2);
     const bool xl = (i == 1), xh = (i == nx - 2), yl = (j == 1), yh = (j == ny - 2);
@@ -162,9 +250,14 @@ __global__ void __launch_bounds__(256, MINB) pt_iter_kernel(const double* __rest
             if (yl) store_row(p, plane, i, k, u, xl, xh);
             if (yh) store_row(p, plane + (ptrdiff_t)(ny - 1) * nx, i, k, u, xl, xh);
         }
-        if (k == 1 && !p.zlo_halo) store_plane(p, PrN, i, j, 0, u, xl, xh, yl, yh);  // bc_z! M:129
-        if (k == nz - 2 && !p.zhi_halo)
-            store_plane(p, PrN + (ptrdiff_t)(nz - 1) * sxy, i, j, nz - 1, u, xl, xh, yl, yh);  // bc_z! M:130
+        if (k == 1) {
+            if (!p.zlo_halo) store_plane(p, PrN, i, j, 0, u, xl, xh, yl, yh);  // bc_z! M:129
+            else if (P2P) store_plane(p, p.peer_lo_plane, i, j, k, u, xl, xh, yl, yh);  // update_halo!(Pr)
+        }
+        if (k == nz - 2) {
+            if (!p.zhi_halo) store_plane(p, PrN + (ptrdiff_t)(nz - 1) * sxy, i, j, nz - 1, u, xl, xh, yl, yh);  // M:130
+            else if (P2P) store_plane(p, p.peer_hi_plane, i, j, k, u, xl, xh, yl, yh);
+        }
         pm = pc;
         pc = r.zp;
     };
@@ -179,6 +272,16 @@ __global__ void __launch_bounds__(256, MINB) pt_iter_kernel(const double* __rest
         if (has1) compute(B, k + 1, off + sxy, dof + dxy);
         off += 2 * sxy;
         dof += 2 * dxy;
+    }
+    }  // active
+    if (P2P && (lo_face | hi_face)) {
+        __threadfence_system();  // this thread's peer stores are performed before the flag can be seen
+        __syncthreads();
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            const unsigned nface = gridDim.x * gridDim.y;
+            if (lo_face) signal_neighbour(p.mbox, 0, p.peer_lo_flag, nface);
+            if (hi_face) signal_neighbour(p.mbox, 1, p.peer_hi_flag, nface);
+        }
     }
 }
 
@@ -268,6 +371,12 @@ int ensure_shadow(ns3d_ctx* ctx, size_t count)
     if (ctx->pr_shadow_count >= count) return NS3D_OK;
     if (ctx->pr_shadow) {
         NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        auto it = ctx->p2p_map.find(ctx->pr_shadow);  // the neighbours' old shadows are going away too
+        if (it != ctx->p2p_map.end()) {
+            if (it->second.first) cudaIpcCloseMemHandle(it->second.first);
+            if (it->second.second) cudaIpcCloseMemHandle(it->second.second);
+            ctx->p2p_map.erase(it);
+        }
         NS3D_CUDA(ctx, cudaFree(ctx->pr_shadow));
         ctx->pr_shadow = nullptr;
         ctx->pr_shadow_count = 0;
@@ -291,7 +400,11 @@ inline dim3 pt_grid(const PtK& k)
 int launch_iter(ns3d_ctx* ctx, cudaStream_t st, const PtK& k, const double* cur, double* nxt, double* dP,
                 const double* divV)
 {
-#define PT_LAUNCH(MODE, MINB) pt_iter_kernel<MODE, MINB><<<pt_grid(k), pt_block(), 0, st>>>(cur, nxt, dP, divV, k)
+#define PT_LAUNCH(MODE, MINB)                                                                      \
+    do {                                                                                           \
+        if (k.mbox) pt_iter_kernel<MODE, MINB, true><<<pt_grid(k), pt_block(), 0, st>>>(cur, nxt, dP, divV, k);  \
+        else pt_iter_kernel<MODE, MINB, false><<<pt_grid(k), pt_block(), 0, st>>>(cur, nxt, dP, divV, k);        \
+    } while (0)
 #define PT_LAUNCH_MODE(MINB)                                  \
     switch (ctx->mode) {                                      \
         case NS3D_PARITY: PT_LAUNCH(NS3D_PARITY, MINB); break; \
@@ -303,6 +416,7 @@ int launch_iter(ns3d_ctx* ctx, cudaStream_t st, const PtK& k, const double* cur,
     // that does not spill.
     int minb = ctx->opt_pt_minb;
     if (minb == 0) minb = ctx->mode == NS3D_FASTEST ? 5 : (ctx->mode == NS3D_FAST ? 4 : 3);
+    if (k.mbox && minb > 4) minb = 4;  // the peer-store variant spills at 48 registers
     switch (minb) {
         case 3: PT_LAUNCH_MODE(3); break;
         case 5: PT_LAUNCH_MODE(5); break;
@@ -346,9 +460,55 @@ int pt_begin(ns3d_ctx* ctx)
     return NS3D_OK;
 }
 
-int pt_iteration(ns3d_ctx* ctx, const PtK& k, const double* cur, double* nxt, double* dP, const double* divV)
+// Peer-memory path usable for this solve?  Maps the neighbours' copies of both ping-pong buffers
+// on first use (collective: every rank reaches this point with its own Pr / shadow).
+struct PeerBufs {
+    bool on = false;
+    double* lo[2] = {nullptr, nullptr};  // lower neighbour's {Pr, shadow}
+    double* hi[2] = {nullptr, nullptr};  // upper neighbour's {Pr, shadow}
+};
+
+int peer_prepare(ns3d_ctx* ctx, const PtK& k, double* Pr, double* shadow, PeerBufs* pb)
+{
+    pb->on = false;
+    if (ctx->nranks == 1 || !ctx->opt_p2p || !ctx->p2p_ready || k.nz < 6) return NS3D_OK;
+    void *l0, *h0, *l1, *h1;
+    NS3D_TRY(ns3d_internal_p2p_map(ctx, Pr, &l0, &h0));
+    NS3D_TRY(ns3d_internal_p2p_map(ctx, shadow, &l1, &h1));
+    pb->lo[0] = (double*)l0; pb->hi[0] = (double*)h0;
+    pb->lo[1] = (double*)l1; pb->hi[1] = (double*)h1;
+    pb->on = true;
+    return NS3D_OK;
+}
+
+int pt_iteration(ns3d_ctx* ctx, const PtK& k, const double* cur, double* nxt, double* dP, const double* divV,
+                 const PeerBufs& pb, const double* Pr_user)
 {
     if (ctx->nranks == 1) return launch_iter(ctx, ctx->stream, k, cur, nxt, dP, divV);
+    if (pb.on) {
+        // The update of the two planes a slab sends and their delivery are ONE kernel: the face
+        // CTAs store the new values into the neighbour's halo plane (peer memory over NVLink) and
+        // hand over with mailbox flags.  It runs on the high-priority stream next to the launch
+        // that updates the other planes; kernel-only, so whole chunks replay as a CUDA graph.
+        PtK q = k, inner = k;
+        const int which = (nxt == Pr_user) ? 0 : 1;  // all ranks ping-pong in lockstep
+        const ptrdiff_t sxy = (ptrdiff_t)k.nx * k.ny;
+        q.faces = 1;
+        q.mbox = ctx->mbox;
+        q.peer_lo_plane = pb.lo[which] ? pb.lo[which] + (ptrdiff_t)(k.nz - 1) * sxy : nullptr;
+        q.peer_hi_plane = pb.hi[which];
+        q.peer_lo_flag = ctx->peer_mbox[0] ? ctx->peer_mbox[0] + NS3D_MB_FLAG_HI : nullptr;
+        q.peer_hi_flag = ctx->peer_mbox[1] ? ctx->peer_mbox[1] + NS3D_MB_FLAG_LO : nullptr;
+        inner.kbeg = 2;
+        inner.kend = k.nz - 2;
+        NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_a, 0));
+        NS3D_TRY(launch_iter(ctx, ctx->comm_stream, q, cur, nxt, dP, divV));
+        NS3D_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->comm_stream));
+        NS3D_TRY(launch_iter(ctx, ctx->stream, inner, cur, nxt, dP, divV));
+        NS3D_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+        NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
+        return NS3D_OK;
+    }
     double* f[1] = {nxt};
     if (k.nz < 6) {  // too thin to split: update, then exchange, on one stream
         NS3D_TRY(launch_iter(ctx, ctx->stream, k, cur, nxt, dP, divV));
@@ -365,6 +525,15 @@ int pt_iteration(ns3d_ctx* ctx, const PtK& k, const double* cur, double* nxt, do
     NS3D_TRY(launch_iter(ctx, ctx->stream, inner, cur, nxt, dP, divV));
     NS3D_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
     NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
+    return NS3D_OK;
+}
+
+// The halos of the current iterate are complete once both neighbours have caught up.
+int peer_join(ns3d_ctx* ctx, const PtK& k, const PeerBufs& pb)
+{
+    if (!pb.on) return NS3D_OK;
+    pt_halo_wait_kernel<<<1, 32, 0, ctx->stream>>>(ctx->mbox, k.zlo_halo, k.zhi_halo);
+    NS3D_LAUNCH_CHECK(ctx);
     return NS3D_OK;
 }
 
@@ -385,6 +554,7 @@ struct PtGraph {
     double* dP = nullptr;
     const double* divV = nullptr;
     int n = 0, parity = 0, mode = 0, minb = 0;
+    bool p2p = false;
     long long kernels = 0;
 };
 struct PtGraphCache {
@@ -392,25 +562,27 @@ struct PtGraphCache {
     int next = 0;
 };
 
-int run_direct(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double* dP, const double* divV, int n, int iter0)
+int run_direct(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double* dP, const double* divV, int n, int iter0,
+               const PeerBufs& pb, const double* Pr_user)
 {
     NS3D_TRY(pt_begin(ctx));
     for (int q = 0; q < n; ++q) {
         k.reverse = k.serpentine && ((iter0 + q) & 1);
-        NS3D_TRY(pt_iteration(ctx, k, cur, nxt, dP, divV));
+        NS3D_TRY(pt_iteration(ctx, k, cur, nxt, dP, divV, pb, Pr_user));
         double* t = cur; cur = nxt; nxt = t;
     }
-    return NS3D_OK;
+    return peer_join(ctx, k, pb);
 }
 
 // Runs iterations iter0 .. iter0+n-1 (0-based count since the start of the solve).
-int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double* dP, const double* divV, int n, int iter0)
+int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double* dP, const double* divV, int n, int iter0,
+                   const PeerBufs& pb, const double* Pr_user)
 {
     // NCCL send/recv captured in a graph drags host-callback nodes along (proxy progress) and
     // replays slower than the stream version (measured 55.9 vs 44.9 us/iteration on 2 GPUs), so
     // only kernel-only iterations are replayed as graphs.
-    const bool graphable = ctx->opt_graphs && n >= 8 && ctx->nranks == 1;
-    if (!graphable) return run_direct(ctx, k, cur, nxt, dP, divV, n, iter0);
+    const bool graphable = ctx->opt_graphs && n >= 8 && (ctx->nranks == 1 || pb.on);
+    if (!graphable) return run_direct(ctx, k, cur, nxt, dP, divV, n, iter0, pb, Pr_user);
     if (!ctx->pt_graphs) ctx->pt_graphs = new PtGraphCache();
     PtGraphCache* cache = (PtGraphCache*)ctx->pt_graphs;
     PtK key;
@@ -419,7 +591,7 @@ int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double* dP
     PtGraph* g = nullptr;
     for (PtGraph& c : cache->slot)
         if (c.exec && c.cur == cur && c.nxt == nxt && c.dP == dP && c.divV == divV && c.n == n &&
-            c.parity == (iter0 & 1) && c.mode == ctx->mode && c.minb == ctx->opt_pt_minb &&
+            c.parity == (iter0 & 1) && c.mode == ctx->mode && c.minb == ctx->opt_pt_minb && c.p2p == pb.on &&
             !memcmp(&c.k, &key, sizeof key))
             g = &c;
     if (!g) {
@@ -432,7 +604,7 @@ int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double* dP
         double *ccur = cur, *cnxt = nxt;
         const long long l0 = ctx->launches;
         NS3D_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        const int rc = run_direct(ctx, k, ccur, cnxt, dP, divV, n, iter0);
+        const int rc = run_direct(ctx, k, ccur, cnxt, dP, divV, n, iter0, pb, Pr_user);
         cudaGraph_t graph = nullptr;
         const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
         const long long captured = ctx->launches - l0;
@@ -451,7 +623,7 @@ int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double* dP
         }
         memcpy(&g->k, &key, sizeof key);
         g->cur = cur; g->nxt = nxt; g->dP = dP; g->divV = divV; g->n = n;
-        g->parity = iter0 & 1; g->mode = ctx->mode; g->minb = ctx->opt_pt_minb; g->kernels = captured;
+        g->parity = iter0 & 1; g->p2p = pb.on; g->mode = ctx->mode; g->minb = ctx->opt_pt_minb; g->kernels = captured;
     }
     NS3D_CUDA(ctx, cudaGraphLaunch(g->exec, ctx->stream));
     ctx->launches += g->kernels;
@@ -488,9 +660,11 @@ extern "C" int ns3d_pt_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const d
     double* cur = Pr;
     double* nxt = ctx->pr_shadow;
     int iters = 0, nc = 0;
+    PeerBufs pb;
+    NS3D_TRY(peer_prepare(ctx, k, Pr, ctx->pr_shadow, &pb));
     while (iters < p->niter) {
         const int chunk = std::min(p->nchk - iters % p->nchk, p->niter - iters);  // up to the next check
-        NS3D_TRY(run_iterations(ctx, k, cur, nxt, dPrdtau, divV, chunk, iters));
+        NS3D_TRY(run_iterations(ctx, k, cur, nxt, dPrdtau, divV, chunk, iters, pb, Pr));
         iters += chunk;
         if (iters % p->nchk == 0) {
             NS3D_TRY(launch_residual(ctx, k, cur, divV));
@@ -503,7 +677,12 @@ extern "C" int ns3d_pt_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const d
         }
     }
     if (cur != Pr) NS3D_CUDA(ctx, cudaMemcpyAsync(Pr, cur, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (pb.on)
+        NS3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_maxbits + 3, ctx->mbox + NS3D_MB_ERROR, 8, cudaMemcpyDeviceToHost, ctx->stream));
     NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (pb.on && ctx->h_maxbits[3] != 0ULL)
+        return ns3d_fail(ctx, NS3D_ECOMM, "peer-memory halo exchange: neighbour %s did not answer within the spin limit",
+                         ctx->h_maxbits[3] == 1ULL ? "below" : "above");
     if (h_iters) *h_iters = iters;
     if (h_nchecks) *h_nchecks = nc;
     return NS3D_OK;
@@ -521,7 +700,9 @@ extern "C" int ns3d_pt_iterate(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const
     NS3D_TRY(ensure_shadow(ctx, n));
     double* cur = Pr;
     double* nxt = ctx->pr_shadow;
-    NS3D_TRY(run_iterations(ctx, k, cur, nxt, dPrdtau, divV, n_iter, 0));
+    PeerBufs pb;
+    NS3D_TRY(peer_prepare(ctx, k, Pr, ctx->pr_shadow, &pb));
+    NS3D_TRY(run_iterations(ctx, k, cur, nxt, dPrdtau, divV, n_iter, 0, pb, Pr));
     if (cur != Pr) NS3D_CUDA(ctx, cudaMemcpyAsync(Pr, cur, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     return NS3D_OK;
 }
