@@ -35,6 +35,7 @@ WORKLOADS = {
     "C": ("M", 511, 511, 511),       # configs[2] geometry (Poisson-only timing uses --pt-only)
     "E": ("M", 511, 511, 511),       # configs[4]: 511^3 per GPU
     "A": ("M", 63, None, None),      # configs[0] (parity grid; launch-bound, for completeness)
+    "D": ("M", 1023, 511, 511),      # configs[3]: large single-GPU cylinder flow (2.14 GB per field)
 }
 
 
@@ -155,6 +156,51 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# Poisson-only leg (BASELINE configs[2])
+# ------------------------------------------------------------------------------------------------
+def pt_only(args, ns, ctx, s, stream, rank, world, barrier):
+    import torch
+    nx, ny, nz = s.nx, s.ny, s.nz
+    n = nx * ny * nz
+    rng = np.random.default_rng(1234)
+    x = (np.arange(nx) + 0.5) / nx
+    y = (np.arange(ny) + 0.5) / ny
+    z = (np.arange(nz) + 0.5) / nz
+    rhs = (np.sin(2 * np.pi * x)[:, None, None] * np.sin(2 * np.pi * y)[None, :, None]
+           * np.sin(2 * np.pi * z)[None, None, :])
+    rhs += rng.uniform(-0.01, 0.01, size=rhs.shape)
+    Pr = ctx.zeros(nx, ny, nz)
+    dP = ctx.zeros(nx - 2, ny - 2, nz - 2)
+    dv = ctx.from_host(np.asfortranarray(rhs))
+    del rhs
+    pt = s.pt_params(args.zchunk)
+    pt.eps_it, pt.niter, pt.nchk = 0.0, args.pt_only, min(510, args.pt_only)
+    ctx.pt_solve(Pr, dP, dv, pt)          # warm-up (also builds the graph)
+    times = []
+    for _ in range(max(args.steps, 1)):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        iters, hist = ctx.pt_solve(Pr, dP, dv, pt)
+        e1.record(stream)
+        barrier()
+        times.append(e0.elapsed_time(e1) / 1e3)
+    t = float(np.median(times))
+    peak, peak_src = hbm_peak()
+    if rank == 0:
+        bytes_ = (5 * iters + 2 * len(hist)) * 8.0 * n * world
+        print(json.dumps({"metric": "T_eff", "value": bytes_ / t / 1e9, "unit": "GB/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": f"Poisson-only PT solve {nx}x{ny}x{nz} per GPU, {iters} iterations, "
+                                                 f"{len(hist)} residual checks, rhs = sin*sin*sin + U(-0.01,0.01) (seed 1234)",
+                                     "mode": args.mode},
+                          "us_per_iteration": t / iters * 1e6, "frac_of_hbm_peak_per_gpu": bytes_ / t / 1e9 / world / peak,
+                          "final_err": hist[-1] if hist else None}))
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def main():
@@ -170,6 +216,9 @@ def main():
     ap.add_argument("--zchunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pt-only", type=int, default=0,
+                    help="Poisson-only benchmark (BASELINE configs[2]): time exactly this many PT iterations "
+                         "(ns3d_pt_solve with eps_it=0, one residual check per 510) on a synthetic rhs instead of time steps")
     ap.add_argument("--fixed-iters", type=int, default=0,
                     help="fixed PT work per step (eps_it=0, niter=this, nchk=niter/2): SURVEY.md 8d config E")
     args = ap.parse_args()
@@ -219,6 +268,9 @@ def main():
     sim = ns.Simulation(s, ctx, zchunk=args.zchunk)
     n_cells = s.nx * s.ny * s.nz
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
+
+    if args.pt_only:
+        return pt_only(args, ns, ctx, s, stream, rank, world, barrier)
 
     # ---- device-resident timing: W warm-up steps, then exactly K steps -------------------------
     for _ in range(args.warmup):
