@@ -229,7 +229,6 @@ def gather_interior(sim: Simulation, name: str) -> np.ndarray | None:
         return a
     if name == "Vz" and rank < world - 1:
         a = a[:, :, : s.nz - 2]
-    import torch
     import torch.distributed as dist
     parts = [None] * world if rank == 0 else None
     dist.gather_object(np.ascontiguousarray(a), parts, dst=0)

@@ -1,0 +1,69 @@
+"""GPU tests of the drop-in drivers (the reference's run-script surface) and of bench.py's output."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_run_navierstokes3D_is_the_reference_test_call(O, ns):
+    """test/test3D.jl:6 -- run_navierstokes3D(do_vis=false, do_save=false, do_print=true, nx=63, nt=1)
+    returns the interior arrays C,Pr,Vx,Vy,Vz.  With the script as shipped Pr is exactly 0 after one
+    step (the stale literals of test3D.jl:12-27 are the recorded expected mismatch)."""
+    C, Pr, Vx, Vy, Vz = ns.run_navierstokes3D(do_vis=False, do_save=False, do_print=False, nx=63, nt=1, mode=ns.PARITY)
+    assert Pr.shape == C.shape == (61, 36, 36) and Vx.shape == (62, 36, 36)
+    assert Vy.shape == (61, 37, 36) and Vz.shape == (61, 36, 37)
+    assert (Pr == 0.0).all()
+    p = O.params_M(63)
+    f, _, _ = O.run(p, 1)
+    for got, name in ((C, "C"), (Pr, "Pr"), (Vx, "Vx"), (Vy, "Vy"), (Vz, "Vz")):
+        assert np.array_equal(got, O.interior(f[name])), name
+    assert (C == 1.0).sum() > 0
+
+
+def test_run_navierstokes3D_matches_oracle_after_six_steps(O, ns):
+    out = ns.run_navierstokes3D(nx=63, nt=6, mode=ns.PARITY)
+    p = O.params_M(63)
+    f, iters, _ = O.run(p, 6)
+    for got, name in zip(out, ("C", "Pr", "Vx", "Vy", "Vz")):
+        assert np.array_equal(got, O.interior(f[name])), name
+
+
+def test_runme_single_gpu_script(O, ns):
+    sim = ns.runme(do_vis=False, do_save=False, nx=40, nt=2, mode=ns.PARITY, do_print=False, return_sim=True)
+    p = O.params_G(40)
+    f, iters, _ = O.run(p, 2)
+    assert sim.iters == iters
+    for name in ("Pr", "Vx", "Vy", "Vz", "C"):
+        assert np.array_equal(sim.host(name), f[name]), name
+    sim.ctx.close()
+
+
+def test_do_save_writes_float32_bins(ns, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    out = ns.run_navierstokes3D(do_save=True, nx=40, nt=2)
+    for name, arr in zip(("C", "Pr", "Vx", "Vy", "Vz"), out):
+        raw = np.fromfile(tmp_path / "out_save" / f"out_{name}_v_0002.bin", dtype=np.float32)   # M:27-30,517-521
+        assert raw.size == arr.size
+        assert np.array_equal(raw, arr.astype(np.float32).ravel(order="F"))
+
+
+def test_bench_line_has_the_contract_keys():
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "A", "--steps", "2", "--warmup", "3",
+                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-3000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "parity_check"):
+        assert k in line, k
+    assert line["dtype"] == "f64" and line["unit"] == "GB/s" and line["vs_baseline"] is None
+    assert line["gpu_launches"] > 0 and line["value"] > 0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
+    assert line["e2e"]["h2d_bytes_per_step"] > 0
+    assert line["parity_check"]["pt_iters_identical"] and line["parity_check"]["within_tolerance"]
