@@ -105,6 +105,8 @@ def oracle_sample(variant: str, nx: int, ny, nz, budget_s: float = 12.0):
     (one residual check included), n_it chosen from a probe so the sample is ~budget_s."""
     from oracle import oracle as O
     p = O.params_G(nx, ny=ny, nz=nz) if variant == "G" else O.params_M(nx, ny=ny, nz=nz)
+    # all the host threads the box offers (torchrun exports OMP_NUM_THREADS=1 to its ranks)
+    O.lib().ns3d_oracle_set_num_threads(len(os.sched_getaffinity(0)))
     cores = O.lib().ns3d_oracle_num_threads()
     f = O.initial_fields(p)
     t0 = time.perf_counter()
