@@ -206,7 +206,9 @@ extern "C" int ns3d_zeros(ns3d_ctx* ctx, int sx, int sy, int sz, double** dptr)
     if (!dptr || sx <= 0 || sy <= 0 || sz <= 0)
         return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_zeros: bad shape (%d,%d,%d)", sx, sy, sz);
     NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
-    size_t bytes = (size_t)sx * sy * sz * sizeof(double);
+    // The block is padded by three x-y planes behind the array: the software-pipelined hot kernel
+    // prefetches up to two planes ahead unconditionally (values past the end are never used).
+    size_t bytes = ((size_t)sx * sy * sz + 3 * (size_t)sx * sy) * sizeof(double) + 256;
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, bytes);  // cudaMalloc returns >= 256-byte aligned blocks
     if (e != cudaSuccess) {

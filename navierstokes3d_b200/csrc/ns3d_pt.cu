@@ -53,6 +53,9 @@ struct PtK {
     unsigned long long* mbox;          // this rank's mailbox (NS3D_MB_*)
     unsigned long long* peer_lo_flag;  // lower neighbour's NS3D_MB_FLAG_HI
     unsigned long long* peer_hi_flag;  // upper neighbour's NS3D_MB_FLAG_LO
+    // byte strides, precomputed on the host so that the kernel takes them from the constant bank
+    // instead of re-deriving 64-bit products under register pressure
+    long long rowB, planeB, dplaneB;
 };
 
 // a / b with y = RN(1/b): one multiply + two FMAs (Markstein's correction step).
@@ -218,21 +221,25 @@ __global__ void __launch_bounds__(256, MINB) pt_iter_kernel(const double* __rest
         __syncthreads();
     }
     if (active) {
-    const ptrdiff_t sxy = (ptrdiff_t)nx * ny;
-    const ptrdiff_t dxy = (ptrdiff_t)(nx - 2) * (ny - 2);
     const bool xl = (i == 1), xh = (i == nx - 2), yl = (j == 1), yh = (j == ny - 2);
-    const bool edge = xl | xh | yl | yh;
-    ptrdiff_t off = (ptrdiff_t)idx3(i, j, kb, nx, ny);                      // into Pr, PrN, divV
-    ptrdiff_t dof = (ptrdiff_t)idx3(i - 1, j - 1, kb - 1, nx - 2, ny - 2);  // into dPrdτ
-
-    auto load = [&](StreamRegs& r, ptrdiff_t o, ptrdiff_t d) {
-        r.zp = Pr[o + sxy];
-        r.dq = dP[d];
-        r.dv = divV[o];
+    // One predicate keeps every boundary store off the hot path: threads next to an x/y face, and
+    // whole CTAs whose chunk holds plane 1 or nz-2 (z faces / slab interfaces).
+    const bool slow = xl | xh | yl | yh | (kb == 1) | (ke == nz - 1);
+    const long long rowB = p.rowB, planeB = p.planeB, dplaneB = p.dplaneB;
+    // byte pointers to this thread's column at plane kb; all other addresses are this + constants
+    const char* c0 = (const char*)(Pr + idx3(i, j, kb, nx, ny));
+    const long long dDV = (const char*)divV - (const char*)Pr;    // same shape: constant displacements
+    const long long dOUT = (const char*)PrN - (const char*)Pr;
+    char* d0 = (char*)(dP + idx3(i - 1, j - 1, kb - 1, nx - 2, ny - 2));
+#define LD(ptr) (*(const double*)(ptr))
+    auto load = [&](StreamRegs& r, const char* c, const char* d) {
+        r.zp = LD(c + planeB);
+        r.dq = LD(d);
+        r.dv = LD(c + dDV);
     };
-    double pm = Pr[off - sxy], pc = Pr[off];
-    auto compute = [&](const StreamRegs& r, int k, ptrdiff_t o, ptrdiff_t d) {
-        const double L = bracket<MODE>(p, pc, Pr[o - 1], Pr[o + 1], Pr[o - nx], Pr[o + nx], pm, r.zp, r.dv);
+    double pm = LD(c0 - planeB), pc = LD(c0);
+    auto compute = [&](const StreamRegs& r, int k, const char* c, char* d) {
+        const double L = bracket<MODE>(p, pc, LD(c - 8), LD(c + 8), LD(c - rowB), LD(c + rowB), pm, r.zp, r.dv);
         double dn, u;
         if (MODE == NS3D_FASTEST) {
             dn = fma(p.dtau, L, r.dq * p.omd);
@@ -241,38 +248,42 @@ __global__ void __launch_bounds__(256, MINB) pt_iter_kernel(const double* __rest
             dn = r.dq * p.omd + p.dtau * L;  // M:71
             u = pc + p.dtau * dn;            // M:80
         }
-        dP[d] = dn;
-        PrN[o] = u;
-        if (edge) {  // x/y mirror images in this plane (bc_x!, bc_y!; outlet / hydrostatic x faces)
-            double* plane = PrN + (o - ((ptrdiff_t)j * nx + i));
+        *(double*)d = dn;
+        *(double*)(const_cast<char*>(c) + dOUT) = u;
+        if (slow) {
+            const ptrdiff_t sxy = (ptrdiff_t)nx * ny;
+            double* plane = PrN + (ptrdiff_t)k * sxy;
+            // x/y mirror images in this plane (bc_x!, bc_y!; outlet / hydrostatic x faces)
             if (xl) plane[(ptrdiff_t)j * nx] = xface(p, false, k, u);
             if (xh) plane[(ptrdiff_t)j * nx + nx - 1] = xface(p, true, k, u);
             if (yl) store_row(p, plane, i, k, u, xl, xh);
             if (yh) store_row(p, plane + (ptrdiff_t)(ny - 1) * nx, i, k, u, xl, xh);
-        }
-        if (k == 1) {
-            if (!p.zlo_halo) store_plane(p, PrN, i, j, 0, u, xl, xh, yl, yh);  // bc_z! M:129
-            else if (P2P) store_plane(p, p.peer_lo_plane, i, j, k, u, xl, xh, yl, yh);  // update_halo!(Pr)
-        }
-        if (k == nz - 2) {
-            if (!p.zhi_halo) store_plane(p, PrN + (ptrdiff_t)(nz - 1) * sxy, i, j, nz - 1, u, xl, xh, yl, yh);  // M:130
-            else if (P2P) store_plane(p, p.peer_hi_plane, i, j, k, u, xl, xh, yl, yh);
+            if (k == 1) {
+                if (!p.zlo_halo) store_plane(p, PrN, i, j, 0, u, xl, xh, yl, yh);  // bc_z! M:129
+                else if (P2P) store_plane(p, p.peer_lo_plane, i, j, k, u, xl, xh, yl, yh);  // update_halo!(Pr)
+            }
+            if (k == nz - 2) {
+                if (!p.zhi_halo) store_plane(p, PrN + (ptrdiff_t)(nz - 1) * sxy, i, j, nz - 1, u, xl, xh, yl, yh);  // M:130
+                else if (P2P) store_plane(p, p.peer_hi_plane, i, j, k, u, xl, xh, yl, yh);
+            }
         }
         pm = pc;
         pc = r.zp;
     };
 
     StreamRegs A, B;
-    load(A, off, dof);
+    load(A, c0, d0);
     for (int k = kb; k < ke; k += 2) {
-        const bool has1 = k + 1 < ke, has2 = k + 2 < ke;
-        if (has1) load(B, off + sxy, dof + dxy);
-        compute(A, k, off, dof);
-        if (has2) load(A, off + 2 * sxy, dof + 2 * dxy);
-        if (has1) compute(B, k + 1, off + sxy, dof + dxy);
-        off += 2 * sxy;
-        dof += 2 * dxy;
+        // Prefetches are unconditional: past the chunk they touch planes other CTAs own, past the
+        // array the allocator's padding (ns3d_zeros); such values are loaded and never used.
+        load(B, c0 + planeB, d0 + dplaneB);
+        compute(A, k, c0, d0);
+        load(A, c0 + 2 * planeB, d0 + 2 * dplaneB);
+        if (k + 1 < ke) compute(B, k + 1, c0 + planeB, d0 + dplaneB);
+        c0 += 2 * planeB;
+        d0 += 2 * dplaneB;
     }
+#undef LD
     }  // active
     if (P2P && (lo_face | hi_face)) {
         __threadfence_system();  // this thread's peer stores are performed before the flag can be seen
@@ -359,6 +370,9 @@ int make_ptk(ns3d_ctx* ctx, const ns3d_pt_params* p, PtK* k)
     k->kend = p->nz - 1;
     k->faces = 0;
     k->reverse = 0;
+    k->rowB = 8LL * p->nx;
+    k->planeB = 8LL * p->nx * p->ny;
+    k->dplaneB = 8LL * (p->nx - 2) * (p->ny - 2);
     // serpentine pays while a good part of the 4-field working set can stay in L2 (measured:
     // +5..8 % at 255x153x153, neutral to -1 % at 511^3; profiles/r01_v4_sweep_serpentine.jsonl)
     k->serpentine = ctx->opt_serpentine < 0 ? (4.0 * 8.0 * p->nx * p->ny * p->nz < 6.0 * ctx->l2_bytes)
@@ -366,8 +380,19 @@ int make_ptk(ns3d_ctx* ctx, const ns3d_pt_params* p, PtK* k)
     return NS3D_OK;
 }
 
-int ensure_shadow(ns3d_ctx* ctx, size_t count)
+// The hot kernel prefetches past the end of its arrays into the allocator's padding, so the
+// fields of the fused loop must be blocks handed out by ns3d_zeros of this context.
+int check_owned(ns3d_ctx* ctx, const double* Pr, const double* dP, const double* divV)
 {
+    for (const double* a : {Pr, dP, divV})
+        if (!ctx->allocs.count((void*)a))
+            return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_pt_*: field %p was not allocated by ns3d_zeros of this context", (const void*)a);
+    return NS3D_OK;
+}
+
+int ensure_shadow(ns3d_ctx* ctx, size_t count, size_t pad_bytes)
+{
+    count += pad_bytes / sizeof(double);
     if (ctx->pr_shadow_count >= count) return NS3D_OK;
     if (ctx->pr_shadow) {
         NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -415,7 +440,7 @@ int launch_iter(ns3d_ctx* ctx, cudaStream_t st, const PtK& k, const double* cur,
     // the measured optimum per mode (profiles/r01_v4_sweep_minb.jsonl): the largest occupancy
     // that does not spill.
     int minb = ctx->opt_pt_minb;
-    if (minb == 0) minb = ctx->mode == NS3D_FASTEST ? 5 : (ctx->mode == NS3D_FAST ? 4 : 3);
+    if (minb == 0) minb = ctx->mode == NS3D_PARITY ? 3 : 5;
     if (k.mbox && minb > 4) minb = 4;  // the peer-store variant spills at 48 registers
     switch (minb) {
         case 3: PT_LAUNCH_MODE(3); break;
@@ -656,7 +681,8 @@ extern "C" int ns3d_pt_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const d
     if (p->nchk <= 0 || p->niter < 0) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_pt_solve: bad niter/nchk");
     NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t n = (size_t)p->nx * p->ny * p->nz;
-    NS3D_TRY(ensure_shadow(ctx, n));
+    NS3D_TRY(check_owned(ctx, Pr, dPrdtau, divV));
+    NS3D_TRY(ensure_shadow(ctx, n, 3 * (size_t)p->nx * p->ny * sizeof(double) + 256));
     double* cur = Pr;
     double* nxt = ctx->pr_shadow;
     int iters = 0, nc = 0;
@@ -697,7 +723,8 @@ extern "C" int ns3d_pt_iterate(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const
     NS3D_TRY(make_ptk(ctx, p, &k));
     NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t n = (size_t)p->nx * p->ny * p->nz;
-    NS3D_TRY(ensure_shadow(ctx, n));
+    NS3D_TRY(check_owned(ctx, Pr, dPrdtau, divV));
+    NS3D_TRY(ensure_shadow(ctx, n, 3 * (size_t)p->nx * p->ny * sizeof(double) + 256));
     double* cur = Pr;
     double* nxt = ctx->pr_shadow;
     PeerBufs pb;
