@@ -141,6 +141,7 @@ extern "C" int ns3d_destroy(ns3d_ctx* ctx)
     if (ctx->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl);
     for (auto& kv : ctx->allocs) cudaFree(kv.first);
     if (ctx->pr_shadow) cudaFree(ctx->pr_shadow);
+    if (ctx->dp_shadow) cudaFree(ctx->dp_shadow);
     cudaFree(ctx->d_maxbits);
     cudaFreeHost(ctx->h_maxbits);
     cudaEventDestroy(ctx->ev_a);
@@ -170,6 +171,10 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
     }
     if (!strcmp(name, "p2p_halo")) {
         ctx->opt_p2p = value != 0;
+        return NS3D_OK;
+    }
+    if (!strcmp(name, "tb2")) {
+        ctx->opt_tb2 = value < 0 ? -1 : (value != 0);
         return NS3D_OK;
     }
     if (!strcmp(name, "graphs")) {

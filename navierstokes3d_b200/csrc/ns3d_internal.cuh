@@ -26,6 +26,8 @@ struct ns3d_ctx {
     // scratch owned by the context
     double* pr_shadow = nullptr;  // ping-pong partner of Pr in the fused PT loop
     size_t pr_shadow_count = 0;
+    double* dp_shadow = nullptr;  // ping-pong partner of dPrdtau (two-iterations-per-launch path)
+    size_t dp_shadow_count = 0;
     unsigned long long* d_maxbits = nullptr;  // device accumulator of max |x| bit patterns
     unsigned long long* h_maxbits = nullptr;  // pinned host mirror
     // communicator (z-slabs, one rank per GPU)
@@ -41,6 +43,7 @@ struct ns3d_ctx {
     // tuning knobs (ns3d_set_option)
     int opt_pt_minb = 0;  // 0 = per-mode default
     int opt_serpentine = -1;  // -1 = by working-set size
+    int opt_tb2 = -1;         // two PT iterations per launch: -1 = when the working set is far beyond L2 (single rank)
     int opt_graphs = 1;       // replay chunks of PT iterations as CUDA graphs
     long long halo_calls = 0; // uncaptured halo exchanges so far (NCCL peers connected)
     void* pt_graphs = nullptr;  // graph cache owned by ns3d_pt.cu

@@ -56,6 +56,7 @@ struct PtK {
     // byte strides, precomputed on the host so that the kernel takes them from the constant bank
     // instead of re-deriving 64-bit products under register pressure
     long long rowB, planeB, dplaneB;
+    int zchunk_tb;  // chunk length of the two-iterations-per-launch kernel
 };
 
 // a / b with y = RN(1/b): one multiply + two FMAs (Markstein's correction step).
@@ -296,6 +297,134 @@ __global__ void __launch_bounds__(256, MINB) pt_iter_kernel(const double* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two PT iterations per launch (temporal blocking, opt-in: ns3d_set_option("tb2", 1)).
+//
+// A CTA owns a 32x16 tile of columns and marches along z with a two-stage pipeline: stage 1
+// computes the first iteration's pressure q = Pr^(1) of plane s for every tile column (from
+// global memory, exactly like pt_iter_kernel), publishes it in a three-deep shared-memory ring,
+// and stage 2 computes the second iteration of plane s-1 for the 30x14 inner columns from the
+// ring (in-plane neighbours) and registers (z neighbours, dPrdτ^(1), ∇V) -- no global loads.
+// Pr^(1) and dPrdτ^(1) never touch DRAM: 5 field passes per TWO iterations.  Tile rims and the
+// two extra planes per z-chunk are recomputed by the neighbouring CTAs; columns on a domain face
+// take the value of their index clamped into the interior (the folded bc_x!/bc_y!), so stage 1
+// needs no extra synchronisation for the boundary conditions, and z faces are handled in
+// registers (q[0] = q[1], q[nz-1] = q[nz-2]).  Same per-cell arithmetic as pt_iter_kernel, so
+// PARITY mode stays bit-equal to the oracle.  dPrdτ ping-pongs with a context-owned shadow
+// (rim columns of other CTAs read the old value while the owner writes the new one).
+// ---------------------------------------------------------------------------------------------
+constexpr int TB_X = 32, TB_Y = 16;
+
+template <int MODE>
+__global__ void __launch_bounds__(TB_X* TB_Y, 2) pt_tb2_kernel(const double* __restrict__ Pr, double* __restrict__ PrN,
+                                                              const double* __restrict__ dP, double* __restrict__ dPN,
+                                                              const double* __restrict__ divV, const PtK p)
+{
+    __shared__ double ring[3][TB_Y][TB_X];
+    const int nx = p.nx, ny = p.ny, nz = p.nz;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.x * (TB_X - 2) + tx;  // tile columns include the rim (and the domain faces)
+    const int j = blockIdx.y * (TB_Y - 2) + ty;
+    const bool in_dom = (i <= nx - 1) && (j <= ny - 1);
+    const int ci = min(max(i, 1), nx - 2), cj = min(max(j, 1), ny - 2);  // clamped into the interior
+    const bool interior = in_dom && ci == i && cj == j;
+    const bool owner = interior && tx >= 1 && tx <= TB_X - 2 && ty >= 1 && ty <= TB_Y - 2;  // stage-2 output
+    const int bz = p.reverse ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
+    const int kb = p.kbeg + bz * p.zchunk;
+    const int ke = min(kb + p.zchunk, p.kend);  // stage-2 planes [kb, ke)
+    const int s0 = max(kb - 1, 1), s1 = min(ke, nz - 2);  // stage-1 planes [s0, s1]
+    const bool xl = (i == 1), xh = (i == nx - 2), yl = (j == 1), yh = (j == ny - 2);
+    const long long rowB = p.rowB, planeB = p.planeB, dplaneB = p.dplaneB;
+    const long long dDV = (const char*)divV - (const char*)Pr;
+    const char* c = (const char*)(Pr + idx3(ci, cj, s0, nx, ny));
+    const char* d = (const char*)(dP + idx3(ci - 1, cj - 1, s0 - 1, nx - 2, ny - 2));
+#define LD(ptr) (*(const double*)(ptr))
+    double pm = 0, pc = 0, zp = 0, dq = 0, dv = 0;
+    if (in_dom) {
+        pm = LD(c - planeB);
+        pc = LD(c);
+        zp = LD(c + planeB);
+        dq = LD(d);
+        dv = LD(c + dDV);
+    }
+    double q_m = 0, q_c = 0, d1_c = 0, dv_c = 0;  // stage-2 state of plane s-1 (and q of s-2)
+    for (int s = s0; s <= s1; ++s) {
+        // prefetch the three streamed values of plane s+1 (the allocator pads the arrays)
+        double n_zp = 0, n_dq = 0, n_dv = 0;
+        if (in_dom) {
+            n_zp = LD(c + 2 * planeB);
+            n_dq = LD(d + dplaneB);
+            n_dv = LD(c + planeB + dDV);
+        }
+        // ---- stage 1: first iteration at the clamped column, plane s ---------------------------
+        double q = 0, d1 = 0;
+        if (in_dom) {
+            const double L = bracket<MODE>(p, pc, LD(c - 8), LD(c + 8), LD(c - rowB), LD(c + rowB), pm, zp, dv);
+            if (MODE == NS3D_FASTEST) {
+                d1 = fma(p.dtau, L, dq * p.omd);
+                q = fma(p.dtau, d1, pc);
+            } else {
+                d1 = dq * p.omd + p.dtau * L;
+                q = pc + p.dtau * d1;
+            }
+            if (i == 0) q = xface(p, false, s, q);        // bc_x_Pr! / bc_xhydstatic! images
+            if (i == nx - 1) q = xface(p, true, s, q);
+        }
+        ring[s % 3][ty][tx] = q;
+        __syncthreads();
+        // ---- stage 2: second iteration of plane s-1 ---------------------------------------------
+        const int k2 = s - 1;
+        if (owner && k2 >= kb) {
+            const double(*rp)[TB_X] = ring[k2 % 3];
+            const double L = bracket<MODE>(p, q_c, rp[ty][tx - 1], rp[ty][tx + 1], rp[ty - 1][tx], rp[ty + 1][tx], q_m, q, dv_c);
+            double d2, u;
+            if (MODE == NS3D_FASTEST) {
+                d2 = fma(p.dtau, L, d1_c * p.omd);
+                u = fma(p.dtau, d2, q_c);
+            } else {
+                d2 = d1_c * p.omd + p.dtau * L;
+                u = q_c + p.dtau * d2;
+            }
+            dPN[idx3(i - 1, j - 1, k2 - 1, nx - 2, ny - 2)] = d2;
+            store_plane(p, PrN + (ptrdiff_t)k2 * (ptrdiff_t)nx * ny, i, j, k2, u, xl, xh, yl, yh);
+            if (k2 == 1) store_plane(p, PrN, i, j, 0, u, xl, xh, yl, yh);  // bc_z! M:129
+        }
+        // rotate: plane s becomes "s-1"
+        q_m = q_c;
+        q_c = q;
+        if (s == 1) {  // bc_z!: q[0] is the image of q[1] (hydrostatic x faces depend on the plane)
+            q_m = q;
+            if (i == 0) q_m = xface(p, false, 0, q);
+            if (i == nx - 1) q_m = xface(p, true, 0, q);
+        }
+        d1_c = d1;
+        dv_c = dv;
+        pm = pc; pc = zp; zp = n_zp; dq = n_dq; dv = n_dv;
+        c += planeB;
+        d += dplaneB;
+    }
+    // last chunk: plane nz-2 needs q[nz-1], the image of q[nz-2]
+    if (s1 == nz - 2 && ke == nz - 1 && owner) {
+        const int k2 = nz - 2;
+        double q_p = q_c;
+        const double(*rp)[TB_X] = ring[k2 % 3];
+        const double L = bracket<MODE>(p, q_c, rp[ty][tx - 1], rp[ty][tx + 1], rp[ty - 1][tx], rp[ty + 1][tx], q_m, q_p, dv_c);
+        double d2, u;
+        if (MODE == NS3D_FASTEST) {
+            d2 = fma(p.dtau, L, d1_c * p.omd);
+            u = fma(p.dtau, d2, q_c);
+        } else {
+            d2 = d1_c * p.omd + p.dtau * L;
+            u = q_c + p.dtau * d2;
+        }
+        dPN[idx3(i - 1, j - 1, k2 - 1, nx - 2, ny - 2)] = d2;
+        store_plane(p, PrN + (ptrdiff_t)k2 * (ptrdiff_t)nx * ny, i, j, k2, u, xl, xh, yl, yh);
+        if (k2 == 1) store_plane(p, PrN, i, j, 0, u, xl, xh, yl, yh);
+        store_plane(p, PrN + (ptrdiff_t)(nz - 1) * (ptrdiff_t)nx * ny, i, j, nz - 1, u, xl, xh, yl, yh);  // bc_z! M:130
+    }
+#undef LD
+}
+
 // compute_res! + abs + maximum (K8 + K8') in one pass, no Rp array: max over the interior of
 // the bit pattern of |bracket| (NaN-propagating, see absbits()).
 template <int MODE>
@@ -366,6 +495,7 @@ int make_ptk(ns3d_ctx* ctx, const ns3d_pt_params* p, PtK* k)
         while (zc > 4 && xy * cdiv(p->nz - 2, zc) < 2LL * 8 * ctx->num_sms) zc /= 2;  // measured: profiles/r01_*sweep*
     }
     k->zchunk = zc;
+    k->zchunk_tb = p->zchunk > 0 ? p->zchunk : std::max(zc, 16);  // two extra stage-1 planes per chunk: keep them long
     k->kbeg = 1;
     k->kend = p->nz - 1;
     k->faces = 0;
@@ -451,6 +581,50 @@ int launch_iter(ns3d_ctx* ctx, cudaStream_t st, const PtK& k, const double* cur,
 #undef PT_LAUNCH_MODE
 #undef PT_LAUNCH
     NS3D_LAUNCH_CHECK(ctx);
+    return NS3D_OK;
+}
+
+int launch_tb2(ns3d_ctx* ctx, const PtK& k, const double* cur, double* nxt, const double* dpc, double* dpn,
+               const double* divV)
+{
+    const dim3 blk(TB_X, TB_Y, 1);
+    const dim3 grd(cdiv(k.nx - 2, TB_X - 2), cdiv(k.ny - 2, TB_Y - 2), cdiv(k.kend - k.kbeg, k.zchunk));
+    switch (ctx->mode) {
+        case NS3D_PARITY: pt_tb2_kernel<NS3D_PARITY><<<grd, blk, 0, ctx->stream>>>(cur, nxt, dpc, dpn, divV, k); break;
+        case NS3D_FAST: pt_tb2_kernel<NS3D_FAST><<<grd, blk, 0, ctx->stream>>>(cur, nxt, dpc, dpn, divV, k); break;
+        default: pt_tb2_kernel<NS3D_FASTEST><<<grd, blk, 0, ctx->stream>>>(cur, nxt, dpc, dpn, divV, k); break;
+    }
+    NS3D_LAUNCH_CHECK(ctx);
+    return NS3D_OK;
+}
+
+// Two iterations per launch pay where the loop is DRAM-bound: measured +27 % at 511^3 (675 vs
+// 856 us/iteration, T_eff above the HBM copy peak) but only +5 % at 255x153x153, where the
+// single-iteration kernel is latency/issue-bound and L2 already serves part of the traffic.  Slabs
+// keep the single-iteration kernel (the rim of a two-iteration update would need a second halo
+// plane), so the automatic policy is: single rank and a working set far beyond L2.
+bool use_tb2(const ns3d_ctx* ctx, const ns3d_pt_params* p)
+{
+    if (ctx->nranks != 1 || ctx->opt_tb2 == 0) return false;
+    if (ctx->opt_tb2 > 0) return true;
+    return 4.0 * 8.0 * p->nx * p->ny * p->nz >= 6.0 * ctx->l2_bytes;
+}
+
+int ensure_dp_shadow(ns3d_ctx* ctx, size_t count)
+{
+    if (ctx->dp_shadow_count >= count) return NS3D_OK;
+    if (ctx->dp_shadow) {
+        NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        NS3D_CUDA(ctx, cudaFree(ctx->dp_shadow));
+        ctx->dp_shadow = nullptr;
+        ctx->dp_shadow_count = 0;
+    }
+    cudaError_t e = cudaMalloc(&ctx->dp_shadow, count * sizeof(double));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ns3d_fail(ctx, NS3D_ENOMEM, "pt: cannot allocate the dPrdtau shadow (%zu B)", count * sizeof(double));
+    }
+    ctx->dp_shadow_count = count;
     return NS3D_OK;
 }
 
@@ -577,6 +751,7 @@ struct PtGraph {
     const double* cur = nullptr;
     double* nxt = nullptr;
     double* dP = nullptr;
+    double* dPn = nullptr;
     const double* divV = nullptr;
     int n = 0, parity = 0, mode = 0, minb = 0;
     bool p2p = false;
@@ -587,11 +762,22 @@ struct PtGraphCache {
     int next = 0;
 };
 
-int run_direct(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double* dP, const double* divV, int n, int iter0,
-               const PeerBufs& pb, const double* Pr_user)
+int run_direct(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double*& dP, double*& dPn, const double* divV, int n,
+               int iter0, const PeerBufs& pb, const double* Pr_user)
 {
     NS3D_TRY(pt_begin(ctx));
-    for (int q = 0; q < n; ++q) {
+    int q = 0;
+    if (dPn) {  // two iterations per launch; Pr and dPrdτ both ping-pong
+        PtK k2 = k;
+        k2.zchunk = k.zchunk_tb;
+        for (; q + 2 <= n; q += 2) {
+            k2.reverse = k.serpentine && (((iter0 + q) >> 1) & 1);
+            NS3D_TRY(launch_tb2(ctx, k2, cur, nxt, dP, dPn, divV));
+            double* t = cur; cur = nxt; nxt = t;
+            t = dP; dP = dPn; dPn = t;
+        }
+    }
+    for (; q < n; ++q) {
         k.reverse = k.serpentine && ((iter0 + q) & 1);
         NS3D_TRY(pt_iteration(ctx, k, cur, nxt, dP, divV, pb, Pr_user));
         double* t = cur; cur = nxt; nxt = t;
@@ -600,14 +786,14 @@ int run_direct(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double* dP, co
 }
 
 // Runs iterations iter0 .. iter0+n-1 (0-based count since the start of the solve).
-int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double* dP, const double* divV, int n, int iter0,
-                   const PeerBufs& pb, const double* Pr_user)
+int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double*& dP, double*& dPn, const double* divV,
+                   int n, int iter0, const PeerBufs& pb, const double* Pr_user)
 {
     // NCCL send/recv captured in a graph drags host-callback nodes along (proxy progress) and
     // replays slower than the stream version (measured 55.9 vs 44.9 us/iteration on 2 GPUs), so
     // only kernel-only iterations are replayed as graphs.
     const bool graphable = ctx->opt_graphs && n >= 8 && (ctx->nranks == 1 || pb.on);
-    if (!graphable) return run_direct(ctx, k, cur, nxt, dP, divV, n, iter0, pb, Pr_user);
+    if (!graphable) return run_direct(ctx, k, cur, nxt, dP, dPn, divV, n, iter0, pb, Pr_user);
     if (!ctx->pt_graphs) ctx->pt_graphs = new PtGraphCache();
     PtGraphCache* cache = (PtGraphCache*)ctx->pt_graphs;
     PtK key;
@@ -615,8 +801,8 @@ int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double* dP
     key.reverse = 0;
     PtGraph* g = nullptr;
     for (PtGraph& c : cache->slot)
-        if (c.exec && c.cur == cur && c.nxt == nxt && c.dP == dP && c.divV == divV && c.n == n &&
-            c.parity == (iter0 & 1) && c.mode == ctx->mode && c.minb == ctx->opt_pt_minb && c.p2p == pb.on &&
+        if (c.exec && c.cur == cur && c.nxt == nxt && c.dP == dP && c.dPn == dPn && c.divV == divV && c.n == n &&
+            c.parity == (iter0 & 3) && c.mode == ctx->mode && c.minb == ctx->opt_pt_minb && c.p2p == pb.on &&
             !memcmp(&c.k, &key, sizeof key))
             g = &c;
     if (!g) {
@@ -626,10 +812,10 @@ int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double* dP
             cudaGraphExecDestroy(g->exec);
             g->exec = nullptr;
         }
-        double *ccur = cur, *cnxt = nxt;
+        double *ccur = cur, *cnxt = nxt, *cdp = dP, *cdpn = dPn;
         const long long l0 = ctx->launches;
         NS3D_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        const int rc = run_direct(ctx, k, ccur, cnxt, dP, divV, n, iter0, pb, Pr_user);
+        const int rc = run_direct(ctx, k, ccur, cnxt, cdp, cdpn, divV, n, iter0, pb, Pr_user);
         cudaGraph_t graph = nullptr;
         const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
         const long long captured = ctx->launches - l0;
@@ -647,12 +833,20 @@ int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double* dP
             return ns3d_fail(ctx, NS3D_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e2));
         }
         memcpy(&g->k, &key, sizeof key);
-        g->cur = cur; g->nxt = nxt; g->dP = dP; g->divV = divV; g->n = n;
-        g->parity = iter0 & 1; g->p2p = pb.on; g->mode = ctx->mode; g->minb = ctx->opt_pt_minb; g->kernels = captured;
+        g->cur = cur; g->nxt = nxt; g->dP = dP; g->dPn = dPn; g->divV = divV; g->n = n;
+        g->parity = iter0 & 3; g->p2p = pb.on; g->mode = ctx->mode; g->minb = ctx->opt_pt_minb; g->kernels = captured;
     }
     NS3D_CUDA(ctx, cudaGraphLaunch(g->exec, ctx->stream));
     ctx->launches += g->kernels;
-    if (n & 1) {
+    if (dPn) {  // n/2 double launches swap both pairs, a trailing single launch swaps Pr only
+        if ((n >> 1) & 1) {
+            double* t = cur; cur = nxt; nxt = t;
+            t = dP; dP = dPn; dPn = t;
+        }
+        if (n & 1) {
+            double* t = cur; cur = nxt; nxt = t;
+        }
+    } else if (n & 1) {
         double* t = cur; cur = nxt; nxt = t;
     }
     return NS3D_OK;
@@ -688,9 +882,15 @@ extern "C" int ns3d_pt_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const d
     int iters = 0, nc = 0;
     PeerBufs pb;
     NS3D_TRY(peer_prepare(ctx, k, Pr, ctx->pr_shadow, &pb));
+    double *dpc = dPrdtau, *dpn = nullptr;
+    if (use_tb2(ctx, p)) {
+        const size_t nd = (size_t)(p->nx - 2) * (p->ny - 2) * (p->nz - 2) + 3 * (size_t)(p->nx - 2) * (p->ny - 2) + 32;
+        NS3D_TRY(ensure_dp_shadow(ctx, nd));
+        dpn = ctx->dp_shadow;
+    }
     while (iters < p->niter) {
         const int chunk = std::min(p->nchk - iters % p->nchk, p->niter - iters);  // up to the next check
-        NS3D_TRY(run_iterations(ctx, k, cur, nxt, dPrdtau, divV, chunk, iters, pb, Pr));
+        NS3D_TRY(run_iterations(ctx, k, cur, nxt, dpc, dpn, divV, chunk, iters, pb, Pr));
         iters += chunk;
         if (iters % p->nchk == 0) {
             NS3D_TRY(launch_residual(ctx, k, cur, divV));
@@ -703,6 +903,9 @@ extern "C" int ns3d_pt_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const d
         }
     }
     if (cur != Pr) NS3D_CUDA(ctx, cudaMemcpyAsync(Pr, cur, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (dpc != dPrdtau)
+        NS3D_CUDA(ctx, cudaMemcpyAsync(dPrdtau, dpc, (size_t)(p->nx - 2) * (p->ny - 2) * (p->nz - 2) * sizeof(double),
+                                       cudaMemcpyDeviceToDevice, ctx->stream));
     if (pb.on)
         NS3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_maxbits + 3, ctx->mbox + NS3D_MB_ERROR, 8, cudaMemcpyDeviceToHost, ctx->stream));
     NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -729,7 +932,16 @@ extern "C" int ns3d_pt_iterate(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const
     double* nxt = ctx->pr_shadow;
     PeerBufs pb;
     NS3D_TRY(peer_prepare(ctx, k, Pr, ctx->pr_shadow, &pb));
-    NS3D_TRY(run_iterations(ctx, k, cur, nxt, dPrdtau, divV, n_iter, 0, pb, Pr));
+    double *dpc = dPrdtau, *dpn = nullptr;
+    if (use_tb2(ctx, p)) {
+        const size_t nd = (size_t)(p->nx - 2) * (p->ny - 2) * (p->nz - 2) + 3 * (size_t)(p->nx - 2) * (p->ny - 2) + 32;
+        NS3D_TRY(ensure_dp_shadow(ctx, nd));
+        dpn = ctx->dp_shadow;
+    }
+    NS3D_TRY(run_iterations(ctx, k, cur, nxt, dpc, dpn, divV, n_iter, 0, pb, Pr));
+    if (dpc != dPrdtau)
+        NS3D_CUDA(ctx, cudaMemcpyAsync(dPrdtau, dpc, (size_t)(p->nx - 2) * (p->ny - 2) * (p->nz - 2) * sizeof(double),
+                                       cudaMemcpyDeviceToDevice, ctx->stream));
     if (cur != Pr) NS3D_CUDA(ctx, cudaMemcpyAsync(Pr, cur, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     return NS3D_OK;
 }

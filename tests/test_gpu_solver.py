@@ -63,6 +63,46 @@ def test_fused_iteration_bit_exact(O, ns, ctx, variant, grid, zchunk):
             assert (got == f[name]).all(), f"{name} differs after {done} iterations ({(got != f[name]).sum()} values)"
 
 
+@pytest.mark.parametrize("variant", ["M", "G"])
+@pytest.mark.parametrize("grid", [(3, 3, 3), (5, 4, 3), (4, 3, 6), (37, 23, 19), (63, 38, 38), (70, 47, 41)])
+@pytest.mark.parametrize("zchunk", [0, 1, 2, 7])
+def test_two_iterations_per_launch_bit_exact(O, ns, ctx, variant, grid, zchunk):
+    """Temporal blocking (option "tb2"): 2 PT iterations per launch, rims recomputed, Pr^(1) kept in
+    shared memory.  Same per-cell arithmetic -> still bit-equal to the oracle; odd counts end with
+    one single-iteration launch, (70,47,41) spans 3x4 tiles and several z-chunks."""
+    p, f = pt_problem(O, variant, grid, 15)
+    s = setup_for(ns, variant, grid[0], ny=grid[1], nz=grid[2])
+    ctx.set_option("tb2", 1)
+    d = {k: ctx.from_host(f[k]) for k in ("Pr", "dPrdtau", "divV")}
+    done = 0
+    for n in (2, 1, 5, 40):
+        ctx.pt_iterate(d["Pr"], d["dPrdtau"], d["divV"], s.pt_params(zchunk), n)
+        for _ in range(n):
+            O.update_dPrdtau(p, f)
+            O.update_Pr(p, f)
+            O.set_bc_Pr(p, f)
+        done += n
+        for name in ("Pr", "dPrdtau"):
+            got = d[name].to_host()
+            bad = np.argwhere(got != f[name])
+            assert len(bad) == 0, f"{name} differs after {done} iterations: {len(bad)} values, first {bad[:3].tolist()}"
+
+
+@pytest.mark.parametrize("variant,nx,nt", [("M", 63, 4), ("G", 40, 2)])
+def test_time_steps_with_two_iterations_per_launch(O, ns, variant, nx, nt):
+    p = oracle_params(O, variant, nx)
+    f, iters_o, errs_o = O.run(p, nt)
+    c = ns.Context(0, ns.PARITY)
+    c.set_option("tb2", 1)
+    sim = ns.Simulation(setup_for(ns, variant, nx), c)
+    for _ in range(nt):
+        sim.step()
+    assert sim.iters == iters_o and sim.err_hist == errs_o
+    for name in ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C"):
+        assert (sim.host(name) == f[name]).all(), name
+    c.close()
+
+
 def test_outlet_guard_off(O, ns, ctx):
     """Variant M with the float == guard false (quirk 5): plain Neumann outlet."""
     p, f = pt_problem(O, "M", (20, 12, 12), 12)

@@ -13,6 +13,7 @@ ap.add_argument("--iters", type=int, default=200)
 ap.add_argument("--variant", default="G")
 ap.add_argument("--minb", default="0")
 ap.add_argument("--serp", default="1")
+ap.add_argument("--tb2", default="0")
 args = ap.parse_args()
 rng = np.random.default_rng(0)
 for g in args.grids.split(","):
@@ -28,6 +29,7 @@ for g in args.grids.split(","):
         for zc, minb, serp in [(z, m, sp) for sp in map(int, args.serp.split(",")) for m in map(int, args.minb.split(",")) for z in map(int, args.zchunks.split(","))]:
             ctx.set_option("pt_minb", minb)
             ctx.set_option("serpentine", serp)
+            ctx.set_option("tb2", int(args.tb2))
             pt = s.pt_params(zc)
             ctx.pt_iterate(Pr, dP, dv, pt, 20)
             ctx.sync()
