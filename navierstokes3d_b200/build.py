@@ -46,6 +46,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     cmd = [_nvcc(), *NVCC_FLAGS, "-Xptxas", "-v" if verbose else "-warn-spills",
            *[os.path.join(CSRC, s) for s in SOURCES], "-o", LIB, "-ldl"]
+    if os.path.exists(LIB):
+        os.remove(LIB)  # never leave a stale library behind a failed build
     env = dict(os.environ)
     env.pop("CC", None)  # the image exports a gcc wrapper that nvcc must not pick up
     res = subprocess.run(cmd, capture_output=True, text=True, env=env)

@@ -53,6 +53,12 @@ struct PtK {
     unsigned long long* mbox;          // this rank's mailbox (NS3D_MB_*)
     unsigned long long* peer_lo_flag;  // lower neighbour's NS3D_MB_FLAG_HI
     unsigned long long* peer_hi_flag;  // upper neighbour's NS3D_MB_FLAG_LO
+    // two-iterations-per-launch on slabs: the first iteration of the halo planes is recomputed
+    // locally, which needs one more plane of the neighbour's CURRENT iterate and its dPrdτ plane
+    const double* peer_lo_cur;  // lower neighbour's Pr plane nz-3   (= local plane -1)
+    const double* peer_hi_cur;  // upper neighbour's Pr plane 2      (= local plane nz)
+    const double* peer_lo_dp;   // lower neighbour's dPrdτ of its plane nz-2 (= local plane 0)
+    const double* peer_hi_dp;   // upper neighbour's dPrdτ of its plane 1    (= local plane nz-1)
     // byte strides, precomputed on the host so that the kernel takes them from the constant bank
     // instead of re-deriving 64-bit products under register pressure
     long long rowB, planeB, dplaneB;
@@ -313,10 +319,10 @@ __global__ void __launch_bounds__(256, MINB) pt_iter_kernel(const double* __rest
 // PARITY mode stays bit-equal to the oracle.  dPrdτ ping-pongs with a context-owned shadow
 // (rim columns of other CTAs read the old value while the owner writes the new one).
 // ---------------------------------------------------------------------------------------------
-constexpr int TB_X = 32, TB_Y = 16;
+constexpr int TB_X = 32;
 
-template <int MODE>
-__global__ void __launch_bounds__(TB_X* TB_Y, 2) pt_tb2_kernel(const double* __restrict__ Pr, double* __restrict__ PrN,
+template <int MODE, int TB_Y, bool P2P>
+__global__ void __launch_bounds__(TB_X* TB_Y, 1024 / (TB_X * TB_Y)) pt_tb2_kernel(const double* __restrict__ Pr, double* __restrict__ PrN,
                                                               const double* __restrict__ dP, double* __restrict__ dPN,
                                                               const double* __restrict__ divV, const PtK p)
 {
@@ -329,22 +335,48 @@ __global__ void __launch_bounds__(TB_X* TB_Y, 2) pt_tb2_kernel(const double* __r
     const int ci = min(max(i, 1), nx - 2), cj = min(max(j, 1), ny - 2);  // clamped into the interior
     const bool interior = in_dom && ci == i && cj == j;
     const bool owner = interior && tx >= 1 && tx <= TB_X - 2 && ty >= 1 && ty <= TB_Y - 2;  // stage-2 output
-    const int bz = p.reverse ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
+    int bz = blockIdx.z;
+    if (P2P) {  // the chunks next to a slab interface go first
+        const int nc = gridDim.z;
+        if (bz == 1) bz = nc - 1;
+        else if (bz >= 2) bz = p.reverse ? nc - bz : bz - 1;
+    } else if (p.reverse) {
+        bz = gridDim.z - 1 - bz;
+    }
     const int kb = p.kbeg + bz * p.zchunk;
     const int ke = min(kb + p.zchunk, p.kend);  // stage-2 planes [kb, ke)
-    const int s0 = max(kb - 1, 1), s1 = min(ke, nz - 2);  // stage-1 planes [s0, s1]
+    // On a slab interface the halo plane's first iteration is RECOMPUTED here (it is the
+    // neighbour's plane nz-2 / 1) from the local halo plane plus one peer plane.
+    const bool lo_face = P2P && p.zlo_halo && kb == 1;
+    const bool hi_face = P2P && p.zhi_halo && ke == nz - 1;
+    if (P2P && (lo_face | hi_face)) {
+        if (tx == 0 && ty == 0) {
+            if (lo_face) wait_neighbour(p.mbox, 0);
+            if (hi_face) wait_neighbour(p.mbox, 1);
+        }
+        __syncthreads();
+    }
+    const int s0 = lo_face ? 0 : max(kb - 1, 1);
+    const int s1 = hi_face ? nz - 1 : min(ke, nz - 2);  // stage-1 planes [s0, s1]
     const bool xl = (i == 1), xh = (i == nx - 2), yl = (j == 1), yh = (j == ny - 2);
     const long long rowB = p.rowB, planeB = p.planeB, dplaneB = p.dplaneB;
     const long long dDV = (const char*)divV - (const char*)Pr;
-    const char* c = (const char*)(Pr + idx3(ci, cj, s0, nx, ny));
-    const char* d = (const char*)(dP + idx3(ci - 1, cj - 1, s0 - 1, nx - 2, ny - 2));
+    const ptrdiff_t tcol = (ptrdiff_t)cj * nx + ci;                    // column offset in a Pr plane
+    const ptrdiff_t dcol = (ptrdiff_t)(cj - 1) * (nx - 2) + (ci - 1);  // ... in a dPrdτ plane
+    const char* c = (const char*)(Pr + (ptrdiff_t)s0 * nx * ny + tcol);
+    const char* d = (const char*)(dP + ((ptrdiff_t)s0 - 1) * (nx - 2) * (ny - 2) + dcol);
 #define LD(ptr) (*(const double*)(ptr))
     double pm = 0, pc = 0, zp = 0, dq = 0, dv = 0;
     if (in_dom) {
-        pm = LD(c - planeB);
+        if (P2P && lo_face) {  // plane -1 and the dPrdτ of plane 0 live on the lower neighbour
+            pm = __ldcv(p.peer_lo_cur + tcol);
+            dq = __ldcv(p.peer_lo_dp + dcol);
+        } else {
+            pm = LD(c - planeB);
+            dq = LD(d);
+        }
         pc = LD(c);
         zp = LD(c + planeB);
-        dq = LD(d);
         dv = LD(c + dDV);
     }
     double q_m = 0, q_c = 0, d1_c = 0, dv_c = 0;  // stage-2 state of plane s-1 (and q of s-2)
@@ -352,8 +384,13 @@ __global__ void __launch_bounds__(TB_X* TB_Y, 2) pt_tb2_kernel(const double* __r
         // prefetch the three streamed values of plane s+1 (the allocator pads the arrays)
         double n_zp = 0, n_dq = 0, n_dv = 0;
         if (in_dom) {
-            n_zp = LD(c + 2 * planeB);
-            n_dq = LD(d + dplaneB);
+            if (P2P && hi_face && s == nz - 2) {  // plane nz and the dPrdτ of plane nz-1: upper neighbour
+                n_zp = __ldcv(p.peer_hi_cur + tcol);
+                n_dq = __ldcv(p.peer_hi_dp + dcol);
+            } else {
+                n_zp = LD(c + 2 * planeB);
+                n_dq = LD(d + dplaneB);
+            }
             n_dv = LD(c + planeB + dDV);
         }
         // ---- stage 1: first iteration at the clamped column, plane s ---------------------------
@@ -387,12 +424,16 @@ __global__ void __launch_bounds__(TB_X* TB_Y, 2) pt_tb2_kernel(const double* __r
             }
             dPN[idx3(i - 1, j - 1, k2 - 1, nx - 2, ny - 2)] = d2;
             store_plane(p, PrN + (ptrdiff_t)k2 * (ptrdiff_t)nx * ny, i, j, k2, u, xl, xh, yl, yh);
-            if (k2 == 1) store_plane(p, PrN, i, j, 0, u, xl, xh, yl, yh);  // bc_z! M:129
+            if (k2 == 1) {
+                if (!p.zlo_halo) store_plane(p, PrN, i, j, 0, u, xl, xh, yl, yh);  // bc_z! M:129
+                else if (P2P) store_plane(p, p.peer_lo_plane, i, j, k2, u, xl, xh, yl, yh);  // update_halo!(Pr)
+            }
+            if (P2P && k2 == nz - 2 && p.zhi_halo) store_plane(p, p.peer_hi_plane, i, j, k2, u, xl, xh, yl, yh);
         }
         // rotate: plane s becomes "s-1"
         q_m = q_c;
         q_c = q;
-        if (s == 1) {  // bc_z!: q[0] is the image of q[1] (hydrostatic x faces depend on the plane)
+        if (s == 1 && !p.zlo_halo) {  // bc_z!: q[0] is the image of q[1] (hydrostatic x faces depend on the plane)
             q_m = q;
             if (i == 0) q_m = xface(p, false, 0, q);
             if (i == nx - 1) q_m = xface(p, true, 0, q);
@@ -403,8 +444,8 @@ __global__ void __launch_bounds__(TB_X* TB_Y, 2) pt_tb2_kernel(const double* __r
         c += planeB;
         d += dplaneB;
     }
-    // last chunk: plane nz-2 needs q[nz-1], the image of q[nz-2]
-    if (s1 == nz - 2 && ke == nz - 1 && owner) {
+    // physical top face: plane nz-2 needs q[nz-1], the image of q[nz-2]
+    if (!p.zhi_halo && s1 == nz - 2 && ke == nz - 1 && owner) {
         const int k2 = nz - 2;
         double q_p = q_c;
         const double(*rp)[TB_X] = ring[k2 % 3];
@@ -419,10 +460,22 @@ __global__ void __launch_bounds__(TB_X* TB_Y, 2) pt_tb2_kernel(const double* __r
         }
         dPN[idx3(i - 1, j - 1, k2 - 1, nx - 2, ny - 2)] = d2;
         store_plane(p, PrN + (ptrdiff_t)k2 * (ptrdiff_t)nx * ny, i, j, k2, u, xl, xh, yl, yh);
-        if (k2 == 1) store_plane(p, PrN, i, j, 0, u, xl, xh, yl, yh);
+        if (k2 == 1) {
+            if (!p.zlo_halo) store_plane(p, PrN, i, j, 0, u, xl, xh, yl, yh);
+            else if (P2P) store_plane(p, p.peer_lo_plane, i, j, k2, u, xl, xh, yl, yh);
+        }
         store_plane(p, PrN + (ptrdiff_t)(nz - 1) * (ptrdiff_t)nx * ny, i, j, nz - 1, u, xl, xh, yl, yh);  // bc_z! M:130
     }
 #undef LD
+    if (P2P && (lo_face | hi_face)) {
+        __threadfence_system();
+        __syncthreads();
+        if (tx == 0 && ty == 0) {
+            const unsigned nface = gridDim.x * gridDim.y;
+            if (lo_face) signal_neighbour(p.mbox, 0, p.peer_lo_flag, nface);
+            if (hi_face) signal_neighbour(p.mbox, 1, p.peer_hi_flag, nface);
+        }
+    }
 }
 
 // compute_res! + abs + maximum (K8 + K8') in one pass, no Rp array: max over the interior of
@@ -584,16 +637,65 @@ int launch_iter(ns3d_ctx* ctx, cudaStream_t st, const PtK& k, const double* cur,
     return NS3D_OK;
 }
 
-int launch_tb2(ns3d_ctx* ctx, const PtK& k, const double* cur, double* nxt, const double* dpc, double* dpn,
-               const double* divV)
+// Neighbours' buffers mapped through CUDA IPC (see peer_prepare).
+struct PeerBufs {
+    bool on = false;
+    bool tb2 = false;                                       // dPrdτ buffers mapped too
+    double* lo[4] = {nullptr, nullptr, nullptr, nullptr};  // lower neighbour's {Pr, Pr shadow, dPrdτ, dPrdτ shadow}
+    double* hi[4] = {nullptr, nullptr, nullptr, nullptr};  // upper neighbour's
+    const double* dP_user = nullptr;
+};
+
+// Balanced z-chunks whose last one keeps at least two planes: on slabs a neighbour reads plane
+// nz-3 (resp. 2) of this rank, and the CTAs that own it are the ones holding the hand-over flag.
+void balance_chunks(PtK& k)
 {
-    const dim3 blk(TB_X, TB_Y, 1);
-    const dim3 grd(cdiv(k.nx - 2, TB_X - 2), cdiv(k.ny - 2, TB_Y - 2), cdiv(k.kend - k.kbeg, k.zchunk));
-    switch (ctx->mode) {
-        case NS3D_PARITY: pt_tb2_kernel<NS3D_PARITY><<<grd, blk, 0, ctx->stream>>>(cur, nxt, dpc, dpn, divV, k); break;
-        case NS3D_FAST: pt_tb2_kernel<NS3D_FAST><<<grd, blk, 0, ctx->stream>>>(cur, nxt, dpc, dpn, divV, k); break;
-        default: pt_tb2_kernel<NS3D_FASTEST><<<grd, blk, 0, ctx->stream>>>(cur, nxt, dpc, dpn, divV, k); break;
+    const int n = k.kend - k.kbeg;
+    int nch = (n + k.zchunk - 1) / k.zchunk;
+    int len = (n + nch - 1) / nch;
+    if (nch > 1 && n - (nch - 1) * len == 1) {
+        nch -= 1;
+        len = (n + nch - 1) / nch;
     }
+    k.zchunk = len;
+}
+
+int launch_tb2(ns3d_ctx* ctx, const PtK& k_in, const double* cur, double* nxt, const double* dpc, double* dpn,
+               const double* divV, const PeerBufs& pb, const double* Pr_user)
+{
+    PtK k = k_in;
+    balance_chunks(k);
+    if (pb.on && pb.tb2) {
+        const int wp = (nxt == Pr_user) ? 0 : 1;        // neighbours' NEW iterate: same role as ours
+        const int wc = 1 - wp;                          // ... CURRENT iterate
+        const int wd = (dpc == pb.dP_user) ? 2 : 3;     // ... CURRENT dPrdτ
+        const ptrdiff_t sxy = (ptrdiff_t)k.nx * k.ny, dxy = (ptrdiff_t)(k.nx - 2) * (k.ny - 2);
+        k.mbox = ctx->mbox;
+        k.peer_lo_plane = pb.lo[wp] ? pb.lo[wp] + (ptrdiff_t)(k.nz - 1) * sxy : nullptr;
+        k.peer_hi_plane = pb.hi[wp];
+        k.peer_lo_cur = pb.lo[wc] ? pb.lo[wc] + (ptrdiff_t)(k.nz - 3) * sxy : nullptr;
+        k.peer_hi_cur = pb.hi[wc] ? pb.hi[wc] + 2 * sxy : nullptr;
+        k.peer_lo_dp = pb.lo[wd] ? pb.lo[wd] + (ptrdiff_t)(k.nz - 3) * dxy : nullptr;
+        k.peer_hi_dp = pb.hi[wd];
+        k.peer_lo_flag = ctx->peer_mbox[0] ? ctx->peer_mbox[0] + NS3D_MB_FLAG_HI : nullptr;
+        k.peer_hi_flag = ctx->peer_mbox[1] ? ctx->peer_mbox[1] + NS3D_MB_FLAG_LO : nullptr;
+    }
+    const int ty = k.mbox ? 16 : (ctx->opt_tb2_ty == 8 ? 8 : (ctx->opt_tb2_ty == 32 ? 32 : 16));
+    const dim3 blk(TB_X, ty, 1);
+    const dim3 grd(cdiv(k.nx - 2, TB_X - 2), cdiv(k.ny - 2, ty - 2), cdiv(k.kend - k.kbeg, k.zchunk));
+#define TB_LAUNCH(MODE)                                                                                        \
+    do {                                                                                                       \
+        if (k.mbox) pt_tb2_kernel<MODE, 16, true><<<grd, blk, 0, ctx->stream>>>(cur, nxt, dpc, dpn, divV, k);          \
+        else if (ty == 8) pt_tb2_kernel<MODE, 8, false><<<grd, blk, 0, ctx->stream>>>(cur, nxt, dpc, dpn, divV, k);    \
+        else if (ty == 32) pt_tb2_kernel<MODE, 32, false><<<grd, blk, 0, ctx->stream>>>(cur, nxt, dpc, dpn, divV, k);  \
+        else pt_tb2_kernel<MODE, 16, false><<<grd, blk, 0, ctx->stream>>>(cur, nxt, dpc, dpn, divV, k);                \
+    } while (0)
+    switch (ctx->mode) {
+        case NS3D_PARITY: TB_LAUNCH(NS3D_PARITY); break;
+        case NS3D_FAST: TB_LAUNCH(NS3D_FAST); break;
+        default: TB_LAUNCH(NS3D_FASTEST); break;
+    }
+#undef TB_LAUNCH
     NS3D_LAUNCH_CHECK(ctx);
     return NS3D_OK;
 }
@@ -603,9 +705,10 @@ int launch_tb2(ns3d_ctx* ctx, const PtK& k, const double* cur, double* nxt, cons
 // single-iteration kernel is latency/issue-bound and L2 already serves part of the traffic.  Slabs
 // keep the single-iteration kernel (the rim of a two-iteration update would need a second halo
 // plane), so the automatic policy is: single rank and a working set far beyond L2.
-bool use_tb2(const ns3d_ctx* ctx, const ns3d_pt_params* p)
+bool use_tb2(const ns3d_ctx* ctx, const ns3d_pt_params* p, bool peer_on)
 {
-    if (ctx->nranks != 1 || ctx->opt_tb2 == 0) return false;
+    if (ctx->opt_tb2 == 0) return false;
+    if (ctx->nranks > 1 && !peer_on) return false;  // slabs: needs the peer-memory path
     if (ctx->opt_tb2 > 0) return true;
     return 4.0 * 8.0 * p->nx * p->ny * p->nz >= 6.0 * ctx->l2_bytes;
 }
@@ -615,6 +718,12 @@ int ensure_dp_shadow(ns3d_ctx* ctx, size_t count)
     if (ctx->dp_shadow_count >= count) return NS3D_OK;
     if (ctx->dp_shadow) {
         NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        auto it = ctx->p2p_map.find(ctx->dp_shadow);
+        if (it != ctx->p2p_map.end()) {
+            if (it->second.first) cudaIpcCloseMemHandle(it->second.first);
+            if (it->second.second) cudaIpcCloseMemHandle(it->second.second);
+            ctx->p2p_map.erase(it);
+        }
         NS3D_CUDA(ctx, cudaFree(ctx->dp_shadow));
         ctx->dp_shadow = nullptr;
         ctx->dp_shadow_count = 0;
@@ -661,12 +770,6 @@ int pt_begin(ns3d_ctx* ctx)
 
 // Peer-memory path usable for this solve?  Maps the neighbours' copies of both ping-pong buffers
 // on first use (collective: every rank reaches this point with its own Pr / shadow).
-struct PeerBufs {
-    bool on = false;
-    double* lo[2] = {nullptr, nullptr};  // lower neighbour's {Pr, shadow}
-    double* hi[2] = {nullptr, nullptr};  // upper neighbour's {Pr, shadow}
-};
-
 int peer_prepare(ns3d_ctx* ctx, const PtK& k, double* Pr, double* shadow, PeerBufs* pb)
 {
     pb->on = false;
@@ -680,10 +783,39 @@ int peer_prepare(ns3d_ctx* ctx, const PtK& k, double* Pr, double* shadow, PeerBu
     return NS3D_OK;
 }
 
+// The two-iterations-per-launch kernel also reads the neighbours' dPrdτ (both ping-pong buffers).
+int peer_prepare_tb2(ns3d_ctx* ctx, double* dP, double* dp_shadow, PeerBufs* pb)
+{
+    if (!pb->on) return NS3D_OK;
+    void *l2, *h2, *l3, *h3;
+    NS3D_TRY(ns3d_internal_p2p_map(ctx, dP, &l2, &h2));
+    NS3D_TRY(ns3d_internal_p2p_map(ctx, dp_shadow, &l3, &h3));
+    pb->lo[2] = (double*)l2; pb->hi[2] = (double*)h2;
+    pb->lo[3] = (double*)l3; pb->hi[3] = (double*)h3;
+    pb->dP_user = dP;
+    pb->tb2 = true;
+    return NS3D_OK;
+}
+
 int pt_iteration(ns3d_ctx* ctx, const PtK& k, const double* cur, double* nxt, double* dP, const double* divV,
                  const PeerBufs& pb, const double* Pr_user)
 {
     if (ctx->nranks == 1) return launch_iter(ctx, ctx->stream, k, cur, nxt, dP, divV);
+    if (pb.on && pb.tb2) {
+        // Next to two-iterations-per-launch kernels (whose face CTAs read the neighbour's planes 2
+        // and nz-3) a single iteration is one unsplit launch: the CTAs that own those planes are
+        // then the ones that signal.
+        PtK q = k;
+        const int which = (nxt == Pr_user) ? 0 : 1;
+        const ptrdiff_t sxy = (ptrdiff_t)k.nx * k.ny;
+        balance_chunks(q);
+        q.mbox = ctx->mbox;
+        q.peer_lo_plane = pb.lo[which] ? pb.lo[which] + (ptrdiff_t)(k.nz - 1) * sxy : nullptr;
+        q.peer_hi_plane = pb.hi[which];
+        q.peer_lo_flag = ctx->peer_mbox[0] ? ctx->peer_mbox[0] + NS3D_MB_FLAG_HI : nullptr;
+        q.peer_hi_flag = ctx->peer_mbox[1] ? ctx->peer_mbox[1] + NS3D_MB_FLAG_LO : nullptr;
+        return launch_iter(ctx, ctx->stream, q, cur, nxt, dP, divV);
+    }
     if (pb.on) {
         // The update of the two planes a slab sends and their delivery are ONE kernel: the face
         // CTAs store the new values into the neighbour's halo plane (peer memory over NVLink) and
@@ -772,11 +904,12 @@ int run_direct(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double*& dP, d
         k2.zchunk = k.zchunk_tb;
         for (; q + 2 <= n; q += 2) {
             k2.reverse = k.serpentine && (((iter0 + q) >> 1) & 1);
-            NS3D_TRY(launch_tb2(ctx, k2, cur, nxt, dP, dPn, divV));
+            NS3D_TRY(launch_tb2(ctx, k2, cur, nxt, dP, dPn, divV, pb, Pr_user));
             double* t = cur; cur = nxt; nxt = t;
             t = dP; dP = dPn; dPn = t;
         }
     }
+    if (q > 0 && q < n) NS3D_TRY(pt_begin(ctx));  // the split path forks from HERE, not from the chunk start
     for (; q < n; ++q) {
         k.reverse = k.serpentine && ((iter0 + q) & 1);
         NS3D_TRY(pt_iteration(ctx, k, cur, nxt, dP, divV, pb, Pr_user));
@@ -883,10 +1016,11 @@ extern "C" int ns3d_pt_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const d
     PeerBufs pb;
     NS3D_TRY(peer_prepare(ctx, k, Pr, ctx->pr_shadow, &pb));
     double *dpc = dPrdtau, *dpn = nullptr;
-    if (use_tb2(ctx, p)) {
+    if (use_tb2(ctx, p, pb.on)) {
         const size_t nd = (size_t)(p->nx - 2) * (p->ny - 2) * (p->nz - 2) + 3 * (size_t)(p->nx - 2) * (p->ny - 2) + 32;
         NS3D_TRY(ensure_dp_shadow(ctx, nd));
         dpn = ctx->dp_shadow;
+        NS3D_TRY(peer_prepare_tb2(ctx, dPrdtau, ctx->dp_shadow, &pb));
     }
     while (iters < p->niter) {
         const int chunk = std::min(p->nchk - iters % p->nchk, p->niter - iters);  // up to the next check
@@ -933,10 +1067,11 @@ extern "C" int ns3d_pt_iterate(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const
     PeerBufs pb;
     NS3D_TRY(peer_prepare(ctx, k, Pr, ctx->pr_shadow, &pb));
     double *dpc = dPrdtau, *dpn = nullptr;
-    if (use_tb2(ctx, p)) {
+    if (use_tb2(ctx, p, pb.on)) {
         const size_t nd = (size_t)(p->nx - 2) * (p->ny - 2) * (p->nz - 2) + 3 * (size_t)(p->nx - 2) * (p->ny - 2) + 32;
         NS3D_TRY(ensure_dp_shadow(ctx, nd));
         dpn = ctx->dp_shadow;
+        NS3D_TRY(peer_prepare_tb2(ctx, dPrdtau, ctx->dp_shadow, &pb));
     }
     NS3D_TRY(run_iterations(ctx, k, cur, nxt, dpc, dpn, divV, n_iter, 0, pb, Pr));
     if (dpc != dPrdtau)

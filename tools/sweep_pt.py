@@ -14,6 +14,7 @@ ap.add_argument("--variant", default="G")
 ap.add_argument("--minb", default="0")
 ap.add_argument("--serp", default="1")
 ap.add_argument("--tb2", default="0")
+ap.add_argument("--tb2ty", default="16")
 args = ap.parse_args()
 rng = np.random.default_rng(0)
 for g in args.grids.split(","):
@@ -26,7 +27,8 @@ for g in args.grids.split(","):
         Pr = ctx.from_host(np.asfortranarray(rng.uniform(-1, 1, size=(nx, ny, nz))))
         dP = ctx.zeros(nx - 2, ny - 2, nz - 2)
         dv = ctx.from_host(np.asfortranarray(rng.uniform(-1e-3, 1e-3, size=(nx, ny, nz))))
-        for zc, minb, serp in [(z, m, sp) for sp in map(int, args.serp.split(",")) for m in map(int, args.minb.split(",")) for z in map(int, args.zchunks.split(","))]:
+        for zc, minb, serp, tbty in [(z, m, sp, t) for t in map(int, args.tb2ty.split(",")) for sp in map(int, args.serp.split(",")) for m in map(int, args.minb.split(",")) for z in map(int, args.zchunks.split(","))]:
+            ctx.set_option("tb2_ty", tbty)
             ctx.set_option("pt_minb", minb)
             ctx.set_option("serpentine", serp)
             ctx.set_option("tb2", int(args.tb2))
@@ -41,6 +43,6 @@ for g in args.grids.split(","):
                 e1.record(stream)
                 ctx.sync()
                 best = min(best, e0.elapsed_time(e1) / args.iters * 1e3)
-            print(json.dumps({"grid": g, "mode": mode, "zchunk": zc, "minb": minb, "serp": serp, "us_per_iter": round(best, 2),
+            print(json.dumps({"grid": g, "mode": mode, "zchunk": zc, "minb": minb, "serp": serp, "tb2": int(args.tb2), "tb2_ty": tbty, "us_per_iter": round(best, 2),
                               "T_eff_GBs": round(40.0 * n / best / 1e3, 1)}), flush=True)
         ctx.close()
