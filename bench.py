@@ -312,11 +312,14 @@ def main():
     ctx.sync()
     t_launch = k0.elapsed_time(k1) / 1e3 / n_probe
     peak, peak_src = hbm_peak()
-    achieved = 40.0 * n_cells / t_launch / 1e9
+    tb2_on = "tb2=0" not in args.opt     # default path: pt_tb2_kernel, two PT iterations per launch
+    per_launch = 2 if tb2_on else 1
+    t_launch *= per_launch
+    achieved = 40.0 * per_launch * n_cells / t_launch / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get(f"{args.workload}:{args.mode}")
+            traffic = json.load(fh).get(f"{args.workload}:{args.mode}" + (":tb2" if tb2_on else ""))
     except Exception:  # noqa: BLE001
         pass
 
@@ -411,11 +414,14 @@ def main():
             "t_eff_per_gpu": teff / world, "frac_of_hbm_peak_per_gpu": teff / world / peak,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "pt_iter_kernel (fused K5+K6+set_bc_Pr!)", "achieved": achieved,
+            "roofline": {"bound": "hbm",
+                         "kernel": ("pt_tb2_kernel (two fused PT iterations per launch: 2 x (K5+K6+set_bc_Pr!))" if tb2_on
+                                    else "pt_iter_kernel (fused K5+K6+set_bc_Pr!)"),
+                         "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "us_per_launch": t_launch * 1e6,
-                         "algorithmic_bytes_per_launch": 40.0 * n_cells,
-                         "share_of_step": (sum(iters) / args.steps) * t_launch / (t_all / args.steps)},
+                         "algorithmic_bytes_per_launch": 40.0 * per_launch * n_cells,
+                         "share_of_step": (sum(iters) / args.steps) * (t_launch / per_launch) / (t_all / args.steps)},
         }
         if parity:
             line["parity_check"] = parity

@@ -174,7 +174,7 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
         return NS3D_OK;
     }
     if (!strcmp(name, "tb2")) {
-        ctx->opt_tb2 = value < 0 ? -1 : (value != 0);
+        ctx->opt_tb2 = value != 0;
         return NS3D_OK;
     }
     if (!strcmp(name, "tb2_ty")) {

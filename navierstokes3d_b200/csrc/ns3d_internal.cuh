@@ -43,7 +43,7 @@ struct ns3d_ctx {
     // tuning knobs (ns3d_set_option)
     int opt_pt_minb = 0;  // 0 = per-mode default
     int opt_serpentine = -1;  // -1 = by working-set size
-    int opt_tb2 = -1;         // two PT iterations per launch: -1 = when the working set is far beyond L2 (single rank)
+    int opt_tb2 = 1;          // two PT iterations per launch (pt_tb2_kernel); 0 = one-iteration kernel only
     int opt_tb2_ty = 16;      // tile height of pt_tb2_kernel (8, 16 or 32)
     int opt_graphs = 1;       // replay chunks of PT iterations as CUDA graphs
     long long halo_calls = 0; // uncaptured halo exchanges so far (NCCL peers connected)

@@ -336,15 +336,16 @@ __global__ void __launch_bounds__(TB_X* TB_Y, 1024 / (TB_X * TB_Y)) pt_tb2_kerne
     const bool interior = in_dom && ci == i && cj == j;
     const bool owner = interior && tx >= 1 && tx <= TB_X - 2 && ty >= 1 && ty <= TB_Y - 2;  // stage-2 output
     int bz = blockIdx.z;
-    if (P2P) {  // the chunks next to a slab interface go first
+    if (P2P && !p.faces) {  // the chunks next to a slab interface go first
         const int nc = gridDim.z;
         if (bz == 1) bz = nc - 1;
         else if (bz >= 2) bz = p.reverse ? nc - bz : bz - 1;
-    } else if (p.reverse) {
+    } else if (p.reverse && !p.faces) {
         bz = gridDim.z - 1 - bz;
     }
-    const int kb = p.kbeg + bz * p.zchunk;
-    const int ke = min(kb + p.zchunk, p.kend);  // stage-2 planes [kb, ke)
+    // faces launch: only the two chunks of p.zchunk planes next to the z faces
+    const int kb = p.faces ? (bz == 0 ? 1 : nz - 1 - p.zchunk) : p.kbeg + bz * p.zchunk;
+    const int ke = p.faces ? kb + p.zchunk : min(kb + p.zchunk, p.kend);  // stage-2 planes [kb, ke)
     // On a slab interface the halo plane's first iteration is RECOMPUTED here (it is the
     // neighbour's plane nz-2 / 1) from the local halo plane plus one peer plane.
     const bool lo_face = P2P && p.zlo_halo && kb == 1;
@@ -660,12 +661,12 @@ void balance_chunks(PtK& k)
     k.zchunk = len;
 }
 
-int launch_tb2(ns3d_ctx* ctx, const PtK& k_in, const double* cur, double* nxt, const double* dpc, double* dpn,
-               const double* divV, const PeerBufs& pb, const double* Pr_user)
+int launch_tb2(ns3d_ctx* ctx, cudaStream_t st, const PtK& k_in, const double* cur, double* nxt, const double* dpc,
+               double* dpn, const double* divV, const PeerBufs& pb, const double* Pr_user, bool peer)
 {
     PtK k = k_in;
-    balance_chunks(k);
-    if (pb.on && pb.tb2) {
+    if (!k.faces) balance_chunks(k);
+    if (peer) {
         const int wp = (nxt == Pr_user) ? 0 : 1;        // neighbours' NEW iterate: same role as ours
         const int wc = 1 - wp;                          // ... CURRENT iterate
         const int wd = (dpc == pb.dP_user) ? 2 : 3;     // ... CURRENT dPrdτ
@@ -682,13 +683,13 @@ int launch_tb2(ns3d_ctx* ctx, const PtK& k_in, const double* cur, double* nxt, c
     }
     const int ty = k.mbox ? 16 : (ctx->opt_tb2_ty == 8 ? 8 : (ctx->opt_tb2_ty == 32 ? 32 : 16));
     const dim3 blk(TB_X, ty, 1);
-    const dim3 grd(cdiv(k.nx - 2, TB_X - 2), cdiv(k.ny - 2, ty - 2), cdiv(k.kend - k.kbeg, k.zchunk));
+    const dim3 grd(cdiv(k.nx - 2, TB_X - 2), cdiv(k.ny - 2, ty - 2), k.faces ? 2u : cdiv(k.kend - k.kbeg, k.zchunk));
 #define TB_LAUNCH(MODE)                                                                                        \
     do {                                                                                                       \
-        if (k.mbox) pt_tb2_kernel<MODE, 16, true><<<grd, blk, 0, ctx->stream>>>(cur, nxt, dpc, dpn, divV, k);          \
-        else if (ty == 8) pt_tb2_kernel<MODE, 8, false><<<grd, blk, 0, ctx->stream>>>(cur, nxt, dpc, dpn, divV, k);    \
-        else if (ty == 32) pt_tb2_kernel<MODE, 32, false><<<grd, blk, 0, ctx->stream>>>(cur, nxt, dpc, dpn, divV, k);  \
-        else pt_tb2_kernel<MODE, 16, false><<<grd, blk, 0, ctx->stream>>>(cur, nxt, dpc, dpn, divV, k);                \
+        if (k.mbox) pt_tb2_kernel<MODE, 16, true><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);          \
+        else if (ty == 8) pt_tb2_kernel<MODE, 8, false><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);    \
+        else if (ty == 32) pt_tb2_kernel<MODE, 32, false><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);  \
+        else pt_tb2_kernel<MODE, 16, false><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);                \
     } while (0)
     switch (ctx->mode) {
         case NS3D_PARITY: TB_LAUNCH(NS3D_PARITY); break;
@@ -700,17 +701,16 @@ int launch_tb2(ns3d_ctx* ctx, const PtK& k_in, const double* cur, double* nxt, c
     return NS3D_OK;
 }
 
-// Two iterations per launch pay where the loop is DRAM-bound: measured +27 % at 511^3 (675 vs
-// 856 us/iteration, T_eff above the HBM copy peak) but only +5 % at 255x153x153, where the
-// single-iteration kernel is latency/issue-bound and L2 already serves part of the traffic.  Slabs
-// keep the single-iteration kernel (the rim of a two-iteration update would need a second halo
-// plane), so the automatic policy is: single rank and a working set far beyond L2.
+// Two iterations per launch is the default path wherever it applies (single rank, or slabs with
+// the peer-memory halo path): measured sustained gains +11 % at 255x153x153 (T_eff 6.36 TB/s),
+// +27 % at 511^3 (7.9-8.1 TB/s, above the HBM copy peak), +9.5 % per GPU on two slabs
+// (profiles/r01_tb2_*.jsonl).  ns3d_set_option("tb2", 0) selects the one-iteration kernel.
 bool use_tb2(const ns3d_ctx* ctx, const ns3d_pt_params* p, bool peer_on)
 {
+    (void)p;
     if (ctx->opt_tb2 == 0) return false;
     if (ctx->nranks > 1 && !peer_on) return false;  // slabs: needs the peer-memory path
-    if (ctx->opt_tb2 > 0) return true;
-    return 4.0 * 8.0 * p->nx * p->ny * p->nz >= 6.0 * ctx->l2_bytes;
+    return true;
 }
 
 int ensure_dp_shadow(ns3d_ctx* ctx, size_t count)
@@ -902,9 +902,29 @@ int run_direct(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double*& dP, d
     if (dPn) {  // two iterations per launch; Pr and dPrdτ both ping-pong
         PtK k2 = k;
         k2.zchunk = k.zchunk_tb;
+        const bool peer = pb.on && pb.tb2;
+        const int zf = 8;  // planes per face chunk of the split slab launch
+        const bool split = peer && (k.nz - 2) >= 2 * zf + 4;
         for (; q + 2 <= n; q += 2) {
             k2.reverse = k.serpentine && (((iter0 + q) >> 1) & 1);
-            NS3D_TRY(launch_tb2(ctx, k2, cur, nxt, dP, dPn, divV, pb, Pr_user));
+            if (split) {
+                // slabs: the two chunks next to the interfaces (peer loads/stores, mailbox flags) run
+                // on the high-priority stream beside the launch that updates the other planes with
+                // the plain variant; same event protocol as the single-iteration path
+                PtK f = k2, in = k2;
+                f.faces = 1;
+                f.zchunk = zf;
+                in.kbeg = 1 + zf;
+                in.kend = k.nz - 1 - zf;
+                NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_a, 0));
+                NS3D_TRY(launch_tb2(ctx, ctx->comm_stream, f, cur, nxt, dP, dPn, divV, pb, Pr_user, true));
+                NS3D_CUDA(ctx, cudaEventRecord(ctx->ev_b, ctx->comm_stream));
+                NS3D_TRY(launch_tb2(ctx, ctx->stream, in, cur, nxt, dP, dPn, divV, pb, Pr_user, false));
+                NS3D_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+                NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
+            } else {
+                NS3D_TRY(launch_tb2(ctx, ctx->stream, k2, cur, nxt, dP, dPn, divV, pb, Pr_user, peer));
+            }
             double* t = cur; cur = nxt; nxt = t;
             t = dP; dP = dPn; dPn = t;
         }

@@ -25,7 +25,8 @@ def free_port():
 
 
 @pytest.mark.parametrize("world,grid,nt,lz,level", [(2, (40, 24, 13), 4, None, "fused"), (2, (40, 24, 13), 2, None, "level1"),
-                                                     (2, (40, 24, 13), 4, None, "tb2"), (4, (40, 24, 10), 3, 34 / 40, "tb2"),
+                                                     (2, (40, 24, 13), 4, None, "tb2"), (2, (40, 24, 26), 3, 50 / 40, "tb2"),
+                                                     (4, (40, 24, 10), 3, 34 / 40, "tb2"),
                                                      (8, (40, 24, 6), 3, 34 / 40, "tb2"),
                                                      (4, (40, 24, 10), 3, 34 / 40, "fused"), (8, (40, 24, 6), 3, 34 / 40, "fused")])
 def test_slabs_match_igg_emulation(world, grid, nt, lz, level):

@@ -9,6 +9,9 @@ zc = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 nx, ny, nz = map(int, g.split("x"))
 s = ns.setup_gpu(nx, ny=ny, nz=nz)
 ctx = ns.Context(0, getattr(ns, mode))
+ctx.set_option("graphs", 0)
+if len(sys.argv) > 4:
+    ctx.set_option("tb2", int(sys.argv[4]))
 rng = np.random.default_rng(0)
 Pr = ctx.from_host(np.asfortranarray(rng.uniform(-1, 1, size=(nx, ny, nz))))
 dP = ctx.zeros(nx - 2, ny - 2, nz - 2)
