@@ -11,6 +11,7 @@
 #include <unordered_map>
 
 #include "../../include/ns3d.h"
+#include "ns3d_shared.cuh"
 
 struct ns3d_ctx {
     int device = 0;
@@ -45,6 +46,7 @@ struct ns3d_ctx {
     int opt_serpentine = -1;  // -1 = by working-set size
     int opt_tb2 = 1;          // two PT iterations per launch (pt_tb2_kernel); 0 = one-iteration kernel only
     int opt_tb2_ty = 16;      // tile height of pt_tb2_kernel (8, 16 or 32)
+    int opt_tb2_slim = 1;     // plain two-iteration launches use pt_tb2s_kernel (0 = pt_tb2_kernel)
     int opt_graphs = 1;       // replay chunks of PT iterations as CUDA graphs
     long long halo_calls = 0; // uncaptured halo exchanges so far (NCCL peers connected)
     void* pt_graphs = nullptr;  // graph cache owned by ns3d_pt.cu
@@ -81,12 +83,6 @@ int ns3d_fail(ns3d_ctx* ctx, int code, const char* fmt, ...);
         if (rc__ != NS3D_OK) return rc__; \
     } while (0)
 
-// 0-based column-major index into an array with leading sizes (sx, sy).
-__host__ __device__ __forceinline__ size_t idx3(int i, int j, int k, int sx, int sy)
-{
-    return (size_t)i + (size_t)sx * ((size_t)j + (size_t)sy * (size_t)k);
-}
-
 static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
 // Bit pattern of |x|: for non-negative doubles the unsigned order of the patterns is the
@@ -122,18 +118,6 @@ __device__ __forceinline__ void block_max_to_global(unsigned long long v, unsign
         if (tid == 0 && v != 0ULL) atomicMax(out, v);
     }
 }
-
-// mailbox words
-enum {
-    NS3D_MB_FLAG_LO = 0,    // written by the lower neighbour: epochs whose face work it has finished
-    NS3D_MB_FLAG_HI = 1,    // same, upper neighbour
-    NS3D_MB_ARRIVE_LO = 2,  // face CTAs of the running launch that are done (reset by the last one)
-    NS3D_MB_ARRIVE_HI = 3,
-    NS3D_MB_EPOCH_LO = 4,   // launches whose lower-face work is complete on this rank
-    NS3D_MB_EPOCH_HI = 5,
-    NS3D_MB_ERROR = 6,      // set when a spin-wait timed out
-    NS3D_MB_WORDS = 16
-};
 
 // internal cross-TU entry points
 int ns3d_internal_p2p_map(ns3d_ctx* ctx, const void* local_base, void** peer_lo, void** peer_hi);

@@ -1,0 +1,107 @@
+// Host emulation of the fused PT kernels (test infrastructure, see cuda_host_shim.h): the device
+// code of navierstokes3d_b200/csrc/ns3d_pt_kernels.cuh compiled by g++ and driven like
+// run_direct() in ns3d_pt.cu drives it on one rank.  tests/test_kernel_emu.py compares the
+// result bit for bit with the CPU oracle.
+//
+//   g++ -O1 -ffp-contract=off -std=c++17 -shared -fPIC -pthread pt_emu.cpp -o _build/libpt_emu.so
+#include "cuda_host_shim.h"
+
+#include <cstring>
+#include <limits>
+
+#include "../../navierstokes3d_b200/csrc/ns3d_pt_kernels.cuh"
+
+namespace {
+
+unsigned cdivu(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+// Array copied into a block padded like ns3d_zeros pads (three x-y planes behind the array); the
+// padding holds NaN so that a kernel USING a value it only prefetched is caught by the comparison.
+struct Padded {
+    std::vector<double> buf;
+    size_t count;
+    Padded(const double* src, size_t n, size_t plane) : buf(n + 3 * plane + 32, std::numeric_limits<double>::quiet_NaN()), count(n)
+    {
+        if (src) std::memcpy(buf.data(), src, n * sizeof(double));
+    }
+    double* p() { return buf.data(); }
+};
+
+template <int MODE>
+void launch_iter(const PtK& k, const double* cur, double* nxt, double* dP, const double* divV)
+{
+    const dim3 grid(cdivu(k.nx - 2, 32), cdivu(k.ny - 2, 8), cdivu(k.kend - k.kbeg, k.zchunk));
+    emu::launch(grid, dim3(32, 8, 1), [=]() { pt_iter_kernel<MODE, 4, false>(cur, nxt, dP, divV, k); });
+}
+
+template <int MODE, int TY>
+void launch_tb2(int kernel, PtK k, const double* cur, double* nxt, const double* dpc, double* dpn, const double* divV)
+{
+    balance_chunks(k);
+    const dim3 grid(cdivu(k.nx - 2, TB_X - 2), cdivu(k.ny - 2, TY - 2), cdivu(k.kend - k.kbeg, k.zchunk));
+    if (kernel == 2) {
+        tb2s_set_offsets(k, cur, nxt, dpc, dpn, divV);
+        emu::launch(grid, dim3(TB_X, TY, 1), [=]() { pt_tb2s_kernel<MODE, TY>(cur, nxt, dpc, dpn, divV, k); });
+    } else {
+        emu::launch(grid, dim3(TB_X, TY, 1), [=]() { pt_tb2_kernel<MODE, TY, false>(cur, nxt, dpc, dpn, divV, k); });
+    }
+}
+
+template <int MODE>
+int run(int kernel, int ty, PtK k, int serpentine, double* Pr, double* dP, const double* divV, int n_iter, int zchunk_iter,
+        int zchunk_tb, long long* launches)
+{
+    const size_t sxy = (size_t)k.nx * k.ny, n = sxy * k.nz;
+    const size_t dxy = (size_t)(k.nx - 2) * (k.ny - 2), nd = dxy * (k.nz - 2);
+    Padded a(Pr, n, sxy), b(nullptr, n, sxy), da(dP, nd, dxy), db(nullptr, nd, dxy), dv(divV, n, sxy);
+    double *cur = a.p(), *nxt = b.p(), *dpc = da.p(), *dpn = db.p();
+    long long nl = 0;
+    int q = 0;
+    if (kernel != 0) {
+        PtK k2 = k;
+        k2.zchunk = zchunk_tb;
+        for (; q + 2 <= n_iter; q += 2) {
+            k2.reverse = serpentine && ((q >> 1) & 1);
+            if (ty == 8) launch_tb2<MODE, 8>(kernel, k2, cur, nxt, dpc, dpn, dv.p());
+            else if (ty == 32) launch_tb2<MODE, 32>(kernel, k2, cur, nxt, dpc, dpn, dv.p());
+            else launch_tb2<MODE, 16>(kernel, k2, cur, nxt, dpc, dpn, dv.p());
+            std::swap(cur, nxt);
+            std::swap(dpc, dpn);
+            ++nl;
+        }
+    }
+    k.zchunk = zchunk_iter;
+    for (; q < n_iter; ++q) {
+        k.reverse = serpentine && (q & 1);
+        launch_iter<MODE>(k, cur, nxt, dpc, dv.p());
+        std::swap(cur, nxt);
+        ++nl;
+    }
+    std::memcpy(Pr, cur, n * sizeof(double));
+    std::memcpy(dP, dpc, nd * sizeof(double));
+    if (launches) *launches = nl;
+    return 0;
+}
+
+}  // namespace
+
+// kernel: 0 = pt_iter_kernel, 1 = pt_tb2_kernel (+ pt_iter_kernel for an odd tail), 2 = pt_tb2s_kernel (+ tail).
+// zlo_halo / zhi_halo mark z faces that are slab interfaces (left to the halo exchange).
+extern "C" int emu_pt_iterate(int kernel, int mode, int ty, const ns3d_pt_params* pp, int zlo_halo, int zhi_halo,
+                              int serpentine, double* Pr, double* dP, const double* divV, int n_iter, long long* launches)
+{
+    if (!pp || pp->nx < 3 || pp->ny < 3 || pp->nz < 3) return -1;
+    PtK k;
+    std::memset(&k, 0, sizeof k);
+    ptk_fill(pp, &k);
+    k.zlo_halo = zlo_halo;
+    k.zhi_halo = zhi_halo;
+    const int zc_iter = pp->zchunk > 0 ? pp->zchunk : 8;
+    const int zc_tb = pp->zchunk > 0 ? pp->zchunk : 16;
+    switch (mode) {
+        case NS3D_PARITY: return run<NS3D_PARITY>(kernel, ty, k, serpentine, Pr, dP, divV, n_iter, zc_iter, zc_tb, launches);
+        case NS3D_FAST: return run<NS3D_FAST>(kernel, ty, k, serpentine, Pr, dP, divV, n_iter, zc_iter, zc_tb, launches);
+        case NS3D_FASTEST: return run<NS3D_FASTEST>(kernel, ty, k, serpentine, Pr, dP, divV, n_iter, zc_iter, zc_tb, launches);
+    }
+    return -1;
+}
