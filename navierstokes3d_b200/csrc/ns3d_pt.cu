@@ -195,12 +195,17 @@ int launch_tb2(ns3d_ctx* ctx, cudaStream_t st, const PtK& k_in, const double* cu
     // interface need the peer loads/stores of pt_tb2_kernel<.,.,true>
     const bool slim = !k.mbox && ctx->opt_tb2_slim;
     if (slim) tb2s_set_offsets(k, cur, nxt, dpc, dpn, divV);
+#define TBS_LAUNCH(MODE, TY)                                                                                    \
+    do {                                                                                                        \
+        if (ctx->opt_tb2_pf) pt_tb2s_kernel<MODE, TY, true><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);  \
+        else pt_tb2s_kernel<MODE, TY, false><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);                 \
+    } while (0)
 #define TB_LAUNCH(MODE)                                                                                        \
     do {                                                                                                       \
         if (k.mbox) pt_tb2_kernel<MODE, 16, true><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);          \
-        else if (slim && ty == 8) pt_tb2s_kernel<MODE, 8><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);   \
-        else if (slim && ty == 32) pt_tb2s_kernel<MODE, 32><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k); \
-        else if (slim) pt_tb2s_kernel<MODE, 16><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);             \
+        else if (slim && ty == 8) TBS_LAUNCH(MODE, 8);                                                         \
+        else if (slim && ty == 32) TBS_LAUNCH(MODE, 32);                                                       \
+        else if (slim) TBS_LAUNCH(MODE, 16);                                                                   \
         else if (ty == 8) pt_tb2_kernel<MODE, 8, false><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);    \
         else if (ty == 32) pt_tb2_kernel<MODE, 32, false><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);  \
         else pt_tb2_kernel<MODE, 16, false><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);                \
@@ -211,6 +216,7 @@ int launch_tb2(ns3d_ctx* ctx, cudaStream_t st, const PtK& k_in, const double* cu
         default: TB_LAUNCH(NS3D_FASTEST); break;
     }
 #undef TB_LAUNCH
+#undef TBS_LAUNCH
     NS3D_LAUNCH_CHECK(ctx);
     return NS3D_OK;
 }

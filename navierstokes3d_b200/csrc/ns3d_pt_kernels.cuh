@@ -564,7 +564,17 @@ struct Tb2sInv {
 // pressure of planes s-2, s-1, D1C = first-iteration dPrdτ of plane s-1.  On exit PM holds Pr of
 // plane s+2 and DVN ∇V of plane s+1, QN the first-iteration pressure of plane s, so the caller
 // continues with the roles rotated: (PC,ZP,PM), (DV,DVN,DVC), (QC,QN,QM).
-template <int MODE, int TB_Y, int SLOT>
+// DRAM -> L2 prefetch of one line (no destination register; a no-op on the host emulation).
+__device__ __forceinline__ void prefetch_l2(const void* ptr)
+{
+#ifdef NS3D_HOST_EMU
+    (void)ptr;
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+#endif
+}
+
+template <int MODE, int TB_Y, int SLOT, bool PF>
 __device__ __forceinline__ void tb2s_step(const PtK& p, const Tb2sInv& v, const int s, const char*& c, const char*& d,
                                           double* __restrict__ sm, double& PM, double& PC, double& ZP, double& DQ,
                                           double& DVC, double& DV, double& DVN, double& QM, double& QC, double& QN,
@@ -618,7 +628,7 @@ __device__ __forceinline__ void tb2s_step(const PtK& p, const Tb2sInv& v, const 
 #undef LD
 }
 
-template <int MODE, int TB_Y>
+template <int MODE, int TB_Y, bool PF>
 __global__ void __launch_bounds__(TB_X* TB_Y, 1024 / (TB_X * TB_Y)) pt_tb2s_kernel(const double* __restrict__ Pr, double* __restrict__ PrN,
                                                                const double* __restrict__ dP, double* __restrict__ dPN,
                                                                const double* __restrict__ divV, const PtK p)
@@ -660,13 +670,13 @@ __global__ void __launch_bounds__(TB_X* TB_Y, 1024 / (TB_X * TB_Y)) pt_tb2s_kern
 #undef LD
     int s = s0;
     while (true) {
-        tb2s_step<MODE, TB_Y, 0>(p, v, s, c, d, sm, A, B, C, DQ, VA, VB, VC, QA, QB, QC, D1);
+        tb2s_step<MODE, TB_Y, 0, PF>(p, v, s, c, d, sm, A, B, C, DQ, VA, VB, VC, QA, QB, QC, D1);
         if (s == s1) break;
         ++s;
-        tb2s_step<MODE, TB_Y, 1>(p, v, s, c, d, sm, B, C, A, DQ, VB, VC, VA, QB, QC, QA, D1);
+        tb2s_step<MODE, TB_Y, 1, PF>(p, v, s, c, d, sm, B, C, A, DQ, VB, VC, VA, QB, QC, QA, D1);
         if (s == s1) break;
         ++s;
-        tb2s_step<MODE, TB_Y, 2>(p, v, s, c, d, sm, C, A, B, DQ, VC, VA, VB, QC, QA, QB, D1);
+        tb2s_step<MODE, TB_Y, 2, PF>(p, v, s, c, d, sm, C, A, B, DQ, VC, VA, VB, QC, QA, QB, D1);
         if (s == s1) break;
         ++s;
     }
