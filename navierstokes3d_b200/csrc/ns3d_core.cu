@@ -183,7 +183,12 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
         return NS3D_OK;
     }
     if (!strcmp(name, "tb2_pf")) {
-        ctx->opt_tb2_pf = value != 0;
+        if (value < 0 || value > 2) return ns3d_fail(ctx, NS3D_EINVAL, "tb2_pf must be 0, 1 or 2");
+        ctx->opt_tb2_pf = value;
+        return NS3D_OK;
+    }
+    if (!strcmp(name, "tb2_np")) {
+        ctx->opt_tb2_np = value != 0;
         return NS3D_OK;
     }
     if (!strcmp(name, "tb2_slim")) {

@@ -195,10 +195,15 @@ int launch_tb2(ns3d_ctx* ctx, cudaStream_t st, const PtK& k_in, const double* cu
     // interface need the peer loads/stores of pt_tb2_kernel<.,.,true>
     const bool slim = !k.mbox && ctx->opt_tb2_slim;
     if (slim) tb2s_set_offsets(k, cur, nxt, dpc, dpn, divV);
-#define TBS_LAUNCH(MODE, TY)                                                                                    \
-    do {                                                                                                        \
-        if (ctx->opt_tb2_pf) pt_tb2s_kernel<MODE, TY, true><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);  \
-        else pt_tb2s_kernel<MODE, TY, false><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);                 \
+#define TBS_LAUNCH(MODE, TY)                                                                                      \
+    do {                                                                                                          \
+        const int pf = ctx->opt_tb2_pf, np = ctx->opt_tb2_np;                                                     \
+        if (np && pf == 2) pt_tb2s_kernel<MODE, TY, 2, true><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);  \
+        else if (np && pf == 1) pt_tb2s_kernel<MODE, TY, 1, true><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k); \
+        else if (np) pt_tb2s_kernel<MODE, TY, 0, true><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);        \
+        else if (pf == 2) pt_tb2s_kernel<MODE, TY, 2, false><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);  \
+        else if (pf == 1) pt_tb2s_kernel<MODE, TY, 1, false><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);  \
+        else pt_tb2s_kernel<MODE, TY, 0, false><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);               \
     } while (0)
 #define TB_LAUNCH(MODE)                                                                                        \
     do {                                                                                                       \
@@ -405,7 +410,7 @@ struct PtGraph {
     double* dP = nullptr;
     double* dPn = nullptr;
     const double* divV = nullptr;
-    int n = 0, parity = 0, mode = 0, minb = 0;
+    int n = 0, parity = 0, mode = 0, minb = 0, opts = 0;
     bool p2p = false;
     long long kernels = 0;
 };
@@ -472,10 +477,13 @@ int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double*& d
     PtK key;
     memcpy(&key, &k, sizeof key);  // byte copy: the cache compares with memcmp (padding included)
     key.reverse = 0;
+    // every tuning option that selects a kernel or its launch shape is part of the key
+    const int opts = ctx->opt_tb2 | (ctx->opt_tb2_slim << 1) | (ctx->opt_tb2_np << 2) | (ctx->opt_tb2_pf << 3) |
+                     (ctx->opt_tb2_ty << 8);
     PtGraph* g = nullptr;
     for (PtGraph& c : cache->slot)
         if (c.exec && c.cur == cur && c.nxt == nxt && c.dP == dP && c.dPn == dPn && c.divV == divV && c.n == n &&
-            c.parity == (iter0 & 3) && c.mode == ctx->mode && c.minb == ctx->opt_pt_minb && c.p2p == pb.on &&
+            c.parity == (iter0 & 3) && c.mode == ctx->mode && c.minb == ctx->opt_pt_minb && c.opts == opts && c.p2p == pb.on &&
             !memcmp(&c.k, &key, sizeof key))
             g = &c;
     if (!g) {
@@ -507,7 +515,7 @@ int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double*& d
         }
         memcpy(&g->k, &key, sizeof key);
         g->cur = cur; g->nxt = nxt; g->dP = dP; g->dPn = dPn; g->divV = divV; g->n = n;
-        g->parity = iter0 & 3; g->p2p = pb.on; g->mode = ctx->mode; g->minb = ctx->opt_pt_minb; g->kernels = captured;
+        g->parity = iter0 & 3; g->p2p = pb.on; g->mode = ctx->mode; g->minb = ctx->opt_pt_minb; g->opts = opts; g->kernels = captured;
     }
     NS3D_CUDA(ctx, cudaGraphLaunch(g->exec, ctx->stream));
     ctx->launches += g->kernels;

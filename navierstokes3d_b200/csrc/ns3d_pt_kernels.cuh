@@ -574,11 +574,17 @@ __device__ __forceinline__ void prefetch_l2(const void* ptr)
 #endif
 }
 
-template <int MODE, int TB_Y, int SLOT, bool PF>
+//
+// NP (neighbour prefetch): the four in-plane neighbours of the NEXT plane are loaded one step
+// ahead as well (NB[0..3] = x-, x+, y-, y+), so that no global-load latency sits on the per-plane
+// dependency chain load -> stage 1 -> barrier -> stage 2 (ncu: the kernel is latency-bound, not
+// issue-bound -- long-scoreboard stalls on exactly these loads; the rim columns always miss L1).
+// PF = planes of additional DRAM -> L2 software prefetch ahead of the register prefetches.
+template <int MODE, int TB_Y, int SLOT, int PF, bool NP>
 __device__ __forceinline__ void tb2s_step(const PtK& p, const Tb2sInv& v, const int s, const char*& c, const char*& d,
                                           double* __restrict__ sm, double& PM, double& PC, double& ZP, double& DQ,
                                           double& DVC, double& DV, double& DVN, double& QM, double& QC, double& QN,
-                                          double& D1C)
+                                          double& D1C, double (&NB)[4])
 {
 #define LD(ptr) (*(const double*)(ptr))
     constexpr int SLOTSZ = TB_Y * TB_X;
@@ -628,10 +634,9 @@ __device__ __forceinline__ void tb2s_step(const PtK& p, const Tb2sInv& v, const 
 #undef LD
 }
 
-template <int MODE, int TB_Y, bool PF>
-__global__ void __launch_bounds__(TB_X* TB_Y, 1024 / (TB_X * TB_Y)) pt_tb2s_kernel(const double* __restrict__ Pr, double* __restrict__ PrN,
-                                                               const double* __restrict__ dP, double* __restrict__ dPN,
-                                                               const double* __restrict__ divV, const PtK p)
+template <int MODE, int TB_Y, int PF, bool NP>
+__global__ void __launch_bounds__(TB_X* TB_Y, 1024 / (TB_X * TB_Y)) pt_tb2s_kernel(const double* Pr, double* PrN, const double* dP, double* dPN,
+                                                               const double* divV, const PtK p)
 {
     __shared__ double ring[3 * TB_Y * TB_X];
     const int nx = p.nx, ny = p.ny, nz = p.nz;
@@ -667,16 +672,20 @@ __global__ void __launch_bounds__(TB_X* TB_Y, 1024 / (TB_X * TB_Y)) pt_tb2s_kern
     double DQ = LD(d);
     double VA = 0, VB = LD(c + p.oDV), VC = 0;                         // ∇V of planes s-1, s, s+1
     double QA = 0, QB = 0, QC = 0, D1 = 0;
+    double NB[4] = {0, 0, 0, 0};
+    if (NP) {
+        NB[0] = LD(c - 8); NB[1] = LD(c + 8); NB[2] = LD(c - p.rowB); NB[3] = LD(c + p.rowB);
+    }
 #undef LD
     int s = s0;
     while (true) {
-        tb2s_step<MODE, TB_Y, 0, PF>(p, v, s, c, d, sm, A, B, C, DQ, VA, VB, VC, QA, QB, QC, D1);
+        tb2s_step<MODE, TB_Y, 0, PF, NP>(p, v, s, c, d, sm, A, B, C, DQ, VA, VB, VC, QA, QB, QC, D1, NB);
         if (s == s1) break;
         ++s;
-        tb2s_step<MODE, TB_Y, 1, PF>(p, v, s, c, d, sm, B, C, A, DQ, VB, VC, VA, QB, QC, QA, D1);
+        tb2s_step<MODE, TB_Y, 1, PF, NP>(p, v, s, c, d, sm, B, C, A, DQ, VB, VC, VA, QB, QC, QA, D1, NB);
         if (s == s1) break;
         ++s;
-        tb2s_step<MODE, TB_Y, 2, PF>(p, v, s, c, d, sm, C, A, B, DQ, VC, VA, VB, QC, QA, QB, D1);
+        tb2s_step<MODE, TB_Y, 2, PF, NP>(p, v, s, c, d, sm, C, A, B, DQ, VC, VA, VB, QC, QA, QB, D1, NB);
         if (s == s1) break;
         ++s;
     }

@@ -12,6 +12,10 @@ ctx = ns.Context(0, getattr(ns, mode))
 ctx.set_option("graphs", 0)
 if len(sys.argv) > 4:
     ctx.set_option("tb2", int(sys.argv[4]))
+if len(sys.argv) > 5:   # further library options: name=value,name=value
+    for kv in sys.argv[5].split(","):
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
 rng = np.random.default_rng(0)
 Pr = ctx.from_host(np.asfortranarray(rng.uniform(-1, 1, size=(nx, ny, nz))))
 dP = ctx.zeros(nx - 2, ny - 2, nz - 2)
