@@ -589,13 +589,27 @@ __device__ __forceinline__ void tb2s_step(const PtK& p, const Tb2sInv& v, const 
 #define LD(ptr) (*(const double*)(ptr))
     constexpr int SLOTSZ = TB_Y * TB_X;
     // ---- stage 1: first iteration at the clamped column, plane s ------------------------------
-    const double xm = LD(c - 8), xp = LD(c + 8), ym = LD(c - p.rowB), yp = LD(c + p.rowB);
+    double xm, xp, ym, yp;
+    if (NP) {
+        xm = NB[0]; xp = NB[1]; ym = NB[2]; yp = NB[3];
+    } else {
+        xm = LD(c - 8); xp = LD(c + 8); ym = LD(c - p.rowB); yp = LD(c + p.rowB);
+    }
     DVN = LD(c + p.oDVn);  // streams of the next plane (the allocator pads the arrays)
     const double L1 = bracket<MODE>(p, PC, xm, xp, ym, yp, PM, ZP, DV);
     double D1N;
     pt_update<MODE>(p, L1, DQ, PC, D1N, QN);
     PM = LD(c + p.oZP2);           // PM and DQ are dead: reuse them for planes s+2 / s+1
     DQ = LD(d + p.dplaneB);
+    if (NP) {
+        const char* cn = c + p.planeB;
+        NB[0] = LD(cn - 8); NB[1] = LD(cn + 8); NB[2] = LD(cn - p.rowB); NB[3] = LD(cn + p.rowB);
+    }
+    if (PF > 0) {  // further ahead into L2, so that the register prefetches above hit there
+        prefetch_l2(c + p.oZP2 + PF * p.planeB);
+        prefetch_l2(d + (1 + PF) * p.dplaneB);
+        prefetch_l2(c + p.oDVn + PF * p.planeB);
+    }
     if (v.xfix) QN = xface(p, v.xfix > 1, s, QN);  // bc_x_Pr! / bc_xhydstatic! images (x-face columns only)
     sm[SLOT * SLOTSZ] = QN;
     __syncthreads();
