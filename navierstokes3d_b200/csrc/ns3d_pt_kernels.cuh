@@ -612,8 +612,11 @@ __device__ __forceinline__ void tb2s_step(const PtK& p, const Tb2sInv& v, const 
     }
     if (v.xfix) QN = xface(p, v.xfix > 1, s, QN);  // bc_x_Pr! / bc_xhydstatic! images (x-face columns only)
     sm[SLOT * SLOTSZ] = QN;
-    __syncthreads();
     // ---- stage 2: second iteration of plane s-1 from the ring and registers ---------------------
+    // It reads the ring slot of plane s-1, which the barrier of the PREVIOUS step published, so it
+    // runs before this step's barrier: one synchronisation point per plane, and the two
+    // arithmetic chains of a step are independent up to the z term (ncu: barrier and
+    // fixed-latency waits were the top stalls once the loads were off the critical path).
     const int k2 = s - 1;
     if (k2 >= v.kb_own) {
         const double* r = sm + ((SLOT + 2) % 3) * SLOTSZ;
@@ -629,6 +632,7 @@ __device__ __forceinline__ void tb2s_step(const PtK& p, const Tb2sInv& v, const 
         }
     }
     if (s == 1 && !p.zlo_halo) QC = QN;  // bc_z!: q[0] is the image of q[1] (QC becomes QM of the next plane)
+    __syncthreads();                     // slot SLOT is complete; slot SLOT+1 may be overwritten by the next step
     if (s == v.top_own) {
         // physical top face: plane nz-2 needs q[nz-1], the image of q[nz-2]; its second iteration
         // follows here because there is no further stage-1 plane to trigger it
