@@ -178,7 +178,8 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
         return NS3D_OK;
     }
     if (!strcmp(name, "tb2_ty")) {
-        if (value != 8 && value != 16 && value != 32) return ns3d_fail(ctx, NS3D_EINVAL, "tb2_ty must be 8, 16 or 32");
+        if (value != 0 && value != 8 && value != 16 && value != 32)
+            return ns3d_fail(ctx, NS3D_EINVAL, "tb2_ty must be 0 (auto), 8, 16 or 32");
         ctx->opt_tb2_ty = value;
         return NS3D_OK;
     }

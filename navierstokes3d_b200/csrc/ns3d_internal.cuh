@@ -45,8 +45,8 @@ struct ns3d_ctx {
     int opt_pt_minb = 0;  // 0 = per-mode default
     int opt_serpentine = -1;  // -1 = by working-set size
     int opt_tb2 = 1;          // two PT iterations per launch (pt_tb2_kernel); 0 = one-iteration kernel only
-    int opt_tb2_ty = 16;      // tile height of pt_tb2_kernel (8, 16 or 32)
-    int opt_tb2_pf = 0;       // pt_tb2s_kernel: planes of software prefetch into L2 ahead of the register prefetch (0..2)
+    int opt_tb2_ty = 0;       // tile height of the two-iteration kernels (8, 16 or 32; 0 = by grid size)
+    int opt_tb2_pf = 1;       // pt_tb2s_kernel: planes of software prefetch into L2 ahead of the register prefetch (0..2)
     int opt_tb2_np = 1;       // pt_tb2s_kernel: in-plane neighbours of the next plane loaded one step ahead
     int opt_tb2_slim = 1;     // plain two-iteration launches use pt_tb2s_kernel (0 = pt_tb2_kernel)
     int opt_graphs = 1;       // replay chunks of PT iterations as CUDA graphs

@@ -77,7 +77,12 @@ int make_ptk(ns3d_ctx* ctx, const ns3d_pt_params* p, PtK* k)
         while (zc > 4 && xy * cdiv(p->nz - 2, zc) < 2LL * 8 * ctx->num_sms) zc /= 2;  // measured: profiles/r01_*sweep*
     }
     k->zchunk = zc;
-    k->zchunk_tb = p->zchunk > 0 ? p->zchunk : std::max(zc, 16);  // two extra stage-1 planes per chunk: keep them long
+    // Two-iteration kernels recompute two extra stage-1 planes per chunk.  Measured (profiles/
+    // r01_tb2s_sweep_*.jsonl): 12-plane chunks of 32x8 tiles at 255x153x153 (3.9 waves of 8-warp
+    // CTAs), 64-plane chunks of 32x16 tiles at 511^3.
+    const bool small = (double)(p->nx - 2) * (p->ny - 2) * (p->nz - 2) < 3.0e7;
+    k->zchunk_tb = p->zchunk > 0 ? p->zchunk : (small ? 12 : 64);
+    k->tb_ty = ctx->opt_tb2_ty ? ctx->opt_tb2_ty : (small ? 8 : 16);
     // serpentine pays while a good part of the 4-field working set can stay in L2 (measured:
     // +5..8 % at 255x153x153, neutral to -1 % at 511^3; profiles/r01_v4_sweep_serpentine.jsonl)
     k->serpentine = ctx->opt_serpentine < 0 ? (4.0 * 8.0 * p->nx * p->ny * p->nz < 6.0 * ctx->l2_bytes)
@@ -188,7 +193,7 @@ int launch_tb2(ns3d_ctx* ctx, cudaStream_t st, const PtK& k_in, const double* cu
         k.peer_lo_flag = ctx->peer_mbox[0] ? ctx->peer_mbox[0] + NS3D_MB_FLAG_HI : nullptr;
         k.peer_hi_flag = ctx->peer_mbox[1] ? ctx->peer_mbox[1] + NS3D_MB_FLAG_LO : nullptr;
     }
-    const int ty = k.mbox ? 16 : (ctx->opt_tb2_ty == 8 ? 8 : (ctx->opt_tb2_ty == 32 ? 32 : 16));
+    const int ty = k.mbox ? 16 : k.tb_ty;
     const dim3 blk(TB_X, ty, 1);
     const dim3 grd(cdiv(k.nx - 2, TB_X - 2), cdiv(k.ny - 2, ty - 2), k.faces ? 2u : cdiv(k.kend - k.kbeg, k.zchunk));
     // plain launches run the slim re-write (pt_tb2s_kernel, same results); chunks on a slab

@@ -50,7 +50,8 @@ struct PtK {
     // byte strides, precomputed on the host so that the kernel takes them from the constant bank
     // instead of re-deriving 64-bit products under register pressure
     long long rowB, planeB, dplaneB;
-    int zchunk_tb;  // chunk length of the two-iterations-per-launch kernel
+    int zchunk_tb;  // chunk length of the two-iterations-per-launch kernels
+    int tb_ty;      // ... and their tile height (8, 16 or 32 rows of 32 columns)
     // pt_tb2s_kernel: byte displacements between the arrays of THIS launch (tb2s_set_offsets)
     long long oDV;    // ∇V - Pr
     long long oDVn;   // ∇V - Pr + one plane

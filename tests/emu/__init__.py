@@ -48,7 +48,21 @@ def lib() -> C.CDLL:
         _lib.emu_pt_iterate.restype = C.c_int
         _lib.emu_pt_iterate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
+        _lib.emu_pt_tb2_split.restype = C.c_int
+        _lib.emu_pt_tb2_split.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_int, C.c_int, C.c_int, C.c_int]
     return _lib
+
+
+def pt_tb2_split(kernel_mid: str, mode: int, pt_params, Pr, dP, divV, n_pairs: int, klo: int, khi: int,
+                 ty_mid: int = 16, zchunk_mid: int = 16) -> None:
+    """n_pairs double iterations, each as three launches over the plane ranges [1,klo), [klo,khi),
+    [khi,nz-1) -- the outer two with pt_tb2_kernel, the middle one with `kernel_mid` (the way slabs
+    split every launch into interface chunks and the rest)."""
+    rc = lib().emu_pt_tb2_split(KERNELS[kernel_mid], mode, ty_mid, C.addressof(pt_params), Pr.ctypes.data,
+                                dP.ctypes.data, divV.ctypes.data, n_pairs, klo, khi, zchunk_mid)
+    if rc != 0:
+        raise RuntimeError(f"emu_pt_tb2_split failed ({rc})")
 
 
 def pt_iterate(kernel: str, mode: int, pt_params, Pr: np.ndarray, dP: np.ndarray, divV: np.ndarray, n: int,

@@ -83,7 +83,51 @@ int run(int kernel, int ty, PtK k, int serpentine, double* Pr, double* dP, const
     return 0;
 }
 
+// Like the split launch of run_direct() on slabs: the chunks next to the z faces and the planes
+// between them are updated by DIFFERENT launches (here: pt_tb2_kernel on [1,klo) and [khi,nz-1),
+// `kernel_mid` on [klo,khi)), which must compose to the same iterate.
+template <int MODE>
+int run_split(int kernel_mid, int ty_mid, PtK k, double* Pr, double* dP, const double* divV, int n_pairs, int klo, int khi,
+              int zchunk_mid)
+{
+    const size_t sxy = (size_t)k.nx * k.ny, n = sxy * k.nz;
+    const size_t dxy = (size_t)(k.nx - 2) * (k.ny - 2), nd = dxy * (k.nz - 2);
+    Padded a(Pr, n, sxy), b(nullptr, n, sxy), da(dP, nd, dxy), db(nullptr, nd, dxy), dv(divV, n, sxy);
+    double *cur = a.p(), *nxt = b.p(), *dpc = da.p(), *dpn = db.p();
+    for (int q = 0; q < n_pairs; ++q) {
+        PtK lo = k, mid = k, hi = k;
+        lo.kbeg = 1; lo.kend = klo; lo.zchunk = 8;
+        hi.kbeg = khi; hi.kend = k.nz - 1; hi.zchunk = 8;
+        mid.kbeg = klo; mid.kend = khi; mid.zchunk = zchunk_mid;
+        mid.reverse = q & 1;
+        launch_tb2<MODE, 16>(1, lo, cur, nxt, dpc, dpn, dv.p());
+        launch_tb2<MODE, 16>(1, hi, cur, nxt, dpc, dpn, dv.p());
+        if (ty_mid == 8) launch_tb2<MODE, 8>(kernel_mid, mid, cur, nxt, dpc, dpn, dv.p());
+        else launch_tb2<MODE, 16>(kernel_mid, mid, cur, nxt, dpc, dpn, dv.p());
+        std::swap(cur, nxt);
+        std::swap(dpc, dpn);
+    }
+    std::memcpy(Pr, cur, n * sizeof(double));
+    std::memcpy(dP, dpc, nd * sizeof(double));
+    return 0;
+}
+
 }  // namespace
+
+extern "C" int emu_pt_tb2_split(int kernel_mid, int mode, int ty_mid, const ns3d_pt_params* pp, double* Pr, double* dP,
+                                const double* divV, int n_pairs, int klo, int khi, int zchunk_mid)
+{
+    if (!pp || pp->nx < 3 || pp->ny < 3 || pp->nz < 3 || klo < 2 || khi <= klo || khi > pp->nz - 2) return -1;
+    PtK k;
+    std::memset(&k, 0, sizeof k);
+    ptk_fill(pp, &k);
+    switch (mode) {
+        case NS3D_PARITY: return run_split<NS3D_PARITY>(kernel_mid, ty_mid, k, Pr, dP, divV, n_pairs, klo, khi, zchunk_mid);
+        case NS3D_FAST: return run_split<NS3D_FAST>(kernel_mid, ty_mid, k, Pr, dP, divV, n_pairs, klo, khi, zchunk_mid);
+        case NS3D_FASTEST: return run_split<NS3D_FASTEST>(kernel_mid, ty_mid, k, Pr, dP, divV, n_pairs, klo, khi, zchunk_mid);
+    }
+    return -1;
+}
 
 // kernel: 0 = pt_iter_kernel, 1 = pt_tb2_kernel (+ pt_iter_kernel for an odd tail), 2 = pt_tb2s_kernel (+ tail).
 // zlo_halo / zhi_halo mark z faces that are slab interfaces (left to the halo exchange).

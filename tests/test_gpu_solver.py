@@ -66,13 +66,19 @@ def test_fused_iteration_bit_exact(O, ns, ctx, variant, grid, zchunk):
 @pytest.mark.parametrize("variant", ["M", "G"])
 @pytest.mark.parametrize("grid", [(3, 3, 3), (5, 4, 3), (4, 3, 6), (37, 23, 19), (63, 38, 38), (70, 47, 41)])
 @pytest.mark.parametrize("zchunk", [0, 1, 2, 7])
-def test_two_iterations_per_launch_bit_exact(O, ns, ctx, variant, grid, zchunk):
+@pytest.mark.parametrize("kern", ["tb2s_auto", "tb2s_16_nopf", "tb2s_8_pf2", "tb2_first"])
+def test_two_iterations_per_launch_bit_exact(O, ns, ctx, variant, grid, zchunk, kern):
     """Temporal blocking (option "tb2"): 2 PT iterations per launch, rims recomputed, Pr^(1) kept in
     shared memory.  Same per-cell arithmetic -> still bit-equal to the oracle; odd counts end with
-    one single-iteration launch, (70,47,41) spans 3x4 tiles and several z-chunks."""
+    one single-iteration launch, (70,47,41) spans 3x4 tiles and several z-chunks.  Kernels: the
+    default pt_tb2s_kernel (tile height by grid size, neighbour + L2 prefetch), two of its other
+    instantiations, and the first version pt_tb2_kernel (still the one on slab interfaces)."""
     p, f = pt_problem(O, variant, grid, 15)
     s = setup_for(ns, variant, grid[0], ny=grid[1], nz=grid[2])
     ctx.set_option("tb2", 1)
+    for name, val in {"tb2s_auto": {}, "tb2s_16_nopf": {"tb2_ty": 16, "tb2_pf": 0, "tb2_np": 0},
+                      "tb2s_8_pf2": {"tb2_ty": 8, "tb2_pf": 2}, "tb2_first": {"tb2_slim": 0, "tb2_ty": 16}}[kern].items():
+        ctx.set_option(name, val)
     d = {k: ctx.from_host(f[k]) for k in ("Pr", "dPrdtau", "divV")}
     done = 0
     for n in (2, 1, 5, 40):

@@ -99,3 +99,19 @@ def test_outlet_guard_off_emulated(O):
     emu.pt_iterate("pt_tb2s", ns.PARITY, s.pt_params(), g["Pr"], g["dPrdtau"], g["divV"], 4)
     oracle_iterations(O, p, f, 4)
     assert np.array_equal(g["Pr"], f["Pr"]) and np.array_equal(g["dPrdtau"], f["dPrdtau"])
+
+
+@pytest.mark.parametrize("variant,grid,klo,khi,ty,zc", [("M", (37, 23, 30), 9, 21, 8, 5), ("G", (20, 19, 26), 9, 17, 16, 12),
+                                                         ("M", (35, 12, 22), 9, 13, 8, 12)])
+def test_split_launch_composition(O, variant, grid, klo, khi, ty, zc):
+    """Slabs update the chunks next to their interfaces and the planes in between with different
+    launches (and different kernels): plane ranges must compose without a seam."""
+    p, f = problem(O, variant, grid, 34)
+    s = setup_for(variant, grid)
+    g = {k: f[k].copy(order="F") for k in ("Pr", "dPrdtau", "divV")}
+    emu.pt_tb2_split("pt_tb2s", ns.PARITY, s.pt_params(), g["Pr"], g["dPrdtau"], g["divV"], 2, klo, khi, ty_mid=ty,
+                     zchunk_mid=zc)
+    oracle_iterations(O, p, f, 4)
+    for name in ("Pr", "dPrdtau"):
+        bad = np.argwhere(g[name] != f[name])
+        assert len(bad) == 0, f"{name}: {len(bad)} values differ, first {bad[:3].tolist()}"
