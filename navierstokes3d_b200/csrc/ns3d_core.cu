@@ -192,6 +192,10 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
         ctx->opt_tb2_np = value != 0;
         return NS3D_OK;
     }
+    if (!strcmp(name, "tb2_spec")) {
+        ctx->opt_tb2_spec = value != 0;
+        return NS3D_OK;
+    }
     if (!strcmp(name, "tb2_slim")) {
         ctx->opt_tb2_slim = value != 0;
         return NS3D_OK;

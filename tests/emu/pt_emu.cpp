@@ -41,7 +41,11 @@ void launch_tb2(int kernel, PtK k, const double* cur, double* nxt, const double*
     const dim3 grid(cdivu(k.nx - 2, TB_X - 2), cdivu(k.ny - 2, TY - 2), cdivu(k.kend - k.kbeg, k.zchunk));
     if (kernel == 2) {
         tb2s_set_offsets(k, cur, nxt, dpc, dpn, divV);
-        emu::launch(grid, dim3(TB_X, TY, 1), [=]() { pt_tb2s_kernel<MODE, TY, 1, true>(cur, nxt, dpc, dpn, divV, k); });
+        // like launch_tb2() in ns3d_pt.cu: grids with a compile-time-stride instantiation use it
+        if (TY == 8 && k.nx == 255 && k.ny == 153)
+            emu::launch(grid, dim3(TB_X, TY, 1), [=]() { pt_tb2s_kernel<MODE, 8, 1, true, 255, 153>(cur, nxt, dpc, dpn, divV, k); });
+        else
+            emu::launch(grid, dim3(TB_X, TY, 1), [=]() { pt_tb2s_kernel<MODE, TY, 1, true, 0, 0>(cur, nxt, dpc, dpn, divV, k); });
     } else {
         emu::launch(grid, dim3(TB_X, TY, 1), [=]() { pt_tb2_kernel<MODE, TY, false>(cur, nxt, dpc, dpn, divV, k); });
     }

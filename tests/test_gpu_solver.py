@@ -247,3 +247,29 @@ def test_large_grid_oracle_spot_check(O, ns):
     assert (d["Pr"].to_host() == f["Pr"]).all()
     assert (d["dPrdtau"].to_host() == f["dPrdtau"]).all()
     ctx.close()
+
+
+@pytest.mark.parametrize("variant,grid", [("M", (511, 511, 9)), ("G", (1023, 511, 7)), ("G", (255, 153, 20))])
+def test_compile_time_stride_kernels(O, ns, variant, grid):
+    """Grids whose x-y extent has a compile-time-stride instantiation of pt_tb2s_kernel (255x153,
+    511x511, 1023x511: the reference scripts' and BASELINE.json's planes), thin in z so that the
+    oracle finishes in seconds; 5 iterations = two double launches + one single.  Bit-exact, and
+    identical to the generic-stride instantiation."""
+    p, f = pt_problem(O, variant, grid, 23)
+    s = setup_for(ns, variant, grid[0], ny=grid[1], nz=grid[2])
+    ctx = ns.Context(0, ns.PARITY)
+    out = {}
+    for spec in (1, 0):
+        ctx.set_option("tb2_spec", spec)
+        if grid[0] != 255:
+            ctx.set_option("tb2_ty", 16)   # thin grids are "small": the 511/1023 instantiations are 32x16 tiles
+        d = {k: ctx.from_host(f[k]) for k in ("Pr", "dPrdtau", "divV")}
+        ctx.pt_iterate(d["Pr"], d["dPrdtau"], d["divV"], s.pt_params(), 5)
+        out[spec] = (d["Pr"].to_host(), d["dPrdtau"].to_host())
+    for _ in range(5):
+        O.update_dPrdtau(p, f)
+        O.update_Pr(p, f)
+        O.set_bc_Pr(p, f)
+    assert (out[1][0] == f["Pr"]).all() and (out[1][1] == f["dPrdtau"]).all()
+    assert (out[0][0] == out[1][0]).all() and (out[0][1] == out[1][1]).all()
+    ctx.close()

@@ -115,3 +115,15 @@ def test_split_launch_composition(O, variant, grid, klo, khi, ty, zc):
     for name in ("Pr", "dPrdtau"):
         bad = np.argwhere(g[name] != f[name])
         assert len(bad) == 0, f"{name}: {len(bad)} values differ, first {bad[:3].tolist()}"
+
+
+def test_compile_time_stride_instantiation(O):
+    """pt_tb2s_kernel<., 8, 1, true, 255, 153>: row/plane strides as immediates (the x-y extent of
+    BASELINE configs[1]); a thin 255x153x5 slab keeps the emulation short."""
+    grid = (255, 153, 5)
+    p, f = problem(O, "G", grid, 35)
+    s = setup_for("G", grid)
+    g = {k: f[k].copy(order="F") for k in ("Pr", "dPrdtau", "divV")}
+    emu.pt_iterate("pt_tb2s", ns.PARITY, s.pt_params(), g["Pr"], g["dPrdtau"], g["divV"], 2, ty=8)
+    oracle_iterations(O, p, f, 2)
+    assert np.array_equal(g["Pr"], f["Pr"]) and np.array_equal(g["dPrdtau"], f["dPrdtau"])
