@@ -604,8 +604,14 @@ __device__ __forceinline__ void tb2s_step(const PtK& p, const Tb2sInv& v, const 
 #define LD(ptr) (*(const double*)(ptr))
     constexpr int SLOTSZ = TB_Y * TB_X;
     typedef Tb2sStride<NXC, NYC> G;
-    const long long rowB = G::row(p), planeB = G::plane(p), dplaneB = G::dplane(p);
-    const char* cv = c + p.oDV;  // this column in ∇V
+    // (evaluated at the point of use: ptxas spills when these sit in named locals across the step)
+#define rowB (G::row(p))
+#define planeB (G::plane(p))
+#define dplaneB (G::dplane(p))
+    // ∇V of the next plane / Pr two planes ahead: with compile-time strides one base per array and
+    // immediates, otherwise host-precomputed displacements from c (one 64-bit add each)
+#define a_dvn (NXC > 0 ? (c + p.oDV) + planeB : c + p.oDVn)
+#define a_zp2 (NXC > 0 ? c + 2 * planeB : c + p.oZP2)
     // ---- stage 1: first iteration at the clamped column, plane s ------------------------------
     double xm, xp, ym, yp;
     if (NP) {
@@ -613,20 +619,20 @@ __device__ __forceinline__ void tb2s_step(const PtK& p, const Tb2sInv& v, const 
     } else {
         xm = LD(c - 8); xp = LD(c + 8); ym = LD(c - rowB); yp = LD(c + rowB);
     }
-    DVN = LD(cv + planeB);  // streams of the next plane (the allocator pads the arrays)
+    DVN = LD(a_dvn);  // streams of the next plane (the allocator pads the arrays)
     const double L1 = bracket<MODE>(p, PC, xm, xp, ym, yp, PM, ZP, DV);
     double D1N;
     pt_update<MODE>(p, L1, DQ, PC, D1N, QN);
-    PM = LD(c + 2 * planeB);       // PM and DQ are dead: reuse them for planes s+2 / s+1
+    PM = LD(a_zp2);               // PM and DQ are dead: reuse them for planes s+2 / s+1
     DQ = LD(d + dplaneB);
     if (NP) {
         const char* cn = c + planeB;
         NB[0] = LD(cn - 8); NB[1] = LD(cn + 8); NB[2] = LD(cn - rowB); NB[3] = LD(cn + rowB);
     }
     if (PF > 0) {  // further ahead into L2, so that the register prefetches above hit there
-        prefetch_l2(c + (2 + PF) * planeB);
+        prefetch_l2(a_zp2 + PF * planeB);
         prefetch_l2(d + (1 + PF) * dplaneB);
-        prefetch_l2(cv + (1 + PF) * planeB);
+        prefetch_l2(a_dvn + PF * planeB);
     }
     if (v.xfix) QN = xface(p, v.xfix > 1, s, QN);  // bc_x_Pr! / bc_xhydstatic! images (x-face columns only)
     sm[SLOT * SLOTSZ] = QN;
@@ -668,6 +674,11 @@ __device__ __forceinline__ void tb2s_step(const PtK& p, const Tb2sInv& v, const 
     c += planeB;
     d += dplaneB;
 #undef LD
+#undef rowB
+#undef planeB
+#undef dplaneB
+#undef a_dvn
+#undef a_zp2
 }
 
 template <int MODE, int TB_Y, int PF, bool NP, int NXC, int NYC>
