@@ -168,6 +168,16 @@ NS3D_API int ns3d_update_halo(ns3d_ctx* ctx, double* const* fields, const int* s
 /* MPI.Allreduce(x, MPI.MAX, comm) of one host double (NaN-propagating). */
 NS3D_API int ns3d_allreduce_max(ns3d_ctx* ctx, double* h_inout);
 
+/* ---- output path: interior extraction, save, heat-map planes ------------------
+ * Replaces `Array(A)[2:end-1,2:end-1,2:end-1]` ahead of gather!/save_array (M:399-412, 481-523,
+ * 528-532; G:169) and the planes `A_v[:,:,k]`, `A_v[:,j,:]` of the visualisation block
+ * (M:422-431).  The box [x0,x1) x [y0,y1) x [z0,z1) (0-based) of the device array A (sx,sy,sz) is
+ * packed on the device and copied densely, column-major, to h_out: Float64, or Float32 when
+ * f32 != 0 (`convert.(Float32, A_v)`, M:408; round to nearest even like Julia).  The interior is
+ * the box [1,sx-1) x [1,sy-1) x [1,sz-1); a plane is a box one point thick.  Synchronises.    */
+NS3D_API int ns3d_box_d2h(ns3d_ctx* ctx, const double* A, int sx, int sy, int sz, int x0, int x1, int y0, int y1,
+                          int z0, int z1, void* h_out, int f32);
+
 /* ---- level 2: fused fast path ------------------------------------------------- */
 typedef struct ns3d_pt_params {
     int nx, ny, nz;         /* local grid */

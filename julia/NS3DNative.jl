@@ -14,7 +14,7 @@ export Ctx, DevArray, zeros3, to_host, set!, set_mode!, PARITY, FAST, FASTEST,
        update_τ!, predict_V!, update_∇V!, update_dPrdτ!, update_Pr!, compute_res!, max_g_abs, correct_V!,
        bc_x!, bc_y!, bc_z!, bc_x_Vx!, bc_x_Pr!, bc_zV!, bc_xhydstatic!, set_bc_Vel_M!, set_bc_Vel_G!,
        set_bc_Pr_M!, set_bc_Pr_G!, advect!, set_cylinder_M!, set_cylinder_G!, update_halo!, copy!,
-       comm_init_mpi!, PtParams, pt_solve!
+       comm_init_mpi!, PtParams, pt_solve!, inner, inner32, plane_xy, plane_xz
 
 const LIB = get(ENV, "NS3D_LIB", joinpath(@__DIR__, "..", "navierstokes3d_b200", "csrc", "libns3d.so"))
 const PARITY, FAST, FASTEST = Cint(0), Cint(1), Cint(2)
@@ -67,6 +67,21 @@ end
 "`A_o .= A` (M:475)"
 copy!(c::Ctx, dst::DevArray, src::DevArray) =
     check(c, ccall((:ns3d_copy, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Csize_t), c.h, dst.p, src.p, length(src)))
+
+# ---- output path: only the requested box leaves the device (ns3d_box_d2h) ---------------------
+function box(c::Ctx, a::DevArray, xr::UnitRange, yr::UnitRange, zr::UnitRange, ::Type{T}) where {T<:Union{Float64,Float32}}
+    h = Array{T,3}(undef, length(xr), length(yr), length(zr))      # 1-based inclusive ranges -> 0-based half-open
+    check(c, ccall((:ns3d_box_d2h, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Ptr{Cvoid}, Cint),
+                   c.h, a.p, a.dims..., first(xr) - 1, last(xr), first(yr) - 1, last(yr), first(zr) - 1, last(zr), h, T == Float32))
+    return h
+end
+"`Array(A)[2:end-1,2:end-1,2:end-1]` (M:399-403, 528-532)"
+inner(c::Ctx, a::DevArray) = box(c, a, 2:a.dims[1]-1, 2:a.dims[2]-1, 2:a.dims[3]-1, Float64)
+"`convert.(Float32, Array(A)[2:end-1,2:end-1,2:end-1])` (M:408): converted on the device"
+inner32(c::Ctx, a::DevArray) = box(c, a, 2:a.dims[1]-1, 2:a.dims[2]-1, 2:a.dims[3]-1, Float32)
+"`A_v[:, :, k]` / `A_v[:, j, :]` of the interior (heat-map planes, M:422-431); k, j index the interior"
+plane_xy(c::Ctx, a::DevArray, k::Integer) = box(c, a, 2:a.dims[1]-1, 2:a.dims[2]-1, k+1:k+1, Float64)[:, :, 1]
+plane_xz(c::Ctx, a::DevArray, j::Integer) = box(c, a, 2:a.dims[1]-1, j+1:j+1, 2:a.dims[3]-1, Float64)[:, 1, :]
 
 const P = Ptr{Float64}
 n3(Pr::DevArray) = (Cint(Pr.dims[1]), Cint(Pr.dims[2]), Cint(Pr.dims[3]))

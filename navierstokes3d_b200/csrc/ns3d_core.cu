@@ -131,6 +131,7 @@ extern "C" int ns3d_destroy(ns3d_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->comm_stream);
     ns3d_internal_pt_free_graphs(ctx);
+    ns3d_internal_out_free(ctx);
     for (auto& kv : ctx->p2p_map) {
         if (kv.second.first) cudaIpcCloseMemHandle(kv.second.first);
         if (kv.second.second) cudaIpcCloseMemHandle(kv.second.second);

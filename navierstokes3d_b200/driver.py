@@ -156,9 +156,28 @@ class Simulation:
     def host(self, name: str) -> np.ndarray:
         return self.f[name].to_host()
 
-    def interior(self, name: str) -> np.ndarray:
-        """``Array(A)[2:end-1,2:end-1,2:end-1]`` (M:528-532)."""
-        return self.host(name)[1:-1, 1:-1, 1:-1]
+    def interior(self, name: str, dtype=np.float64, drop_last_z: bool = False) -> np.ndarray:
+        """``Array(A)[2:end-1,2:end-1,2:end-1]`` (M:399-403, 528-532), extracted on the device: only
+        the interior crosses PCIe.  ``dtype=np.float32`` is ``convert.(Float32, .)`` (M:408);
+        ``drop_last_z`` leaves out the last interior plane (z-slab gather of ``Vz``)."""
+        a = self.f[name]
+        sx, sy, sz = a.shape
+        return self.ctx.box(a, (1, sx - 1), (1, sy - 1), (1, sz - 1 - int(drop_last_z)), dtype)
+
+    def slice_xy(self, name: str, dtype=np.float64) -> np.ndarray:
+        """The horizontal heat-map plane of the visualisation block, ``A_v[:, :, ceil(Int, nz_g()/2)]``
+        (M:422-426), of the LOCAL interior: one x-y plane leaves the device."""
+        a = self.f[name]
+        sx, sy, sz = a.shape
+        k = -(-self.s.nz // 2)            # ceil(nz/2), 1-based index into the interior = 0-based index into A
+        return self.ctx.box(a, (1, sx - 1), (1, sy - 1), (k, k + 1), dtype)[:, :, 0]
+
+    def slice_xz(self, name: str, dtype=np.float64) -> np.ndarray:
+        """The vertical heat-map plane ``A_v[:, ceil(Int, ny_g()/2), :]`` (M:428-432)."""
+        a = self.f[name]
+        sx, sy, sz = a.shape
+        j = -(-self.s.ny // 2)
+        return self.ctx.box(a, (1, sx - 1), (j, j + 1), (1, sz - 1), dtype)[:, 0, :]
 
 
 def _dist_env():
@@ -184,19 +203,24 @@ def attach_communicator(ctx: native.Context, rank: int, world: int):
 
 def run_navierstokes3D(*, do_vis: bool = False, do_save: bool = False, do_print: bool = False, nx: int = 255,
                        nt: int = 10, ny: int | None = None, nz: int | None = None, mode: int = native.FAST,
-                       level1: bool = False, return_sim: bool = False):
+                       level1: bool = False, return_sim: bool = False, nsave: int | None = None):
     """Drop-in for ``run_navierstokes3D`` (M:287): same keywords, same return value.
 
     Under ``torchrun`` (WORLD_SIZE > 1, torch.distributed initialised by the caller) the domain is
     split into z-slabs, one rank per GPU, with the script's local ``nx, ny, nz`` per rank.
     ``do_vis`` is accepted and ignored (plotting is out of scope); ``do_save`` writes the
-    script's Float32 ``out_save/out_*_v_%04d.bin`` dumps of the returned arrays on rank 0.
+    script's Float32 frames ``out_save/out_<A>_v_%04d.bin`` on rank 0: frame 0 holds the initial
+    conditions (M:404-413), then one frame every ``nsave`` (M:332: 10) time steps (M:515-523).
     """
+    nsave = NSAVE if nsave is None else nsave
     rank, world, local = _dist_env()
     s = setup_multi_gpu(nx, ny=ny, nz=nz, rank=rank, nranks=world)
     ctx = native.Context(local, mode)
     attach_communicator(ctx, rank, world)
     sim = Simulation(s, ctx)
+    iframe = 0
+    if do_save:
+        save_frame(sim, iframe)                                          # initial conditions, M:404-413
     for it in range(1, nt + 1):
         if rank == 0 and do_print:
             print(f"#it = {it}")                                         # M:456
@@ -204,18 +228,39 @@ def run_navierstokes3D(*, do_vis: bool = False, do_save: bool = False, do_print:
         if rank == 0 and do_print:
             for c, err in enumerate(hist, 1):
                 print("  #iter = %d, err = %1.3e" % (min(c * s.nchk, iters), err))   # M:468
+        if do_save and it % nsave == 0:                                  # M:479-523
+            iframe += 1
+            save_frame(sim, iframe)
     out = tuple(gather_interior(sim, name) for name in ("C", "Pr", "Vx", "Vy", "Vz"))   # M:528-535
-    if do_save and rank == 0:
-        os.makedirs("out_save", exist_ok=True)
-        for name, arr in zip(("C", "Pr", "Vx", "Vy", "Vz"), out):
-            np.asfortranarray(arr, dtype=np.float32).ravel(order="F").tofile(f"out_save/out_{name}_v_{nt:04d}.bin")
     if return_sim:
         return out, sim
     ctx.close()
     return out
 
 
-def gather_interior(sim: Simulation, name: str) -> np.ndarray | None:
+NSAVE = 10   # M:332 `nsave`: time steps between two saved frames
+
+
+def save_array(aname: str, a: np.ndarray) -> str:
+    """``save_array(Aname, A)`` (M:27-30): the raw column-major bytes of A in ``Aname.bin``."""
+    fname = aname + ".bin"
+    with open(fname, "wb") as fh:
+        fh.write(np.asfortranarray(a).tobytes(order="F"))
+    return fname
+
+
+def save_frame(sim: Simulation, iframe: int, outdir: str = "out_save"):
+    """One frame of the script's ``do_save`` output (M:404-413, 515-523): the gathered interior of
+    C, Pr, Vx, Vy, Vz as Float32 in ``out_save/out_<A>_v_%04d.bin`` on rank 0.  The conversion to
+    Float32 happens on the device, so half the bytes cross PCIe."""
+    for name in ("C", "Pr", "Vx", "Vy", "Vz"):
+        g = gather_interior(sim, name, dtype=np.float32)
+        if sim.s.grid.rank == 0:
+            os.makedirs(outdir, exist_ok=True)
+            save_array(os.path.join(outdir, "out_%s_v_%04d" % (name, iframe)), g)
+
+
+def gather_interior(sim: Simulation, name: str, dtype=np.float64) -> np.ndarray | None:
     """``gather!(A_inn, A_v)`` (M:399-403): interior blocks concatenated along z on rank 0.
 
     The reference's own multi-rank gather of the staggered fields is shape-inconsistent
@@ -223,18 +268,27 @@ def gather_interior(sim: Simulation, name: str) -> np.ndarray | None:
     staggered along the split dimension (Vz), the last rank contributes the extra plane.
     """
     s = sim.s
-    a = sim.interior(name)
     world, rank = s.grid.nranks, s.grid.rank
+    a = sim.interior(name, dtype, drop_last_z=(world > 1 and name == "Vz" and rank < world - 1))
     if world == 1:
         return a
-    if name == "Vz" and rank < world - 1:
-        a = a[:, :, : s.nz - 2]
     import torch.distributed as dist
     parts = [None] * world if rank == 0 else None
     dist.gather_object(np.ascontiguousarray(a), parts, dst=0)
     if rank != 0:
         return None
     return np.asfortranarray(np.concatenate(parts, axis=2))
+
+
+def save_mat(fname: str, sim: Simulation):
+    """``matwrite("out_save/step_$it.mat", Dict("Pr"=>Array(Pr), "Vx"=>..., "Vy"=>..., "Vy"=>Array(Vz),
+    "C"=>..., "dx"=>dx, "dy"=>dy, "dz"=>dz); compress=true)`` (G:169).  The reference's Dict literal names
+    the key "Vy" twice, so its file holds Vz under "Vy" and no Vy at all; the
+    same content is written here, plus the lost field under "Vy_true"."""
+    from scipy.io import savemat
+    s = sim.s
+    savemat(fname, {"Pr": sim.host("Pr"), "Vx": sim.host("Vx"), "Vy": sim.host("Vz"), "C": sim.host("C"),
+                    "Vy_true": sim.host("Vy"), "dx": s.dx, "dy": s.dy, "dz": s.dz}, do_compression=True)
 
 
 def runme(*, do_vis: bool = True, do_save: bool = False, nx: int = 255, nt: int = 10000, mode: int = native.FAST,
@@ -249,10 +303,9 @@ def runme(*, do_vis: bool = True, do_save: bool = False, nx: int = 255, nt: int 
         if do_print:
             for c, err in enumerate(hist, 1):
                 print("  #iter = %d, err = %1.3e" % (min(c * s.nchk, iters), err))   # G:134
-        if do_save and it % 10 == 0:                                     # G:168-170 (npz instead of .mat)
+        if do_save and it % 10 == 0:                                     # G:168-170
             os.makedirs("out_save", exist_ok=True)
-            np.savez(f"out_save/step_{it}.npz", **{k: sim.host(k) for k in ("Pr", "Vx", "Vy", "Vz", "C")},
-                     dx=s.dx, dy=s.dy, dz=s.dz)
+            save_mat(f"out_save/step_{it}.mat", sim)
     if return_sim:
         return sim
     sim.ctx.close()

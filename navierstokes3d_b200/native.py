@@ -71,6 +71,7 @@ SIGNATURES = {
     "ns3d_sync": (_I, [_P]),
     "ns3d_launch_count": (C.c_longlong, [_P]),
     "ns3d_stream": (_P, [_P]),
+    "ns3d_box_d2h": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I]),
     "ns3d_zeros": (_I, [_P, _I, _I, _I, C.POINTER(_P)]),
     "ns3d_free": (_I, [_P, _P]),
     "ns3d_h2d": (_I, [_P, _P, _P, _Z]),
@@ -252,6 +253,22 @@ class Context:
     def d2h(self, host: np.ndarray, src: DeviceArray):
         assert host.dtype == np.float64 and host.flags.f_contiguous and host.shape == src.shape
         self._ck(self.lib.ns3d_d2h(self.h, host.ctypes.data, src.ptr, host.size), "ns3d_d2h")
+
+    def box(self, src: DeviceArray, xr=None, yr=None, zr=None, dtype=np.float64) -> np.ndarray:
+        """The box ``src[xr[0]:xr[1], yr[0]:yr[1], zr[0]:zr[1]]`` (0-based, half-open; default: the
+        whole extent) packed on the device and copied to the host as float64 or float32
+        (``ns3d_box_d2h``): ``Array(A)[2:end-1,2:end-1,2:end-1]`` is ``box(A, (1, sx-1), (1, sy-1), (1, sz-1))``."""
+        sx, sy, sz = src.shape
+        x0, x1 = xr if xr is not None else (0, sx)
+        y0, y1 = yr if yr is not None else (0, sy)
+        z0, z1 = zr if zr is not None else (0, sz)
+        dtype = np.dtype(dtype)
+        if dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise ValueError("box: dtype must be float64 or float32")
+        out = np.empty((max(x1 - x0, 0), max(y1 - y0, 0), max(z1 - z0, 0)), dtype=dtype, order="F")
+        self._ck(self.lib.ns3d_box_d2h(self.h, src.ptr, sx, sy, sz, x0, x1, y0, y1, z0, z1, out.ctypes.data,
+                                       int(dtype == np.dtype(np.float32))), "ns3d_box_d2h")
+        return out
 
     def d2h_raw(self, host_ptr: int, src_ptr: int, count: int):
         self._ck(self.lib.ns3d_d2h(self.h, host_ptr, src_ptr, count), "ns3d_d2h")

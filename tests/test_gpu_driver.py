@@ -46,11 +46,20 @@ def test_runme_single_gpu_script(O, ns):
 
 def test_do_save_writes_float32_bins(ns, tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
-    out = ns.run_navierstokes3D(do_save=True, nx=40, nt=2)
+    out, sim = ns.run_navierstokes3D(do_save=True, nx=40, nt=2, nsave=2, return_sim=True)
+    s = sim.s
     for name, arr in zip(("C", "Pr", "Vx", "Vy", "Vz"), out):
-        raw = np.fromfile(tmp_path / "out_save" / f"out_{name}_v_0002.bin", dtype=np.float32)   # M:27-30,517-521
+        # frame 1 = the first saved time step (here step 2 = the returned state), M:27-30,515-523
+        raw = np.fromfile(tmp_path / "out_save" / f"out_{name}_v_0001.bin", dtype=np.float32)
         assert raw.size == arr.size
         assert np.array_equal(raw, arr.astype(np.float32).ravel(order="F"))
+        # frame 0 = initial conditions (M:404-413): C and V carry the cylinder mask, Vy the (sic) inlet plane
+        ic = np.fromfile(tmp_path / "out_save" / f"out_{name}_v_0000.bin", dtype=np.float32)
+        assert ic.size == arr.size and np.isfinite(ic).all()
+    c0 = np.fromfile(tmp_path / "out_save" / "out_C_v_0000.bin", dtype=np.float32).reshape((s.nx - 2, s.ny - 2, s.nz - 2), order="F")
+    assert (c0 == 1.0).sum() > 0 and set(np.unique(c0)) <= {0.0, 1.0}
+    assert not (tmp_path / "out_save" / "out_C_v_0002.bin").exists()
+    sim.ctx.close()
 
 
 def test_bench_line_has_the_contract_keys():

@@ -1,0 +1,69 @@
+"""GPU tests of the output path: device-side extraction of the interior,
+Float32 conversion, heat-map planes, .mat dump -- against plain numpy slicing of the full field."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 3), (2, 5, 4), (37, 23, 19), (64, 38, 38), (40, 25, 24), (33, 9, 70)])
+def test_box_matches_numpy_slicing(ns, ctx, shape):
+    rng = np.random.default_rng(41)
+    a = np.asfortranarray(rng.standard_normal(shape) * 10.0 ** rng.integers(-30, 30, size=shape))
+    a.flat[::7] = 0.0
+    a[0, 0, 0] = np.nan
+    a[-1, -1, -1] = np.inf
+    d = ctx.from_host(a)
+    sx, sy, sz = shape
+    boxes = [((1, sx - 1), (1, sy - 1), (1, sz - 1)),            # Array(A)[2:end-1,2:end-1,2:end-1]
+             ((0, sx), (0, sy), (0, sz)),                          # the whole array
+             ((1, sx - 1), (1, sy - 1), (sz // 2, sz // 2 + 1)),   # an x-y plane
+             ((1, sx - 1), (sy // 2, sy // 2 + 1), (1, sz - 1)),   # an x-z plane
+             ((sx - 1, sx), (0, sy), (0, sz)),                     # the outlet face
+             ((1, 1), (0, sy), (0, sz))]                           # empty
+    for xr, yr, zr in boxes:
+        want = a[xr[0]:xr[1], yr[0]:yr[1], zr[0]:zr[1]]
+        for dtype in (np.float64, np.float32):
+            got = ctx.box(d, xr, yr, zr, dtype)
+            assert got.shape == want.shape and got.dtype == dtype and got.flags.f_contiguous
+            with np.errstate(over="ignore"):
+                w = want.astype(dtype)   # numpy converts like Julia: round to nearest even, overflow to Inf
+            assert np.array_equal(got, w, equal_nan=True), (xr, yr, zr, dtype)
+
+
+def test_box_rejects_a_box_outside_the_array(ns, ctx):
+    d = ctx.zeros(5, 4, 3)
+    with pytest.raises(ns.NS3DError, match="outside"):
+        ctx.box(d, (0, 6), (0, 4), (0, 3))
+    with pytest.raises(ns.NS3DError, match="outside"):
+        ctx.box(d, (2, 1), (0, 4), (0, 3))
+
+
+@pytest.mark.parametrize("variant", ["M", "G"])
+def test_interior_and_planes_of_a_simulation(ns, variant):
+    s = ns.setup_multi_gpu(40) if variant == "M" else ns.setup_gpu(40)
+    sim = ns.Simulation(s, ns.Context(0, ns.PARITY))
+    sim.step()
+    for name in ("C", "Pr", "Vx", "Vy", "Vz"):
+        full = sim.host(name)
+        assert np.array_equal(sim.interior(name), full[1:-1, 1:-1, 1:-1]), name
+        assert np.array_equal(sim.interior(name, np.float32), full[1:-1, 1:-1, 1:-1].astype(np.float32)), name
+        inn = full[1:-1, 1:-1, 1:-1]
+        kz, jy = -(-s.nz // 2), -(-s.ny // 2)          # ceil(Int, nz_g()/2), ceil(Int, ny_g()/2)  (M:422,428), 1-based
+        assert np.array_equal(sim.slice_xy(name), inn[:, :, kz - 1]), name
+        assert np.array_equal(sim.slice_xz(name), inn[:, jy - 1, :]), name
+    assert np.array_equal(sim.interior("Vz", drop_last_z=True), sim.host("Vz")[1:-1, 1:-1, 1:-2])
+    sim.ctx.close()
+
+
+def test_runme_do_save_writes_the_mat_file(ns, tmp_path, monkeypatch):
+    """G:168-170: every 10th step -> out_save/step_$it.mat with the script's (quirky) key set."""
+    from scipy.io import loadmat
+    monkeypatch.chdir(tmp_path)
+    sim = ns.runme(do_vis=False, do_save=True, nx=40, nt=10, mode=ns.PARITY, do_print=False, return_sim=True)
+    m = loadmat(tmp_path / "out_save" / "step_10.mat")
+    assert np.array_equal(m["Pr"], sim.host("Pr")) and np.array_equal(m["Vx"], sim.host("Vx"))
+    assert np.array_equal(m["Vy"], sim.host("Vz"))        # quirk 9: the second "Vy" => Array(Vz) wins
+    assert np.array_equal(m["Vy_true"], sim.host("Vy")) and np.array_equal(m["C"], sim.host("C"))
+    assert m["dx"].item() == sim.s.dx and m["dz"].item() == sim.s.dz
+    sim.ctx.close()
