@@ -11,7 +11,7 @@ pseudo-transient pressure loop with its residual checks, corrector, advection.
 Algorithmic bytes per step:  A_eff = (21 + 5*N_iter + 2*N_chk) * 8 * nx*ny*nz.
 
 Printed keys beyond the driver contract: "time_steps_per_s", "pt_iters_per_step",
-"roofline" (fused PT-iteration kernel: 40 B/cell/launch over the measured HBM peak),
+"roofline" (fused PT kernel: 40 B/cell/iteration, two iterations per launch, over the measured HBM peak),
 "cpu_baseline" (the CPU oracle, a restated reference CPU path, timed on a bounded sample).
 """
 from __future__ import annotations
@@ -416,7 +416,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm",
-                         "kernel": ("pt_tb2_kernel (two fused PT iterations per launch: 2 x (K5+K6+set_bc_Pr!))" if tb2_on
+                         "kernel": ("pt_tb2s_kernel (two fused PT iterations per launch: 2 x (K5+K6+set_bc_Pr!)"
+                                    + ("; slab-interface chunks: pt_tb2_kernel<.,16,true>)" if world > 1 else ")") if tb2_on
                                     else "pt_iter_kernel (fused K5+K6+set_bc_Pr!)"),
                          "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,

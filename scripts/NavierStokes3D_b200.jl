@@ -10,6 +10,7 @@
 # the same C ABI and is what the parity tests drive.
 include(joinpath(@__DIR__, "..", "julia", "NS3DNative.jl"))
 using .NS3DNative
+using Printf
 import MPI
 
 const USE_FUSED_PT = true     # false: the reference's loop, call site by call site (level 1)
@@ -92,10 +93,18 @@ const USE_FUSED_PT = true     # false: the reference's loop, call site by call s
         copy!(ctx, Vx_o, Vx); copy!(ctx, Vy_o, Vy); copy!(ctx, Vz_o, Vz); copy!(ctx, C_o, C)
         advect!(ctx, Vx, Vx_o, Vy, Vy_o, Vz, Vz_o, C, C_o, dt, dx, dy, dz)
         update_halo!(ctx, nz, Vx, Vy, Vz)
+        if do_save && it % 10 == 0 && me == 0                               # M:515-523 (nsave = 10), single rank
+            !ispath("./out_save") && mkdir("./out_save")
+            for (name, A) in (("C", C), ("Pr", Pr), ("Vx", Vx), ("Vy", Vy), ("Vz", Vz))
+                open(@sprintf("out_save/out_%s_v_%04d.bin", name, it ÷ 10), "w") do io
+                    write(io, inner32(ctx, A))                              # Float32 conversion on the device
+                end
+            end
+        end
     end
-    # return value (M:528-535): interior arrays (gathering over ranks is left to MPI.Gatherv here)
-    inn(A) = to_host(ctx, A)[2:end-1, 2:end-1, 2:end-1]
-    return inn(C), inn(Pr), inn(Vx), inn(Vy), inn(Vz)
+    # return value (M:528-535): interior arrays, extracted on the device (ns3d_box_d2h); gathering
+    # over ranks is left to MPI.Gatherv here
+    return inner(ctx, C), inner(ctx, Pr), inner(ctx, Vx), inner(ctx, Vy), inner(ctx, Vz)
 end
 
 if abspath(PROGRAM_FILE) == @__FILE__
