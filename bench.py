@@ -43,6 +43,13 @@ def a_eff_bytes(n_cells: int, n_iter: int, n_chk: int) -> float:
     return (21 + 5 * n_iter + 2 * n_chk) * 8.0 * n_cells
 
 
+def workload_name(key: str, variant: str, s) -> str:
+    """config.workload, shared by both arms (s: anything with nx, ny, nz, eps_it, niter, nchk)."""
+    script = "scripts/NavierStokes3D_gpu.jl" if variant == "G" else "scripts/NavierStokes3D_multi_gpu.jl"
+    return (f"{key}: cylinder flow {s.nx}x{s.ny}x{s.nz} cells per GPU, Float64, variant {variant} ({script} parameters), "
+            f"eps_it={s.eps_it}, niter={s.niter}, nchk={s.nchk}")
+
+
 def hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -148,8 +155,10 @@ def run_reference(args):
         "impl": "reference", "metric": "T_eff", "value": teff, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"cylinder flow {p.nx}x{p.ny}x{p.nz} Float64, variant {variant}, CPU oracle port "
-                               "(Julia/ParallelStencil Threads backend not installable here)"},
+        "config": {"workload": workload_name(args.workload, variant, p), "decomposition": "z-slabs x1",
+                   "implementation": "CPU oracle port of the reference's kernels, OpenMP over z like ParallelStencil's "
+                                     "Threads backend (Julia / ParallelStencil are not installable here); each step is "
+                                     "a bounded sample: one time step with the PT loop cut short"},
         "cpu_baseline": {"value": teff, "unit": "GB/s", "cores": last[0], "kind": "port", "sample": last[1]},
         "e2e": {"value": teff, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -403,9 +412,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": t_all / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": (f"{args.workload}: cylinder flow {s.nx}x{s.ny}x{s.nz} cells per GPU, Float64, variant "
-                             f"{variant} ({'scripts/NavierStokes3D_gpu.jl' if variant == 'G' else 'scripts/NavierStokes3D_multi_gpu.jl'}"
-                             f" parameters), eps_it={s.eps_it}, niter={s.niter}, nchk={s.nchk}"),
+                "workload": workload_name(args.workload, variant, s),
                 "decomposition": f"z-slabs x{world}", "mode": args.mode,
                 "l2_policy": "inputs larger than L2: PT working set 4 fields x %.1f MB > 126 MB" % (n_cells * 8 / 1e6)
                 if 4 * n_cells * 8 > 126e6 else "working set fits L2 (not a bandwidth figure)",
