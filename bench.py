@@ -141,7 +141,7 @@ def run_reference(args):
         return
     variant, nx, ny, nz = WORKLOADS[args.workload]
     vals, last = [], None
-    budget = 8.0
+    budget = args.sample_seconds
     for i in range(args.warmup + args.steps):
         teff, cores, sample, dt, iters = oracle_sample(variant, nx, ny, nz, budget_s=budget)
         if i >= args.warmup:
@@ -227,6 +227,8 @@ def main():
     ap.add_argument("--zchunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sample-seconds", type=float, default=8.0,
+                    help="--impl reference: CPU seconds of the bounded sample that makes one step")
     ap.add_argument("--pt-only", type=int, default=0,
                     help="Poisson-only benchmark (BASELINE configs[2]): time exactly this many PT iterations "
                          "(ns3d_pt_solve with eps_it=0, one residual check per 510) on a synthetic rhs instead of time steps")

@@ -134,3 +134,21 @@ def test_bench_algorithmic_bytes():
     assert bench.a_eff_bytes(n, 0, 0) == 168 * n          # once-per-step part: 21 passes
     assert bench.a_eff_bytes(n, 1, 0) - bench.a_eff_bytes(n, 0, 0) == 40 * n   # one PT iteration: 5 passes
     assert bench.a_eff_bytes(n, 0, 1) - bench.a_eff_bytes(n, 0, 0) == 16 * n   # one residual check: 2 passes
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference`: the CPU arm (oracle port on the host cores) with the native
+    arm's metric / unit / workload naming, `impl`, `cpu_baseline` and a zero-copy `e2e`."""
+    import json
+    import subprocess
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "A",
+                          "--steps", "1", "--warmup", "0", "--sample-seconds", "0.3"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "T_eff" and line["unit"] == "GB/s"
+    assert line["higher_is_better"] is True and line["dtype"] == "f64" and line["value"] > 0
+    assert line["config"]["workload"].startswith("A: cylinder flow 63x38x38")
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0
