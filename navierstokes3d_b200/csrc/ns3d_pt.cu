@@ -1,19 +1,19 @@
-// libns3d.so -- the hot loop: fused pseudo-transient (PT) pressure iteration.
+// libns3d.so -- the hot loop: fused pseudo-transient (PT) pressure iteration, host side.
 //
 // Reference (per PT iteration, M:459-463 / G:127-129): update_dPrdτ! (K5), update_Pr! (K6),
 // set_bc_Pr! = 3-4 face kernels (K7) and up to three update_halo! calls: >= 5 synchronous
-// launches and 7+ full-field passes.  Here ONE launch per iteration does all of it in
-// 5 passes (read Pr, dPrdτ, ∇V; write Pr', dPrdτ): Pr ping-pongs between the caller's array
-// and a context-owned shadow so that every thread reads a consistent old iterate, and the
-// boundary conditions are folded in: after x,y,z zero-gradient copies every boundary point
-// equals the new value at its index clamped into the interior, so the
-// thread that owns an interior point next to a face also stores its mirror images.
+// launches and 7+ full-field passes.  The device code that replaces it lives in
+// ns3d_pt_kernels.cuh (a header without CUDA runtime includes, so that the CPU test suite can
+// execute the same source on host threads, tests/emu/):
+//   pt_tb2s_kernel  two iterations per launch, 5 field passes per TWO iterations  (default)
+//   pt_tb2_kernel   its first version; <.,.,true> also exchanges the slab halos over peer memory
+//   pt_iter_kernel  one iteration per launch (odd trailing iteration, option tb2=0)
+// This file holds what needs the runtime: kernel parameters and launch geometry (make_ptk),
+// the ping-pong buffers, stream/event protocol and peer mappings of the slab path, CUDA-graph
+// replay of iteration chunks, the residual reduction, and the entry points ns3d_pt_solve,
+// ns3d_pt_iterate and ns3d_step.
 //
-// Thread mapping: x on threadIdx.x (coalesced rows), a (32 x BY) tile of interior columns
-// per CTA, each thread marches `zchunk` planes along z keeping Pr[k-1], Pr[k], Pr[k+1] of
-// its column in registers (2.5-D blocking); the x/y neighbours come through L1.
-//
-// Arithmetic (template MODE): see NS3D_PARITY / NS3D_FAST / NS3D_FASTEST in ns3d.h.  The file
+// Arithmetic (template MODE): see NS3D_PARITY / NS3D_FAST / NS3D_FASTEST in ns3d.h.  The library
 // is compiled with --fmad=false; FMA appears only where fma() is written explicitly.
 #include <algorithm>
 #include <cmath>
@@ -240,9 +240,10 @@ int launch_tb2(ns3d_ctx* ctx, cudaStream_t st, const PtK& k_in, const double* cu
 }
 
 // Two iterations per launch is the default path wherever it applies (single rank, or slabs with
-// the peer-memory halo path): measured sustained gains +11 % at 255x153x153 (T_eff 6.36 TB/s),
-// +27 % at 511^3 (7.9-8.1 TB/s, above the HBM copy peak), +9.5 % per GPU on two slabs
-// (profiles/r01_tb2_*.jsonl).  ns3d_set_option("tb2", 0) selects the one-iteration kernel.
+// the peer-memory halo path).  Measured against the one-iteration kernel: 39.4 -> 31.3 us per
+// iteration at 255x153x153 (T_eff 7.06 TB/s for whole time steps), 856 -> 548 us at 511^3
+// (9.7 TB/s, above the HBM copy peak); DESIGN.md 3.4-3.5, profiles/README.md.
+// ns3d_set_option("tb2", 0) selects the one-iteration kernel.
 bool use_tb2(const ns3d_ctx* ctx, const ns3d_pt_params* p, bool peer_on)
 {
     (void)p;

@@ -5,6 +5,18 @@
 // CUDA thread of a block runs as a host thread and __syncthreads() is a barrier -- the CPU test
 // suite executes these kernels bit-for-bit against the oracle without a GPU
 // (tests/test_kernel_emu.py).  The includer provides the CUDA qualifiers and ns3d_shared.cuh.
+//
+// What every kernel here computes per cell is the reference's K5 + K6 + K7 (M:70-82, 175-184):
+//     dPrdτ' = dPrdτ*(1-damp) + dτ*(d2x/dx/dx + d2y/dy/dy + d2z/dz/dz - ρ/dt*∇V)     M:71
+//     Pr'    = Pr + dτ*dPrdτ'                                                       M:80
+// on the interior, then set_bc_Pr!: after the zero-gradient copies in the order x, y, z every
+// boundary point equals the new value at its index clamped into the interior (SURVEY.md Appendix
+// A), then the outlet plane is overwritten (variant M, bc_x_Pr!) or both x planes get the
+// hydrostatic profile (variant G, bc_xhydstatic!) -- so the thread that owns an interior point next
+// to a face also stores its mirror images, and no boundary kernel exists.  Pr (and, in the
+// two-iteration kernels, dPrdτ) ping-pong between two buffers so that every thread reads a
+// consistent old iterate.  Thread mapping: x on threadIdx.x (coalesced rows), one column per
+// thread marched along z with the z neighbours in registers (2.5-D blocking).
 #pragma once
 
 #include "ns3d_shared.cuh"
@@ -315,7 +327,9 @@ __global__ void __launch_bounds__(256, MINB) pt_iter_kernel(const double* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// Two PT iterations per launch (temporal blocking, opt-in: ns3d_set_option("tb2", 1)).
+// Two PT iterations per launch (temporal blocking), first version.  Plain launches now run the
+// re-write below (pt_tb2s_kernel, bit-identical results); this kernel stays for its P2P = true
+// instantiation, which also performs update_halo!(Pr) over peer memory on slab interfaces.
 //
 // A CTA owns a 32x16 tile of columns and marches along z with a two-stage pipeline: stage 1
 // computes the first iteration's pressure q = Pr^(1) of plane s for every tile column (from
