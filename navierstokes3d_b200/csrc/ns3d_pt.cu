@@ -173,25 +173,26 @@ struct PeerBufs {
     const double* dP_user = nullptr;
 };
 
+PeerPtrs peer_ptrs(const ns3d_ctx* ctx, const PeerBufs& pb)
+{
+    PeerPtrs pp;
+    for (int q = 0; q < 4; ++q) {
+        pp.lo[q] = pb.lo[q];
+        pp.hi[q] = pb.hi[q];
+    }
+    pp.mbox = ctx->mbox;
+    pp.lo_mbox = ctx->peer_mbox[0];
+    pp.hi_mbox = ctx->peer_mbox[1];
+    return pp;
+}
+
 int launch_tb2(ns3d_ctx* ctx, cudaStream_t st, const PtK& k_in, const double* cur, double* nxt, const double* dpc,
                double* dpn, const double* divV, const PeerBufs& pb, const double* Pr_user, bool peer)
 {
     PtK k = k_in;
     if (!k.faces) balance_chunks(k);
     if (peer) {
-        const int wp = (nxt == Pr_user) ? 0 : 1;        // neighbours' NEW iterate: same role as ours
-        const int wc = 1 - wp;                          // ... CURRENT iterate
-        const int wd = (dpc == pb.dP_user) ? 2 : 3;     // ... CURRENT dPrdτ
-        const ptrdiff_t sxy = (ptrdiff_t)k.nx * k.ny, dxy = (ptrdiff_t)(k.nx - 2) * (k.ny - 2);
-        k.mbox = ctx->mbox;
-        k.peer_lo_plane = pb.lo[wp] ? pb.lo[wp] + (ptrdiff_t)(k.nz - 1) * sxy : nullptr;
-        k.peer_hi_plane = pb.hi[wp];
-        k.peer_lo_cur = pb.lo[wc] ? pb.lo[wc] + (ptrdiff_t)(k.nz - 3) * sxy : nullptr;
-        k.peer_hi_cur = pb.hi[wc] ? pb.hi[wc] + 2 * sxy : nullptr;
-        k.peer_lo_dp = pb.lo[wd] ? pb.lo[wd] + (ptrdiff_t)(k.nz - 3) * dxy : nullptr;
-        k.peer_hi_dp = pb.hi[wd];
-        k.peer_lo_flag = ctx->peer_mbox[0] ? ctx->peer_mbox[0] + NS3D_MB_FLAG_HI : nullptr;
-        k.peer_hi_flag = ctx->peer_mbox[1] ? ctx->peer_mbox[1] + NS3D_MB_FLAG_LO : nullptr;
+        ptk_set_peers(k, peer_ptrs(ctx, pb), (nxt == Pr_user) ? 0 : 1, (dpc == pb.dP_user) ? 2 : 3);
     }
     const int ty = k.mbox ? 16 : k.tb_ty;
     const dim3 blk(TB_X, ty, 1);
@@ -345,14 +346,8 @@ int pt_iteration(ns3d_ctx* ctx, const PtK& k, const double* cur, double* nxt, do
         // and nz-3) a single iteration is one unsplit launch: the CTAs that own those planes are
         // then the ones that signal.
         PtK q = k;
-        const int which = (nxt == Pr_user) ? 0 : 1;
-        const ptrdiff_t sxy = (ptrdiff_t)k.nx * k.ny;
         balance_chunks(q);
-        q.mbox = ctx->mbox;
-        q.peer_lo_plane = pb.lo[which] ? pb.lo[which] + (ptrdiff_t)(k.nz - 1) * sxy : nullptr;
-        q.peer_hi_plane = pb.hi[which];
-        q.peer_lo_flag = ctx->peer_mbox[0] ? ctx->peer_mbox[0] + NS3D_MB_FLAG_HI : nullptr;
-        q.peer_hi_flag = ctx->peer_mbox[1] ? ctx->peer_mbox[1] + NS3D_MB_FLAG_LO : nullptr;
+        ptk_set_peers(q, peer_ptrs(ctx, pb), (nxt == Pr_user) ? 0 : 1, -1);
         return launch_iter(ctx, ctx->stream, q, cur, nxt, dP, divV);
     }
     if (pb.on) {
@@ -361,14 +356,8 @@ int pt_iteration(ns3d_ctx* ctx, const PtK& k, const double* cur, double* nxt, do
         // hand over with mailbox flags.  It runs on the high-priority stream next to the launch
         // that updates the other planes; kernel-only, so whole chunks replay as a CUDA graph.
         PtK q = k, inner = k;
-        const int which = (nxt == Pr_user) ? 0 : 1;  // all ranks ping-pong in lockstep
-        const ptrdiff_t sxy = (ptrdiff_t)k.nx * k.ny;
         q.faces = 1;
-        q.mbox = ctx->mbox;
-        q.peer_lo_plane = pb.lo[which] ? pb.lo[which] + (ptrdiff_t)(k.nz - 1) * sxy : nullptr;
-        q.peer_hi_plane = pb.hi[which];
-        q.peer_lo_flag = ctx->peer_mbox[0] ? ctx->peer_mbox[0] + NS3D_MB_FLAG_HI : nullptr;
-        q.peer_hi_flag = ctx->peer_mbox[1] ? ctx->peer_mbox[1] + NS3D_MB_FLAG_LO : nullptr;
+        ptk_set_peers(q, peer_ptrs(ctx, pb), (nxt == Pr_user) ? 0 : 1, -1);
         inner.kbeg = 2;
         inner.kend = k.nz - 2;
         NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_a, 0));

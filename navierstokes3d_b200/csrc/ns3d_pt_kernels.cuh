@@ -798,6 +798,38 @@ inline void ptk_fill(const ns3d_pt_params* p, PtK* k)
     k->dplaneB = 8LL * (p->nx - 2) * (p->ny - 2);
 }
 
+// The neighbours' buffers as this rank sees them (CUDA IPC mappings on the device, shared memory in
+// the host emulation): {Pr, Pr shadow, dPrdτ, dPrdτ shadow} of the lower / upper neighbour (NULL
+// without one), this rank's mailbox and the neighbours' mailboxes.
+struct PeerPtrs {
+    double* lo[4];
+    double* hi[4];
+    unsigned long long* mbox;
+    unsigned long long* lo_mbox;
+    unsigned long long* hi_mbox;
+};
+
+// Where a launch on a slab interface reads and writes in its neighbours' memory.  All ranks
+// ping-pong in lockstep, so a neighbour's buffers play the role of this rank's: `w_new` is the
+// index (0 user array, 1 shadow) of the Pr buffer this launch WRITES, `w_dp` (2 user, 3 shadow) of
+// the dPrdτ buffer it READS; w_dp < 0 for the one-iteration kernel, which reads nothing remote.
+inline void ptk_set_peers(PtK& k, const PeerPtrs& pp, int w_new, int w_dp)
+{
+    const ptrdiff_t sxy = (ptrdiff_t)k.nx * k.ny, dxy = (ptrdiff_t)(k.nx - 2) * (k.ny - 2);
+    k.mbox = pp.mbox;
+    k.peer_lo_plane = pp.lo[w_new] ? pp.lo[w_new] + (ptrdiff_t)(k.nz - 1) * sxy : nullptr;  // its halo plane nz-1
+    k.peer_hi_plane = pp.hi[w_new];                                                        // its halo plane 0
+    k.peer_lo_flag = pp.lo_mbox ? pp.lo_mbox + NS3D_MB_FLAG_HI : nullptr;
+    k.peer_hi_flag = pp.hi_mbox ? pp.hi_mbox + NS3D_MB_FLAG_LO : nullptr;
+    if (w_dp >= 0) {
+        const int w_cur = 1 - w_new;  // the neighbours' CURRENT iterate
+        k.peer_lo_cur = pp.lo[w_cur] ? pp.lo[w_cur] + (ptrdiff_t)(k.nz - 3) * sxy : nullptr;
+        k.peer_hi_cur = pp.hi[w_cur] ? pp.hi[w_cur] + 2 * sxy : nullptr;
+        k.peer_lo_dp = pp.lo[w_dp] ? pp.lo[w_dp] + (ptrdiff_t)(k.nz - 3) * dxy : nullptr;
+        k.peer_hi_dp = pp.hi[w_dp];
+    }
+}
+
 // Balanced z-chunks whose last one keeps at least two planes: on slabs a neighbour reads plane
 // nz-3 (resp. 2) of this rank, and the CTAs that own it are the ones holding the hand-over flag.
 inline void balance_chunks(PtK& k)

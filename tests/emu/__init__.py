@@ -51,7 +51,82 @@ def lib() -> C.CDLL:
         _lib.emu_pt_tb2_split.restype = C.c_int
         _lib.emu_pt_tb2_split.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_int, C.c_int, C.c_int, C.c_int]
+        _lib.emu_pt_slab_iterate.restype = C.c_int
+        _lib.emu_pt_slab_iterate.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     return _lib
+
+
+class EmuSlab(C.Structure):
+    """``EmuSlab`` of pt_emu.cpp: this rank's buffers and the neighbours' as 16 raw addresses."""
+    _fields_ = [("pr", C.c_void_p * 2), ("dp", C.c_void_p * 2), ("divV", C.c_void_p),
+                ("lo", C.c_void_p * 4), ("hi", C.c_void_p * 4),
+                ("mbox", C.c_void_p), ("lo_mbox", C.c_void_p), ("hi_mbox", C.c_void_p)]
+
+
+class SlabMemory:
+    """The shared-memory image of one rank of an emulated z-slab run: Pr, its shadow, dPrdτ, its
+    shadow, ∇V (each padded by three planes like ns3d_zeros pads) and a 16-word mailbox, in ONE
+    ``multiprocessing.shared_memory`` block that the neighbouring rank processes map as well --
+    the stand-in for the CUDA IPC mappings of the peer-memory halo path."""
+
+    def __init__(self, nx, ny, nz, name=None, create=False):
+        from multiprocessing import shared_memory
+        self.shape, self.dshape = (nx, ny, nz), (nx - 2, ny - 2, nz - 2)
+        n, nd = nx * ny * nz, (nx - 2) * (ny - 2) * (nz - 2)
+        pn, pd = n + 3 * nx * ny + 32, nd + 3 * (nx - 2) * (ny - 2) + 32
+        self.counts = [pn, pn, pd, pd, pn, 16]           # Pr, Pr shadow, dP, dP shadow, divV, mailbox
+        self.offsets = np.concatenate([[0], np.cumsum(self.counts)[:-1]]) * 8
+        size = int(sum(self.counts) * 8)
+        self.shm = shared_memory.SharedMemory(name=name, create=create, size=size)
+        self._anchor = C.c_char.from_buffer(self.shm.buf)
+        self.base = C.addressof(self._anchor)
+        if create:
+            whole = np.frombuffer(self.shm.buf, dtype=np.float64, count=sum(self.counts))
+            whole[:] = np.nan                            # padding and shadows: a value USED from there poisons the result
+            whole[-16:] = 0.0                            # mailbox words start at zero
+            del whole
+
+    def addr(self, which: int) -> int:
+        return self.base + int(self.offsets[which])
+
+    def view(self, which: int) -> np.ndarray:
+        """A copy-free view while alive; callers drop it before close()."""
+        shape = self.dshape if which in (2, 3) else self.shape
+        return np.frombuffer(self.shm.buf, dtype=np.float64, count=int(np.prod(shape)),
+                             offset=int(self.offsets[which])).reshape(shape, order="F")
+
+    def close(self, unlink=False):
+        self._anchor = None
+        try:
+            self.shm.close()
+        except BufferError:      # a view is still alive somewhere: the mapping goes away with the process
+            pass
+        if unlink:
+            self.shm.unlink()
+
+
+def slab_rank_main(rank, nranks, names, grid, kernel, mode, pt_bytes, n_iter, kernel_mid, ty_mid, queue):
+    """Body of one rank process: map own and neighbours' memory, run the launches, report."""
+    try:
+        mem = {r: SlabMemory(*grid, name=names[r]) for r in (rank - 1, rank, rank + 1) if 0 <= r < nranks}
+        me = mem[rank]
+        b = EmuSlab()
+        b.pr[0], b.pr[1], b.dp[0], b.dp[1], b.divV = me.addr(0), me.addr(1), me.addr(2), me.addr(3), me.addr(4)
+        b.mbox = me.addr(5)
+        for side, r in (("lo", rank - 1), ("hi", rank + 1)):
+            if r in mem:
+                arr = getattr(b, side)
+                for q in range(4):
+                    arr[q] = mem[r].addr(q)
+                setattr(b, side + "_mbox", mem[r].addr(5))
+        pt = (C.c_char * len(pt_bytes)).from_buffer_copy(pt_bytes)
+        wp, wd = C.c_int(-1), C.c_int(-1)
+        rc = lib().emu_pt_slab_iterate(KERNELS[kernel], mode, C.addressof(pt), rank, nranks, C.addressof(b), n_iter,
+                                       KERNELS[kernel_mid], ty_mid, C.byref(wp), C.byref(wd))
+        queue.put((rank, rc, wp.value, wd.value))
+    except BaseException as exc:  # noqa: BLE001
+        queue.put((rank, -99, repr(exc), 0))
 
 
 def pt_tb2_split(kernel_mid: str, mode: int, pt_params, Pr, dP, divV, n_pairs: int, klo: int, khi: int,

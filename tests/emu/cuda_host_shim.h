@@ -8,6 +8,7 @@
 #include <pthread.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -43,7 +44,10 @@ using std::min;
 
 inline void __syncthreads() { pthread_barrier_wait(&emu::g_barrier); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-inline long long clock64() { return 0; }
+inline long long clock64()  // nanoseconds: the kernels' spin limits (8e9 "cycles") become 8 s
+{
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 template <class T>
 inline T __ldcv(const T* p)
 {

@@ -116,7 +116,101 @@ int run_split(int kernel_mid, int ty_mid, PtK k, double* Pr, double* dP, const d
     return 0;
 }
 
+// ---- one rank of a z-slab run: the peer-memory halo exchange fused into the kernels ----------------
+// Every rank is a separate PROCESS; its fields, shadows and mailbox live in shared memory that the
+// neighbours map too -- what CUDA IPC does for GPUs.  The launches below are the ones run_direct()
+// and pt_iteration() issue on slabs (ns3d_pt.cu), minus streams and graphs: the emulation runs a
+// rank's launches one after the other, while the ranks themselves run concurrently and meet only
+// through the mailbox protocol.
+struct EmuSlab {
+    double* pr[2];            // this rank's Pr: user array, shadow
+    double* dp[2];            // this rank's dPrdτ: user array, shadow
+    const double* divV;
+    PeerPtrs peers;           // neighbours' {Pr, Pr shadow, dPrdτ, dPrdτ shadow}, the three mailboxes
+};
+
+template <int MODE>
+int run_slab(int kernel, PtK k, const EmuSlab& b, int n_iter, int kernel_mid, int ty_mid, int zchunk_tb, int zchunk_iter,
+             int* which_pr, int* which_dp)
+{
+    int ip = 0, id = 0;  // index of the CURRENT Pr / dPrdτ buffer
+    int q = 0;
+    const int zf = 8;    // planes per face chunk of the split launch (run_direct)
+    if (kernel != 0) {
+        const bool split = (k.nz - 2) >= 2 * zf + 4;
+        for (; q + 2 <= n_iter; q += 2) {
+            PtK k2 = k;
+            k2.zchunk = zchunk_tb;
+            k2.reverse = (q >> 1) & 1;
+            const double* cur = b.pr[ip];
+            double* nxt = b.pr[1 - ip];
+            const double* dpc = b.dp[id];
+            double* dpn = b.dp[1 - id];
+            if (split) {
+                PtK f = k2, in = k2;
+                f.faces = 1;
+                f.zchunk = zf;
+                ptk_set_peers(f, b.peers, 1 - ip, 2 + id);
+                in.kbeg = 1 + zf;
+                in.kend = k.nz - 1 - zf;
+                emu::launch(dim3(cdivu(k.nx - 2, TB_X - 2), cdivu(k.ny - 2, 16 - 2), 2), dim3(TB_X, 16, 1),
+                            [=]() { pt_tb2_kernel<MODE, 16, true>(cur, nxt, dpc, dpn, b.divV, f); });
+                if (ty_mid == 8) launch_tb2<MODE, 8>(kernel_mid, in, cur, nxt, dpc, dpn, b.divV);
+                else launch_tb2<MODE, 16>(kernel_mid, in, cur, nxt, dpc, dpn, b.divV);
+            } else {
+                PtK u = k2;
+                balance_chunks(u);
+                ptk_set_peers(u, b.peers, 1 - ip, 2 + id);
+                emu::launch(dim3(cdivu(k.nx - 2, TB_X - 2), cdivu(k.ny - 2, 16 - 2), cdivu(u.kend - u.kbeg, u.zchunk)),
+                            dim3(TB_X, 16, 1), [=]() { pt_tb2_kernel<MODE, 16, true>(cur, nxt, dpc, dpn, b.divV, u); });
+            }
+            ip = 1 - ip;
+            id = 1 - id;
+        }
+    }
+    for (; q < n_iter; ++q) {  // pt_iteration(): one unsplit launch of the peer-store instantiation
+        PtK u = k;
+        u.zchunk = zchunk_iter;
+        u.reverse = q & 1;
+        balance_chunks(u);
+        ptk_set_peers(u, b.peers, 1 - ip, -1);
+        const double* cur = b.pr[ip];
+        double* nxt = b.pr[1 - ip];
+        double* dP = b.dp[id];
+        emu::launch(dim3(cdivu(k.nx - 2, 32), cdivu(k.ny - 2, 8), cdivu(u.kend - u.kbeg, u.zchunk)), dim3(32, 8, 1),
+                    [=]() { pt_iter_kernel<MODE, 4, true>(cur, nxt, dP, b.divV, u); });
+        ip = 1 - ip;
+    }
+    // peer_join(): the halos of the current iterate are complete once both neighbours have caught up
+    if (k.zlo_halo) wait_neighbour(b.peers.mbox, 0);
+    if (k.zhi_halo) wait_neighbour(b.peers.mbox, 1);
+    *which_pr = ip;
+    *which_dp = id;
+    return b.peers.mbox[NS3D_MB_ERROR] ? -2 : 0;
+}
+
 }  // namespace
+
+// One rank of an N-rank z-slab run (call it from N processes at once).  All buffers are padded like
+// ns3d_zeros pads; *which_pr / *which_dp tell which of the two buffers hold the result.
+extern "C" int emu_pt_slab_iterate(int kernel, int mode, const ns3d_pt_params* pp, int rank, int nranks, const EmuSlab* b,
+                                   int n_iter, int kernel_mid, int ty_mid, int* which_pr, int* which_dp)
+{
+    if (!pp || !b || nranks < 2 || pp->nz < 6) return -1;
+    PtK k;
+    std::memset(&k, 0, sizeof k);
+    ptk_fill(pp, &k);
+    k.zlo_halo = rank > 0;
+    k.zhi_halo = rank < nranks - 1;
+    const int zc_iter = pp->zchunk > 0 ? pp->zchunk : 8;
+    const int zc_tb = pp->zchunk > 0 ? pp->zchunk : 12;
+    switch (mode) {
+        case NS3D_PARITY: return run_slab<NS3D_PARITY>(kernel, k, *b, n_iter, kernel_mid, ty_mid, zc_tb, zc_iter, which_pr, which_dp);
+        case NS3D_FAST: return run_slab<NS3D_FAST>(kernel, k, *b, n_iter, kernel_mid, ty_mid, zc_tb, zc_iter, which_pr, which_dp);
+        case NS3D_FASTEST: return run_slab<NS3D_FASTEST>(kernel, k, *b, n_iter, kernel_mid, ty_mid, zc_tb, zc_iter, which_pr, which_dp);
+    }
+    return -1;
+}
 
 extern "C" int emu_pt_tb2_split(int kernel_mid, int mode, int ty_mid, const ns3d_pt_params* pp, double* Pr, double* dP,
                                 const double* divV, int n_pairs, int klo, int khi, int zchunk_mid)
