@@ -194,13 +194,15 @@ int launch_tb2(ns3d_ctx* ctx, cudaStream_t st, const PtK& k_in, const double* cu
     if (peer) {
         ptk_set_peers(k, peer_ptrs(ctx, pb), (nxt == Pr_user) ? 0 : 1, (dpc == pb.dP_user) ? 2 : 3);
     }
-    const int ty = k.mbox ? 16 : k.tb_ty;
-    const dim3 blk(TB_X, ty, 1);
+    // round-2 candidate (unmeasured, off by default): two tile rows per thread, 32x16 tiles of 8 warps
+    const int dual = k.mbox ? 0 : ctx->opt_tb2_dual;
+    const int ty = (k.mbox || dual) ? 16 : k.tb_ty;
+    const dim3 blk(TB_X, dual ? ty / 2 : ty, 1);
     const dim3 grd(cdiv(k.nx - 2, TB_X - 2), cdiv(k.ny - 2, ty - 2), k.faces ? 2u : cdiv(k.kend - k.kbeg, k.zchunk));
     // plain launches run the slim re-write (pt_tb2s_kernel, same results); chunks on a slab
     // interface need the peer loads/stores of pt_tb2_kernel<.,.,true>
     const bool slim = !k.mbox && ctx->opt_tb2_slim;
-    if (slim) tb2s_set_offsets(k, cur, nxt, dpc, dpn, divV);
+    if (slim || dual) tb2s_set_offsets(k, cur, nxt, dpc, dpn, divV);
     // Grids whose x-y extent has a compile-time instantiation (default variant only): the
     // reference scripts' nx = 255 and BASELINE.json's 511^2 / 1023x511 planes.
 #define TBS_ARGS <<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k)
@@ -218,9 +220,17 @@ int launch_tb2(ns3d_ctx* ctx, cudaStream_t st, const PtK& k_in, const double* cu
         else if (pf == 1) pt_tb2s_kernel<MODE, TY, 1, false, 0, 0> TBS_ARGS;                                     \
         else pt_tb2s_kernel<MODE, TY, 0, false, 0, 0> TBS_ARGS;                                                  \
     } while (0)
+#define TBD_LAUNCH(MODE, MINB)                                                                                 \
+    do {                                                                                                       \
+        if (k.nx == 255 && k.ny == 153) pt_tb2d_kernel<MODE, 16, 1, MINB, 255, 153> TBS_ARGS;                  \
+        else if (k.nx == 511 && k.ny == 511) pt_tb2d_kernel<MODE, 16, 1, MINB, 511, 511> TBS_ARGS;             \
+        else pt_tb2d_kernel<MODE, 16, 1, MINB, 0, 0> TBS_ARGS;                                                 \
+    } while (0)
 #define TB_LAUNCH(MODE)                                                                                        \
     do {                                                                                                       \
         if (k.mbox) pt_tb2_kernel<MODE, 16, true><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);          \
+        else if (dual == 3) TBD_LAUNCH(MODE, 3);                                                               \
+        else if (dual) TBD_LAUNCH(MODE, 2);                                                                    \
         else if (slim && ty == 8) TBS_LAUNCH(MODE, 8);                                                         \
         else if (slim && ty == 32) TBS_LAUNCH(MODE, 32);                                                       \
         else if (slim) TBS_LAUNCH(MODE, 16);                                                                   \
@@ -235,6 +245,7 @@ int launch_tb2(ns3d_ctx* ctx, cudaStream_t st, const PtK& k_in, const double* cu
     }
 #undef TB_LAUNCH
 #undef TBS_LAUNCH
+#undef TBD_LAUNCH
 #undef TBS_ARGS
     NS3D_LAUNCH_CHECK(ctx);
     return NS3D_OK;
@@ -482,7 +493,7 @@ int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double*& d
     key.reverse = 0;
     // every tuning option that selects a kernel or its launch shape is part of the key
     const int opts = ctx->opt_tb2 | (ctx->opt_tb2_slim << 1) | (ctx->opt_tb2_np << 2) | (ctx->opt_tb2_pf << 3) |
-                     (ctx->opt_tb2_spec << 5) | (ctx->opt_tb2_ty << 8);
+                     (ctx->opt_tb2_spec << 5) | (ctx->opt_tb2_dual << 6) | (ctx->opt_tb2_ty << 8);
     PtGraph* g = nullptr;
     for (PtGraph& c : cache->slot)
         if (c.exec && c.cur == cur && c.nxt == nxt && c.dP == dP && c.dPn == dPn && c.divV == divV && c.n == n &&

@@ -753,6 +753,227 @@ __global__ void __launch_bounds__(TB_X* TB_Y, 1024 / (TB_X * TB_Y)) pt_tb2s_kern
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// pt_tb2d_kernel: pt_tb2s_kernel with TWO tile rows per thread (rows 2*ty and 2*ty+1 of a 32 x TB_Y
+// tile, TB_Y/2 thread rows).  CANDIDATE for round 2 -- bit-exact in the emulation and on the parity
+// tests, NOT yet measured against pt_tb2s_kernel (option "tb2_dual", off by default).  Why it
+// might pay (ncu of pt_tb2s_kernel at 255x153x153: issue slots 60 % busy; per issue 3.0 warps at
+// the barrier, 2.1 on fixed-latency dependencies):
+//   * 8-warp CTAs (cheap barriers, 4 per SM at 32x8 threads) with the rim ratio of 32x16 tiles
+//     (82 % of the columns produce output instead of 70 %);
+//   * two independent dependency chains per thread; half as many barriers per cell;
+//   * the rows' mutual y neighbours are the thread's own registers: 6 instead of 8 neighbour
+//     loads (stage 1) and shared-memory reads (stage 2) per two cells.
+// It costs registers (two sets of per-column state): MINB = CTAs per SM the kernel is compiled for.
+// ---------------------------------------------------------------------------------------------
+struct Tb2dInv {
+    double* PrN;
+    int kb_own[2];   // first stage-2 plane of each row (INT_MAX for rows that own no column)
+    int top_own[2];  // nz-2 when the row closes the physical top face in this chunk, else -1
+    int edge[2];     // owner row next to an x/y face
+    int xfix;        // x-face column with a non-Neumann condition (same for both rows)
+    int adj;         // the rows are neighbours in MEMORY too (no clamping between them): stage 1 of
+                     // row 0 takes its y+ neighbour from row 1's registers and vice versa
+    int bx, by;
+};
+
+template <int MODE, int TB_Y, int SLOT, int PF, int NXC, int NYC>
+__device__ __forceinline__ void tb2d_step(const PtK& p, const Tb2dInv& v, const int s, const char* (&c)[2],
+                                          const char* (&d)[2], double* __restrict__ sm, double (&PM)[2], double (&PC)[2],
+                                          double (&ZP)[2], double (&DQ)[2], double (&DVC)[2], double (&DV)[2],
+                                          double (&DVN)[2], double (&QM)[2], double (&QC)[2], double (&QN)[2],
+                                          double (&D1C)[2], double (&NX)[2][2], double (&NY)[2], double (&NM)[2])
+{
+#define LD(ptr) (*(const double*)(ptr))
+    constexpr int SLOTSZ = TB_Y * TB_X;
+    typedef Tb2sStride<NXC, NYC> G;
+#define rowB (G::row(p))
+#define planeB (G::plane(p))
+#define dplaneB (G::dplane(p))
+    // ---- stage 1: first iteration of plane s for both rows (operands were loaded one step ahead) ----
+    double D1N[2];
+    {
+        const double yp0 = v.adj ? PC[1] : NM[0];  // y+ of row 0
+        const double ym1 = v.adj ? PC[0] : NM[1];  // y- of row 1
+        const double L0 = bracket<MODE>(p, PC[0], NX[0][0], NX[0][1], NY[0], yp0, PM[0], ZP[0], DV[0]);
+        const double L1 = bracket<MODE>(p, PC[1], NX[1][0], NX[1][1], ym1, NY[1], PM[1], ZP[1], DV[1]);
+        pt_update<MODE>(p, L0, DQ[0], PC[0], D1N[0], QN[0]);
+        pt_update<MODE>(p, L1, DQ[1], PC[1], D1N[1], QN[1]);
+    }
+    // ---- operands of the next plane (PM, DQ, NX, NY, NM are dead) ------------------------------------
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const char* a_dvn = NXC > 0 ? (c[r] + p.oDV) + planeB : c[r] + p.oDVn;
+        const char* a_zp2 = NXC > 0 ? c[r] + 2 * planeB : c[r] + p.oZP2;
+        const char* cn = c[r] + planeB;
+        DVN[r] = LD(a_dvn);
+        PM[r] = LD(a_zp2);
+        DQ[r] = LD(d[r] + dplaneB);
+        NX[r][0] = LD(cn - 8);
+        NX[r][1] = LD(cn + 8);
+        if (PF > 0) {
+            prefetch_l2(a_zp2 + PF * planeB);
+            prefetch_l2(d[r] + (1 + PF) * dplaneB);
+            prefetch_l2(a_dvn + PF * planeB);
+        }
+    }
+    NY[0] = LD(c[0] + planeB - rowB);
+    NY[1] = LD(c[1] + planeB + rowB);
+    if (!v.adj) {
+        NM[0] = LD(c[0] + planeB + rowB);
+        NM[1] = LD(c[1] + planeB - rowB);
+    }
+    if (v.xfix) {  // bc_x_Pr! / bc_xhydstatic! images (x-face columns only)
+        QN[0] = xface(p, v.xfix > 1, s, QN[0]);
+        QN[1] = xface(p, v.xfix > 1, s, QN[1]);
+    }
+    sm[SLOT * SLOTSZ] = QN[0];
+    sm[SLOT * SLOTSZ + TB_X] = QN[1];
+    // ---- stage 2: second iteration of plane s-1 (ring slot published by the previous barrier) ---------
+    const int k2 = s - 1;
+    {
+        const double* r0 = sm + ((SLOT + 2) % 3) * SLOTSZ;
+        const double* r1 = r0 + TB_X;
+        if (k2 >= v.kb_own[0]) {
+            const double L2 = bracket<MODE>(p, QC[0], r0[-1], r0[1], r0[-TB_X], QC[1], QM[0], QN[0], DVC[0]);
+            double d2, u;
+            pt_update<MODE>(p, L2, D1C[0], QC[0], d2, u);
+            *(double*)(const_cast<char*>(d[0]) + p.oDP) = d2;
+            *(double*)(const_cast<char*>(c[0]) + p.oPr) = u;
+            if (v.edge[0] | (k2 == 1)) {
+                const int i = v.bx + (int)threadIdx.x, j = v.by + 2 * (int)threadIdx.y;
+                tb2s_images(p, v.PrN, i, j, k2, (k2 == 1 && !p.zlo_halo) ? 0 : -1, u, i == 1, i == p.nx - 2, j == 1,
+                            j == p.ny - 2);
+            }
+        }
+        if (k2 >= v.kb_own[1]) {
+            const double L2 = bracket<MODE>(p, QC[1], r1[-1], r1[1], QC[0], r1[TB_X], QM[1], QN[1], DVC[1]);
+            double d2, u;
+            pt_update<MODE>(p, L2, D1C[1], QC[1], d2, u);
+            *(double*)(const_cast<char*>(d[1]) + p.oDP) = d2;
+            *(double*)(const_cast<char*>(c[1]) + p.oPr) = u;
+            if (v.edge[1] | (k2 == 1)) {
+                const int i = v.bx + (int)threadIdx.x, j = v.by + 2 * (int)threadIdx.y + 1;
+                tb2s_images(p, v.PrN, i, j, k2, (k2 == 1 && !p.zlo_halo) ? 0 : -1, u, i == 1, i == p.nx - 2, j == 1,
+                            j == p.ny - 2);
+            }
+        }
+    }
+    if (s == 1 && !p.zlo_halo) {  // bc_z!: q[0] is the image of q[1]
+        QC[0] = QN[0];
+        QC[1] = QN[1];
+    }
+    __syncthreads();
+    if (s == v.top_own[0] || s == v.top_own[1]) {  // physical top face, see tb2s_step
+        const double* r0 = sm + SLOT * SLOTSZ;
+        const double* r1 = r0 + TB_X;
+        const int i = v.bx + (int)threadIdx.x;
+        const bool xl = i == 1, xh = i == p.nx - 2;
+        if (s == v.top_own[0]) {
+            const double L2 = bracket<MODE>(p, QN[0], r0[-1], r0[1], r0[-TB_X], QN[1], QC[0], QN[0], DV[0]);
+            double d2, u;
+            pt_update<MODE>(p, L2, D1N[0], QN[0], d2, u);
+            *(double*)(const_cast<char*>(d[0]) + p.oDPt) = d2;
+            const int j = v.by + 2 * (int)threadIdx.y;
+            tb2s_images(p, v.PrN, i, j, s, p.nz - 1, u, xl, xh, j == 1, j == p.ny - 2);
+            if (s == 1 && !p.zlo_halo) tb2s_images(p, v.PrN, i, j, 0, -1, u, xl, xh, j == 1, j == p.ny - 2);
+        }
+        if (s == v.top_own[1]) {
+            const double L2 = bracket<MODE>(p, QN[1], r1[-1], r1[1], QN[0], r1[TB_X], QC[1], QN[1], DV[1]);
+            double d2, u;
+            pt_update<MODE>(p, L2, D1N[1], QN[1], d2, u);
+            *(double*)(const_cast<char*>(d[1]) + p.oDPt) = d2;
+            const int j = v.by + 2 * (int)threadIdx.y + 1;
+            tb2s_images(p, v.PrN, i, j, s, p.nz - 1, u, xl, xh, j == 1, j == p.ny - 2);
+            if (s == 1 && !p.zlo_halo) tb2s_images(p, v.PrN, i, j, 0, -1, u, xl, xh, j == 1, j == p.ny - 2);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        D1C[r] = D1N[r];
+        c[r] += planeB;
+        d[r] += dplaneB;
+    }
+#undef LD
+#undef rowB
+#undef planeB
+#undef dplaneB
+}
+
+template <int MODE, int TB_Y, int PF, int MINB, int NXC, int NYC>
+__global__ void __launch_bounds__(TB_X* TB_Y / 2, MINB) pt_tb2d_kernel(const double* Pr, double* PrN, const double* dP,
+                                                                       double* dPN, const double* divV, const PtK p)
+{
+    __shared__ double ring[3 * TB_Y * TB_X];
+    const int nx = p.nx, ny = p.ny, nz = p.nz;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.x * (TB_X - 2) + tx;
+    const int ci = min(max(i, 1), nx - 2);
+    int bz = blockIdx.z;
+    if (p.reverse) bz = gridDim.z - 1 - bz;
+    const int kb = p.kbeg + bz * p.zchunk;
+    const int ke = min(kb + p.zchunk, p.kend);  // stage-2 planes [kb, ke)
+    const int s0 = max(kb - 1, 1);
+    const int s1 = min(ke, nz - 2);             // stage-1 planes [s0, s1]
+    Tb2dInv v;
+    v.PrN = PrN;
+    v.bx = blockIdx.x * (TB_X - 2);
+    v.by = blockIdx.y * (TB_Y - 2);
+    const char* c[2];
+    const char* d[2];
+    int cj[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int tr = 2 * ty + r;                 // tile row
+        const int j = v.by + tr;
+        cj[r] = min(max(j, 1), ny - 2);
+        const bool owner = (ci == i) && (cj[r] == j) && tx >= 1 && tx <= TB_X - 2 && tr >= 1 && tr <= TB_Y - 2;
+        v.kb_own[r] = owner ? kb : 0x7fffffff;
+        v.top_own[r] = (owner && !p.zhi_halo && ke == nz - 1) ? nz - 2 : -1;
+        v.edge[r] = owner && ((i == 1) | (i == nx - 2) | (j == 1) | (j == ny - 2));
+        NS3D_KEEP(v.kb_own[r]); NS3D_KEEP(v.top_own[r]); NS3D_KEEP(v.edge[r]);
+        c[r] = (const char*)(Pr + (ptrdiff_t)s0 * nx * ny + (ptrdiff_t)cj[r] * nx + ci);
+        d[r] = (const char*)(dP + ((ptrdiff_t)s0 - 1) * (nx - 2) * (ny - 2) + (ptrdiff_t)(cj[r] - 1) * (nx - 2) + (ci - 1));
+    }
+    v.adj = cj[1] == cj[0] + 1;
+    v.xfix = (i == 0 && p.xlo_kind != X_NEUMANN) ? 1 : ((i == nx - 1 && p.xhi_kind != X_NEUMANN) ? 2 : 0);
+    NS3D_KEEP(v.adj); NS3D_KEEP(v.xfix);
+    int tslot = 2 * ty * TB_X + tx;
+    NS3D_KEEP(tslot);
+    double* sm = ring + tslot;
+#define LD(ptr) (*(const double*)(ptr))
+    const long long rowB = Tb2sStride<NXC, NYC>::row(p), planeB = Tb2sStride<NXC, NYC>::plane(p);
+    double A[2], B[2], C[2], DQ[2], VA[2], VB[2], VC[2], QA[2], QB[2], QC[2], D1[2], NX[2][2], NY[2], NM[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        A[r] = LD(c[r] - planeB);  // Pr of planes s0-1, s0, s0+1
+        B[r] = LD(c[r]);
+        C[r] = LD(c[r] + planeB);
+        DQ[r] = LD(d[r]);
+        VA[r] = 0; VB[r] = LD(c[r] + p.oDV); VC[r] = 0;
+        QA[r] = QB[r] = QC[r] = D1[r] = 0;
+        NX[r][0] = LD(c[r] - 8);
+        NX[r][1] = LD(c[r] + 8);
+    }
+    NY[0] = LD(c[0] - rowB);
+    NY[1] = LD(c[1] + rowB);
+    NM[0] = LD(c[0] + rowB);
+    NM[1] = LD(c[1] - rowB);
+#undef LD
+    int s = s0;
+    while (true) {
+        tb2d_step<MODE, TB_Y, 0, PF, NXC, NYC>(p, v, s, c, d, sm, A, B, C, DQ, VA, VB, VC, QA, QB, QC, D1, NX, NY, NM);
+        if (s == s1) break;
+        ++s;
+        tb2d_step<MODE, TB_Y, 1, PF, NXC, NYC>(p, v, s, c, d, sm, B, C, A, DQ, VB, VC, VA, QB, QC, QA, D1, NX, NY, NM);
+        if (s == s1) break;
+        ++s;
+        tb2d_step<MODE, TB_Y, 2, PF, NXC, NYC>(p, v, s, c, d, sm, C, A, B, DQ, VC, VA, VB, QC, QA, QB, D1, NX, NY, NM);
+        if (s == s1) break;
+        ++s;
+    }
+}
+
 // Byte displacements between the arrays of one pt_tb2s_kernel launch: launch constants, so the
 // kernel adds them from the constant bank instead of carrying 64-bit differences in registers.
 inline void tb2s_set_offsets(PtK& k, const double* Pr, const double* PrN, const double* dP, const double* dPN,

@@ -39,7 +39,13 @@ void launch_tb2(int kernel, PtK k, const double* cur, double* nxt, const double*
 {
     balance_chunks(k);
     const dim3 grid(cdivu(k.nx - 2, TB_X - 2), cdivu(k.ny - 2, TY - 2), cdivu(k.kend - k.kbeg, k.zchunk));
-    if (kernel == 2) {
+    if (kernel == 3) {  // two tile rows per thread: 32 x TY tiles of TY/2 thread rows
+        tb2s_set_offsets(k, cur, nxt, dpc, dpn, divV);
+        if (TY == 16 && k.nx == 255 && k.ny == 153)
+            emu::launch(grid, dim3(TB_X, TY / 2, 1), [=]() { pt_tb2d_kernel<MODE, 16, 1, 2, 255, 153>(cur, nxt, dpc, dpn, divV, k); });
+        else
+            emu::launch(grid, dim3(TB_X, TY / 2, 1), [=]() { pt_tb2d_kernel<MODE, TY, 1, 2, 0, 0>(cur, nxt, dpc, dpn, divV, k); });
+    } else if (kernel == 2) {
         tb2s_set_offsets(k, cur, nxt, dpc, dpn, divV);
         // like launch_tb2() in ns3d_pt.cu: grids with a compile-time-stride instantiation use it
         if (TY == 8 && k.nx == 255 && k.ny == 153)
@@ -227,7 +233,8 @@ extern "C" int emu_pt_tb2_split(int kernel_mid, int mode, int ty_mid, const ns3d
     return -1;
 }
 
-// kernel: 0 = pt_iter_kernel, 1 = pt_tb2_kernel (+ pt_iter_kernel for an odd tail), 2 = pt_tb2s_kernel (+ tail).
+// kernel: 0 = pt_iter_kernel, 1 = pt_tb2_kernel (+ pt_iter_kernel for an odd tail), 2 = pt_tb2s_kernel (+ tail),
+// 3 = pt_tb2d_kernel (+ tail).
 // zlo_halo / zhi_halo mark z faces that are slab interfaces (left to the halo exchange).
 extern "C" int emu_pt_iterate(int kernel, int mode, int ty, const ns3d_pt_params* pp, int zlo_halo, int zhi_halo,
                               int serpentine, double* Pr, double* dP, const double* divV, int n_iter, long long* launches)

@@ -54,7 +54,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("kernel", ["pt_tb2s", "pt_tb2", "pt_iter"])
+@pytest.mark.parametrize("kernel", ["pt_tb2s", "pt_tb2d", "pt_tb2", "pt_iter"])
 @pytest.mark.parametrize("variant,grid,zchunk,ty,counts", CASES)
 def test_emulated_kernel_bit_exact_vs_oracle(O, kernel, variant, grid, zchunk, ty, counts):
     if kernel == "pt_iter" and (ty != 16 or grid == (63, 38, 38)):
@@ -80,12 +80,13 @@ def test_slim_kernel_identical_to_first_tb2_kernel_in_fast_modes(O, mode, varian
     _, f = problem(O, variant, grid, 32)
     s = setup_for(variant, grid)
     out = {}
-    for kernel in ("pt_tb2", "pt_tb2s"):
+    for kernel in ("pt_tb2", "pt_tb2s", "pt_tb2d"):
         g = {k: f[k].copy(order="F") for k in ("Pr", "dPrdtau", "divV")}
         emu.pt_iterate(kernel, getattr(ns, mode), s.pt_params(zchunk), g["Pr"], g["dPrdtau"], g["divV"], 6)
         out[kernel] = g
     for name in ("Pr", "dPrdtau"):
         assert np.array_equal(out["pt_tb2"][name], out["pt_tb2s"][name]), name
+        assert np.array_equal(out["pt_tb2"][name], out["pt_tb2d"][name]), name
     assert np.isfinite(out["pt_tb2s"]["Pr"]).all()
 
 
