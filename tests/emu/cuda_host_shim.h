@@ -44,9 +44,9 @@ using std::min;
 
 inline void __syncthreads() { pthread_barrier_wait(&emu::g_barrier); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-inline long long clock64()  // nanoseconds: the kernels' spin limits (8e9 "cycles") become 8 s
+inline long long clock64()  // 10 ns ticks: the kernels' spin limits (8e9 "cycles") become 80 s, generous for a loaded CI box
 {
-    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() / 10;
 }
 template <class T>
 inline T __ldcv(const T* p)
