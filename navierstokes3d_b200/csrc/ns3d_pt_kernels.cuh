@@ -147,6 +147,7 @@ struct StreamRegs {
 #ifdef NS3D_HOST_EMU  // host emulation of the kernels (tests/emu/): the same orderings with GCC atomics
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
 {
+    emu::spin_pause();  // only ever polled in a spin loop: let the other ranks' threads run
     return __atomic_load_n(p, __ATOMIC_ACQUIRE);
 }
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)

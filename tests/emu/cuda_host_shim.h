@@ -6,6 +6,7 @@
 #pragma once
 
 #include <pthread.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <chrono>
@@ -55,6 +56,8 @@ inline T __ldcv(const T* p)
 }
 
 namespace emu {
+
+inline void spin_pause() { sched_yield(); }
 
 struct ThreadArg {
     void (*fn)(void*);
