@@ -210,7 +210,12 @@ int launch_tb2(ns3d_ctx* ctx, cudaStream_t st, const PtK& k_in, const double* cu
     do {                                                                                                          \
         const int pf = ctx->opt_tb2_pf, np = ctx->opt_tb2_np;                                                     \
         const bool spec = ctx->opt_tb2_spec && np && pf == 1;                                                     \
-        if (spec && TY == 8 && k.nx == 255 && k.ny == 153) pt_tb2s_kernel<MODE, 8, 1, true, 255, 153> TBS_ARGS;  \
+        const bool pb = ctx->opt_tb2_pb && np && pf == 1 && TY != 32;  /* round-2 candidate, off by default */    \
+        if (pb && spec && TY == 8 && k.nx == 255 && k.ny == 153) pt_tb2s_kernel<MODE, 8, 1, true, 255, 153, true> TBS_ARGS; \
+        else if (pb && spec && TY == 16 && k.nx == 511 && k.ny == 511) pt_tb2s_kernel<MODE, 16, 1, true, 511, 511, true> TBS_ARGS; \
+        else if (pb && TY == 8) pt_tb2s_kernel<MODE, 8, 1, true, 0, 0, true> TBS_ARGS;                            \
+        else if (pb) pt_tb2s_kernel<MODE, 16, 1, true, 0, 0, true> TBS_ARGS;                                      \
+        else if (spec && TY == 8 && k.nx == 255 && k.ny == 153) pt_tb2s_kernel<MODE, 8, 1, true, 255, 153> TBS_ARGS; \
         else if (spec && TY == 16 && k.nx == 511 && k.ny == 511) pt_tb2s_kernel<MODE, 16, 1, true, 511, 511> TBS_ARGS; \
         else if (spec && TY == 16 && k.nx == 1023 && k.ny == 511) pt_tb2s_kernel<MODE, 16, 1, true, 1023, 511> TBS_ARGS; \
         else if (np && pf == 2) pt_tb2s_kernel<MODE, TY, 2, true, 0, 0> TBS_ARGS;                                \
@@ -493,7 +498,7 @@ int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double*& d
     key.reverse = 0;
     // every tuning option that selects a kernel or its launch shape is part of the key
     const int opts = ctx->opt_tb2 | (ctx->opt_tb2_slim << 1) | (ctx->opt_tb2_np << 2) | (ctx->opt_tb2_pf << 3) |
-                     (ctx->opt_tb2_spec << 5) | (ctx->opt_tb2_dual << 6) | (ctx->opt_tb2_ty << 8);
+                     (ctx->opt_tb2_spec << 5) | (ctx->opt_tb2_dual << 6) | (ctx->opt_tb2_ty << 8) | (ctx->opt_tb2_pb << 16);
     PtGraph* g = nullptr;
     for (PtGraph& c : cache->slot)
         if (c.exec && c.cur == cur && c.nxt == nxt && c.dP == dP && c.dPn == dPn && c.divV == divV && c.n == n &&

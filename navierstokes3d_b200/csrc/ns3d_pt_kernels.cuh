@@ -580,6 +580,27 @@ struct Tb2sInv {
 // pressure of planes s-2, s-1, D1C = first-iteration dPrdτ of plane s-1.  On exit PM holds Pr of
 // plane s+2 and DVN ∇V of plane s+1, QN the first-iteration pressure of plane s, so the caller
 // continues with the roles rotated: (PC,ZP,PM), (DV,DVN,DVC), (QC,QN,QM).
+// Synchronisation of one tile row (= one warp, TB_X = 32) with the rows above and below it instead
+// of the whole CTA: a row of the ring is read only by the warps of the adjacent rows, so warp w
+// meets warp w-1 on named barrier w and warp w+1 on named barrier w+1 (64 threads each; ids 1..15,
+// 0 stays __syncthreads).  Lower pair first on every warp: no cycle.  RAW: a neighbour's slot is
+// read after the pair barrier of the step it was written in; WAR: a warp overwrites a slot two
+// pair barriers after its neighbours read it.
+__device__ __forceinline__ void pair_barrier(int id)
+{
+#ifdef NS3D_HOST_EMU
+    emu::named_barrier(id, 64);
+#else
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+#endif
+}
+template <int TB_Y>
+__device__ __forceinline__ void row_barrier(int ty)
+{
+    if (ty > 0) pair_barrier(ty);
+    if (ty < TB_Y - 1) pair_barrier(ty + 1);
+}
+
 // DRAM -> L2 prefetch of one line (no destination register; a no-op on the host emulation).
 __device__ __forceinline__ void prefetch_l2(const void* ptr)
 {
@@ -610,7 +631,8 @@ struct Tb2sStride {
     }
 };
 
-template <int MODE, int TB_Y, int SLOT, int PF, bool NP, int NXC, int NYC>
+// PB: pairwise row barriers (row_barrier) instead of __syncthreads -- ROUND-2 CANDIDATE, unmeasured.
+template <int MODE, int TB_Y, int SLOT, int PF, bool NP, int NXC, int NYC, bool PB>
 __device__ __forceinline__ void tb2s_step(const PtK& p, const Tb2sInv& v, const int s, const char*& c, const char*& d,
                                           double* __restrict__ sm, double& PM, double& PC, double& ZP, double& DQ,
                                           double& DVC, double& DV, double& DVN, double& QM, double& QC, double& QN,
@@ -671,7 +693,9 @@ __device__ __forceinline__ void tb2s_step(const PtK& p, const Tb2sInv& v, const 
         }
     }
     if (s == 1 && !p.zlo_halo) QC = QN;  // bc_z!: q[0] is the image of q[1] (QC becomes QM of the next plane)
-    __syncthreads();                     // slot SLOT is complete; slot SLOT+1 may be overwritten by the next step
+    // slot SLOT is complete; slot SLOT+1 may be overwritten by the next step
+    if (PB) row_barrier<TB_Y>((int)threadIdx.y);
+    else __syncthreads();
     if (s == v.top_own) {
         // physical top face: plane nz-2 needs q[nz-1], the image of q[nz-2]; its second iteration
         // follows here because there is no further stage-1 plane to trigger it
@@ -696,7 +720,7 @@ __device__ __forceinline__ void tb2s_step(const PtK& p, const Tb2sInv& v, const 
 #undef a_zp2
 }
 
-template <int MODE, int TB_Y, int PF, bool NP, int NXC, int NYC>
+template <int MODE, int TB_Y, int PF, bool NP, int NXC, int NYC, bool PB = false>
 __global__ void __launch_bounds__(TB_X* TB_Y, 1024 / (TB_X * TB_Y)) pt_tb2s_kernel(const double* Pr, double* PrN, const double* dP, double* dPN,
                                                                const double* divV, const PtK p)
 {
@@ -742,13 +766,13 @@ __global__ void __launch_bounds__(TB_X* TB_Y, 1024 / (TB_X * TB_Y)) pt_tb2s_kern
 #undef LD
     int s = s0;
     while (true) {
-        tb2s_step<MODE, TB_Y, 0, PF, NP, NXC, NYC>(p, v, s, c, d, sm, A, B, C, DQ, VA, VB, VC, QA, QB, QC, D1, NB);
+        tb2s_step<MODE, TB_Y, 0, PF, NP, NXC, NYC, PB>(p, v, s, c, d, sm, A, B, C, DQ, VA, VB, VC, QA, QB, QC, D1, NB);
         if (s == s1) break;
         ++s;
-        tb2s_step<MODE, TB_Y, 1, PF, NP, NXC, NYC>(p, v, s, c, d, sm, B, C, A, DQ, VB, VC, VA, QB, QC, QA, D1, NB);
+        tb2s_step<MODE, TB_Y, 1, PF, NP, NXC, NYC, PB>(p, v, s, c, d, sm, B, C, A, DQ, VB, VC, VA, QB, QC, QA, D1, NB);
         if (s == s1) break;
         ++s;
-        tb2s_step<MODE, TB_Y, 2, PF, NP, NXC, NYC>(p, v, s, c, d, sm, C, A, B, DQ, VC, VA, VB, QC, QA, QB, D1, NB);
+        tb2s_step<MODE, TB_Y, 2, PF, NP, NXC, NYC, PB>(p, v, s, c, d, sm, C, A, B, DQ, VC, VA, VB, QC, QA, QB, D1, NB);
         if (s == s1) break;
         ++s;
     }

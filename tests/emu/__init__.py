@@ -23,7 +23,7 @@ DEPS = [os.path.join(HERE, "pt_emu.cpp"), os.path.join(HERE, "cuda_host_shim.h")
         os.path.join(ROOT, "include", "ns3d.h")]
 _lib = None
 
-KERNELS = {"pt_iter": 0, "pt_tb2": 1, "pt_tb2s": 2, "pt_tb2d": 3}
+KERNELS = {"pt_iter": 0, "pt_tb2": 1, "pt_tb2s": 2, "pt_tb2d": 3, "pt_tb2s_pb": 4}
 
 
 def build(force: bool = False) -> str:

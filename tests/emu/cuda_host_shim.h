@@ -34,6 +34,9 @@ namespace emu {
 inline thread_local dim3 tls_threadIdx;
 inline dim3 g_blockIdx, g_blockDim, g_gridDim;
 inline pthread_barrier_t g_barrier;
+inline pthread_barrier_t g_named[16];      // bar.sync id, count: initialised on first use within a block
+inline int g_named_count[16];
+inline pthread_mutex_t g_named_lock = PTHREAD_MUTEX_INITIALIZER;
 }  // namespace emu
 #define threadIdx (emu::tls_threadIdx)
 #define blockIdx (emu::g_blockIdx)
@@ -58,6 +61,18 @@ inline T __ldcv(const T* p)
 namespace emu {
 
 inline void spin_pause() { sched_yield(); }
+
+// `bar.sync id, count` (PTX named barrier): every participating thread passes the same count.
+inline void named_barrier(int id, int count)
+{
+    pthread_mutex_lock(&g_named_lock);
+    if (g_named_count[id] == 0) {
+        pthread_barrier_init(&g_named[id], nullptr, (unsigned)count);
+        g_named_count[id] = count;
+    }
+    pthread_mutex_unlock(&g_named_lock);
+    pthread_barrier_wait(&g_named[id]);
+}
 
 struct ThreadArg {
     void (*fn)(void*);
@@ -103,6 +118,11 @@ void launch(dim3 grid, dim3 block, F body)
                         }
                 for (unsigned q = 0; q < nthreads; ++q) pthread_join(th[q], nullptr);
                 pthread_barrier_destroy(&g_barrier);
+                for (int id = 0; id < 16; ++id)
+                    if (g_named_count[id]) {
+                        pthread_barrier_destroy(&g_named[id]);
+                        g_named_count[id] = 0;
+                    }
             }
     pthread_attr_destroy(&attr);
 }

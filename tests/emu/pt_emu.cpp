@@ -45,6 +45,14 @@ void launch_tb2(int kernel, PtK k, const double* cur, double* nxt, const double*
             emu::launch(grid, dim3(TB_X, TY / 2, 1), [=]() { pt_tb2d_kernel<MODE, 16, 1, 2, 255, 153>(cur, nxt, dpc, dpn, divV, k); });
         else
             emu::launch(grid, dim3(TB_X, TY / 2, 1), [=]() { pt_tb2d_kernel<MODE, TY, 1, 2, 0, 0>(cur, nxt, dpc, dpn, divV, k); });
+    } else if (kernel == 4) {  // pt_tb2s_kernel with pairwise row barriers
+        tb2s_set_offsets(k, cur, nxt, dpc, dpn, divV);
+        if (TY == 8 && k.nx == 255 && k.ny == 153)
+            emu::launch(grid, dim3(TB_X, TY, 1), [=]() { pt_tb2s_kernel<MODE, 8, 1, true, 255, 153, true>(cur, nxt, dpc, dpn, divV, k); });
+        else if (TY == 8)
+            emu::launch(grid, dim3(TB_X, TY, 1), [=]() { pt_tb2s_kernel<MODE, 8, 1, true, 0, 0, true>(cur, nxt, dpc, dpn, divV, k); });
+        else
+            emu::launch(grid, dim3(TB_X, 16, 1), [=]() { pt_tb2s_kernel<MODE, 16, 1, true, 0, 0, true>(cur, nxt, dpc, dpn, divV, k); });
     } else if (kernel == 2) {
         tb2s_set_offsets(k, cur, nxt, dpc, dpn, divV);
         // like launch_tb2() in ns3d_pt.cu: grids with a compile-time-stride instantiation use it
@@ -234,7 +242,7 @@ extern "C" int emu_pt_tb2_split(int kernel_mid, int mode, int ty_mid, const ns3d
 }
 
 // kernel: 0 = pt_iter_kernel, 1 = pt_tb2_kernel (+ pt_iter_kernel for an odd tail), 2 = pt_tb2s_kernel (+ tail),
-// 3 = pt_tb2d_kernel (+ tail).
+// 3 = pt_tb2d_kernel (+ tail), 4 = pt_tb2s_kernel with pairwise row barriers (tile heights 8 and 16).
 // zlo_halo / zhi_halo mark z faces that are slab interfaces (left to the halo exchange).
 extern "C" int emu_pt_iterate(int kernel, int mode, int ty, const ns3d_pt_params* pp, int zlo_halo, int zhi_halo,
                               int serpentine, double* Pr, double* dP, const double* divV, int n_iter, long long* launches)
