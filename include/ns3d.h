@@ -78,10 +78,11 @@ NS3D_API int ns3d_get_mode(const ns3d_ctx* ctx);
  *   "tb2"         1* two PT iterations per launch, 0 = one-iteration kernel only
  *   "tb2_ty"      tile height of the two-iteration kernels: 0* = by grid size, 8, 16, 32
  *   "tb2_slim"    1* pt_tb2s_kernel for launches off the slab interfaces, 0 = pt_tb2_kernel everywhere
- *   "tb2_np"      1* in-plane neighbours of the next plane loaded one step ahead
+ *   "tb2_np"      1* in-plane neighbours of the next plane loaded one step ahead; 0 = no prefetch beyond the
+ *                 three streams (the baseline the prefetches were measured against; ignores tb2_pf)
  *   "tb2_pf"      planes of software prefetch into L2 ahead of the register prefetch: 0, 1*, 2
  *   "tb2_spec"    1* compile-time-stride instantiation when the grid's x-y extent has one
- *   "tb2_dual"    0* | 2 | 3: pt_tb2d_kernel, two tile rows per thread (value = CTAs per SM)   [candidate]
+ *   "tb2_dual"    0* | 2: pt_tb2d_kernel, two tile rows per thread (value = CTAs per SM)       [candidate]
  *   "tb2_pairbar" 0* | 1: pairwise row barriers instead of __syncthreads in pt_tb2s_kernel     [candidate]
  *   "pt_minb"     CTAs per SM the one-iteration kernel is compiled for: 0* = per mode, 3..6
  *   "serpentine"  -1* = by working-set size, 0, 1: alternate the z sweep direction between launches

@@ -44,17 +44,37 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-Xptxas", "-v" if verbose else "-warn-spills",
-           *[os.path.join(CSRC, s) for s in SOURCES], "-o", LIB, "-ldl"]
-    if os.path.exists(LIB):
-        os.remove(LIB)  # never leave a stale library behind a failed build
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = _nvcc()
     env = dict(os.environ)
     env.pop("CC", None)  # the image exports a gcc wrapper that nvcc must not pick up
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
+    if os.path.exists(LIB):
+        os.remove(LIB)  # never leave a stale library behind a failed build
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src: str):
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc, *compile_flags, "-Xptxas", "-v" if verbose else "-warn-spills", "-c", os.path.join(CSRC, src), "-o", obj]
+        return obj, subprocess.run(cmd, capture_output=True, text=True, env=env)
+
+    # one nvcc per translation unit, in parallel (ns3d_pt.cu with its kernel instantiations dominates)
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    failed = False
+    for _, res in results:
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+        failed |= res.returncode != 0
+    if failed:
         raise RuntimeError("nvcc failed building libns3d.so (see stderr)")
+    link = subprocess.run([nvcc, "-shared", "-Xcompiler", "-fPIC", *[o for o, _ in results], "-o", LIB, "-ldl"],
+                          capture_output=True, text=True, env=env)
+    for obj, _ in results:
+        if os.path.exists(obj):
+            os.remove(obj)
+    if link.returncode != 0:
+        sys.stderr.write(link.stdout + link.stderr)
+        raise RuntimeError("nvcc failed linking libns3d.so (see stderr)")
     return LIB
 
 

@@ -198,7 +198,7 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
         return NS3D_OK;
     }
     if (!strcmp(name, "tb2_dual")) {
-        if (value != 0 && value != 2 && value != 3) return ns3d_fail(ctx, NS3D_EINVAL, "tb2_dual must be 0, 2 or 3");
+        if (value != 0 && value != 2) return ns3d_fail(ctx, NS3D_EINVAL, "tb2_dual must be 0 or 2 (CTAs per SM)");
         ctx->opt_tb2_dual = value;
         return NS3D_OK;
     }

@@ -53,7 +53,7 @@ struct ns3d_ctx {
     int opt_tb2_np = 1;       // pt_tb2s_kernel: in-plane neighbours of the next plane loaded one step ahead
     int opt_tb2_spec = 1;     // pt_tb2s_kernel: use the compile-time-stride instantiation when the grid has one
     int opt_tb2_pb = 0;       // pt_tb2s_kernel: pairwise row barriers instead of __syncthreads (candidate)
-    int opt_tb2_dual = 0;     // pt_tb2d_kernel (two tile rows per thread) for plain launches: 0 off, 2 / 3 = CTAs per SM
+    int opt_tb2_dual = 0;     // pt_tb2d_kernel (two tile rows per thread) for plain launches: 0 off, 2 = CTAs per SM
     int opt_tb2_slim = 1;     // plain two-iteration launches use pt_tb2s_kernel (0 = pt_tb2_kernel)
     int opt_graphs = 1;       // replay chunks of PT iterations as CUDA graphs
     long long halo_calls = 0; // uncaptured halo exchanges so far (NCCL peers connected)

@@ -221,9 +221,7 @@ int launch_tb2(ns3d_ctx* ctx, cudaStream_t st, const PtK& k_in, const double* cu
         else if (np && pf == 2) pt_tb2s_kernel<MODE, TY, 2, true, 0, 0> TBS_ARGS;                                \
         else if (np && pf == 1) pt_tb2s_kernel<MODE, TY, 1, true, 0, 0> TBS_ARGS;                                \
         else if (np) pt_tb2s_kernel<MODE, TY, 0, true, 0, 0> TBS_ARGS;                                           \
-        else if (pf == 2) pt_tb2s_kernel<MODE, TY, 2, false, 0, 0> TBS_ARGS;                                     \
-        else if (pf == 1) pt_tb2s_kernel<MODE, TY, 1, false, 0, 0> TBS_ARGS;                                     \
-        else pt_tb2s_kernel<MODE, TY, 0, false, 0, 0> TBS_ARGS;                                                  \
+        else pt_tb2s_kernel<MODE, TY, 0, false, 0, 0> TBS_ARGS; /* tb2_np=0: no prefetch at all (the baseline) */ \
     } while (0)
 #define TBD_LAUNCH(MODE, MINB)                                                                                 \
     do {                                                                                                       \
@@ -234,7 +232,6 @@ int launch_tb2(ns3d_ctx* ctx, cudaStream_t st, const PtK& k_in, const double* cu
 #define TB_LAUNCH(MODE)                                                                                        \
     do {                                                                                                       \
         if (k.mbox) pt_tb2_kernel<MODE, 16, true><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);          \
-        else if (dual == 3) TBD_LAUNCH(MODE, 3);                                                               \
         else if (dual) TBD_LAUNCH(MODE, 2);                                                                    \
         else if (slim && ty == 8) TBS_LAUNCH(MODE, 8);                                                         \
         else if (slim && ty == 32) TBS_LAUNCH(MODE, 32);                                                       \
