@@ -65,14 +65,14 @@ def test_fused_iteration_bit_exact(O, ns, ctx, variant, grid, zchunk):
             assert (got == f[name]).all(), f"{name} differs after {done} iterations ({(got != f[name]).sum()} values)"
 
 
-@pytest.mark.parametrize("variant", ["M", "G"])
-@pytest.mark.parametrize("grid", [(3, 3, 3), (5, 4, 3), (4, 3, 6), (37, 23, 19), (63, 38, 38), (70, 47, 41)])
-@pytest.mark.parametrize("zchunk", [0, 1, 2, 7])
 CANDIDATES = pytest.mark.skipif(not os.environ.get("NS3D_TEST_CANDIDATES"),
                                 reason="round-2 candidate kernels (emulation-verified, not yet run on a device): "
                                        "set NS3D_TEST_CANDIDATES=1")
 
 
+@pytest.mark.parametrize("variant", ["M", "G"])
+@pytest.mark.parametrize("grid", [(3, 3, 3), (5, 4, 3), (4, 3, 6), (37, 23, 19), (63, 38, 38), (70, 47, 41)])
+@pytest.mark.parametrize("zchunk", [0, 1, 2, 7])
 @pytest.mark.parametrize("kern", ["tb2s_auto", "tb2s_16_nopf", "tb2s_8_pf2", "tb2_first",
                                   pytest.param("tb2d", marks=CANDIDATES), pytest.param("tb2s_pairbar", marks=CANDIDATES)])
 def test_two_iterations_per_launch_bit_exact(O, ns, ctx, variant, grid, zchunk, kern):
