@@ -431,6 +431,10 @@ def main():
                          "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "us_per_launch": t_launch * 1e6,
+                         # what actually crossed the DRAM interface (ncu) over the same launch time: the
+                         # kernel keeps Pr^(1) and dPrdtau^(1) on chip, so this is well below `achieved`
+                         "dram_achieved": (traffic / t_launch / 1e9) if traffic else None,
+                         "dram_frac": (traffic / t_launch / 1e9 / peak) if traffic else None,
                          "algorithmic_bytes_per_launch": 40.0 * per_launch * n_cells,
                          "share_of_step": (sum(iters) / args.steps) * (t_launch / per_launch) / (t_all / args.steps)},
         }
