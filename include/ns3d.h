@@ -234,8 +234,19 @@ typedef struct ns3d_step_params {
     int reserved;
 } ns3d_step_params;
 
+/* The three once-per-step groups around the PT loop, each the level-1 sequence of its lines:
+ *   predictor   M:449-455 / G:121-124  update_τ!, predict_V!, set_cylinder!, update_halo!(C,V),
+ *                                      update_∇V!, update_halo!(∇V)
+ *   corrector   M:472-474 / G:138-140  correct_V!, set_cylinder!, set_bc_Vel! (halo inside)
+ *   advect_swap M:475-477 / G:141-142  `A_o .= A` x4, advect!, update_halo!(Vx,Vy,Vz)
+ * Asynchronous on the context's stream.                                                  */
+NS3D_API int ns3d_predictor(ns3d_ctx* ctx, const ns3d_fields* f, const ns3d_step_params* p);
+NS3D_API int ns3d_corrector(ns3d_ctx* ctx, const ns3d_fields* f, const ns3d_step_params* p);
+NS3D_API int ns3d_advect_swap(ns3d_ctx* ctx, const ns3d_fields* f, const ns3d_step_params* p);
+
 /* One whole time step M:449-477 / G:121-142 (everything between the `for it` line
- * and the visualisation block).  Same iterates as the level-1 sequence.         */
+ * and the visualisation block) = predictor, ns3d_pt_solve, corrector, advect_swap.
+ * Same iterates as the level-1 sequence.                                         */
 NS3D_API int ns3d_step(ns3d_ctx* ctx, const ns3d_fields* f, const ns3d_step_params* p, int* h_iters,
               double* h_err_hist, int err_cap, int* h_nchecks);
 

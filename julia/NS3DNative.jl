@@ -14,7 +14,8 @@ export Ctx, DevArray, zeros3, to_host, set!, set_mode!, PARITY, FAST, FASTEST,
        update_τ!, predict_V!, update_∇V!, update_dPrdτ!, update_Pr!, compute_res!, max_g_abs, correct_V!,
        bc_x!, bc_y!, bc_z!, bc_x_Vx!, bc_x_Pr!, bc_zV!, bc_xhydstatic!, set_bc_Vel_M!, set_bc_Vel_G!,
        set_bc_Pr_M!, set_bc_Pr_G!, advect!, set_cylinder_M!, set_cylinder_G!, update_halo!, copy!,
-       comm_init_mpi!, PtParams, pt_solve!, inner, inner32, plane_xy, plane_xz
+       comm_init_mpi!, PtParams, pt_solve!, inner, inner32, plane_xy, plane_xz,
+       Fields, StepParams, predictor!, corrector!, advect_swap!, step!
 
 const LIB = get(ENV, "NS3D_LIB", joinpath(@__DIR__, "..", "navierstokes3d_b200", "csrc", "libns3d.so"))
 const PARITY, FAST, FASTEST = Cint(0), Cint(1), Cint(2)
@@ -177,6 +178,32 @@ function pt_solve!(c::Ctx, Pr, dPrdτ, ∇V, p::PtParams)
     hist = zeros(Cdouble, cap); it = Ref{Cint}(0); nc = Ref{Cint}(0)
     check(c, ccall((:ns3d_pt_solve, LIB), Cint, (Ptr{Cvoid}, P, P, P, Ref{PtParams}, Ref{Cint}, Ptr{Cdouble}, Cint, Ref{Cint}),
                    c.h, Pr.p, dPrdτ.p, ∇V.p, p, it, hist, cap, nc))
+    return Int(it[]), hist[1:nc[]]
+end
+
+# ---- level 2: the once-per-step groups and the whole step (M:449-477 / G:121-142) ------------------
+struct Fields            # ns3d_fields: the 18 arrays in the script's allocation order (M:343-360)
+    Pr::P; dPrdtau::P; C::P; C_o::P; txx::P; tyy::P; tzz::P; txy::P; txz::P; tyz::P
+    Vx::P; Vy::P; Vz::P; Vx_o::P; Vy_o::P; Vz_o::P; divV::P; Rp::P
+end
+Fields(a::DevArray...) = Fields((x.p for x in a)...)
+struct StepParams        # ns3d_step_params, field for field
+    pt::PtParams
+    mu::Cdouble; vin::Cdouble
+    a2::Cdouble; b2::Cdouble; ox::Cdouble; oy::Cdouble; sinb::Cdouble; cosb::Cdouble
+    xco_g::Cdouble; yco_g::Cdouble; lx::Cdouble; ly::Cdouble
+    inlet_guard::Cint; reserved::Cint
+end
+for (jl, sym) in ((:predictor!, :ns3d_predictor), (:corrector!, :ns3d_corrector), (:advect_swap!, :ns3d_advect_swap))
+    @eval $jl(c::Ctx, f::Fields, sp::StepParams) =
+        check(c, ccall(($(QuoteNode(sym)), LIB), Cint, (Ptr{Cvoid}, Ref{Fields}, Ref{StepParams}), c.h, f, sp))
+end
+"One time step = predictor!, pt_solve!, corrector!, advect_swap!; returns (iterations, err history)."
+function step!(c::Ctx, f::Fields, sp::StepParams)
+    cap = sp.pt.niter ÷ max(sp.pt.nchk, 1) + 2
+    hist = zeros(Cdouble, cap); it = Ref{Cint}(0); nc = Ref{Cint}(0)
+    check(c, ccall((:ns3d_step, LIB), Cint, (Ptr{Cvoid}, Ref{Fields}, Ref{StepParams}, Ref{Cint}, Ptr{Cdouble}, Cint, Ref{Cint}),
+                   c.h, f, sp, it, hist, cap, nc))
     return Int(it[]), hist[1:nc[]]
 end
 

@@ -114,6 +114,19 @@ class Simulation:
         self.err_hist.append(hist)
         return it, hist
 
+    def step_groups(self):
+        """The same time step through the four level-2 groups: ``ns3d_predictor``, ``ns3d_pt_solve``,
+        ``ns3d_corrector``, ``ns3d_advect_swap`` -- what ``ns3d_step`` composes, for a driver that
+        wants to act between them (the script's ``println`` of the residuals sits there, M:468)."""
+        sp = self.s.step_params(self.zchunk)
+        self.ctx.predictor(self._fields_struct, sp)
+        it, hist = self.ctx.pt_solve(self.f["Pr"], self.f["dPrdtau"], self.f["divV"], sp.pt)
+        self.ctx.corrector(self._fields_struct, sp)
+        self.ctx.advect_swap(self._fields_struct, sp)
+        self.iters.append(it)
+        self.err_hist.append(hist)
+        return it, hist
+
     def step_level1(self):
         """The same time step, call site by call site (M:449-477 / G:121-142) through level 1."""
         s, f, c = self.s, self.f, self.ctx

@@ -110,6 +110,9 @@ SIGNATURES = {
     "ns3d_pt_solve": (_I, [_P, _P, _P, _P, C.POINTER(PtParams), c_int_p, c_double_p, _I, c_int_p]),
     "ns3d_pt_iterate": (_I, [_P, _P, _P, _P, C.POINTER(PtParams), _I]),
     "ns3d_step": (_I, [_P, C.POINTER(Fields), C.POINTER(StepParams), c_int_p, c_double_p, _I, c_int_p]),
+    "ns3d_predictor": (_I, [_P, C.POINTER(Fields), C.POINTER(StepParams)]),
+    "ns3d_corrector": (_I, [_P, C.POINTER(Fields), C.POINTER(StepParams)]),
+    "ns3d_advect_swap": (_I, [_P, C.POINTER(Fields), C.POINTER(StepParams)]),
 }
 
 _lib = None
@@ -323,6 +326,18 @@ class Context:
     def pt_iterate(self, Pr, dPrdtau, divV, p: PtParams, n: int):
         self._ck(self.lib.ns3d_pt_iterate(self.h, _ptr(Pr), _ptr(dPrdtau), _ptr(divV), C.byref(p), n),
                  "ns3d_pt_iterate")
+
+    def predictor(self, fields: Fields, sp: StepParams):
+        """M:449-455: update_τ!, predict_V!, set_cylinder!, update_∇V! + halo updates."""
+        self._ck(self.lib.ns3d_predictor(self.h, C.byref(fields), C.byref(sp)), "ns3d_predictor")
+
+    def corrector(self, fields: Fields, sp: StepParams):
+        """M:472-474: correct_V!, set_cylinder!, set_bc_Vel!."""
+        self._ck(self.lib.ns3d_corrector(self.h, C.byref(fields), C.byref(sp)), "ns3d_corrector")
+
+    def advect_swap(self, fields: Fields, sp: StepParams):
+        """M:475-477: the four snapshots, advect!, update_halo!(Vx,Vy,Vz)."""
+        self._ck(self.lib.ns3d_advect_swap(self.h, C.byref(fields), C.byref(sp)), "ns3d_advect_swap")
 
     def step(self, fields: Fields, sp: StepParams):
         """One time step (M:449-477) -> (iterations, [err at each check])."""

@@ -67,3 +67,18 @@ def test_runme_do_save_writes_the_mat_file(ns, tmp_path, monkeypatch):
     assert np.array_equal(m["Vy_true"], sim.host("Vy")) and np.array_equal(m["C"], sim.host("C"))
     assert m["dx"].item() == sim.s.dx and m["dz"].item() == sim.s.dz
     sim.ctx.close()
+
+
+@pytest.mark.parametrize("variant", ["M", "G"])
+def test_step_groups_equal_the_fused_step(O, ns, variant):
+    """ns3d_predictor + ns3d_pt_solve + ns3d_corrector + ns3d_advect_swap == ns3d_step == the oracle."""
+    nx, nt = 40, 3
+    p = O.params_M(nx) if variant == "M" else O.params_G(nx)
+    f, iters_o, errs_o = O.run(p, nt)
+    sim = ns.Simulation(ns.setup_multi_gpu(nx) if variant == "M" else ns.setup_gpu(nx), ns.Context(0, ns.PARITY))
+    for _ in range(nt):
+        sim.step_groups()
+    assert sim.iters == iters_o and sim.err_hist == errs_o
+    for name in ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C", "divV"):
+        assert np.array_equal(sim.host(name), f[name]), name
+    sim.ctx.close()
