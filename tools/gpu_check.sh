@@ -1,5 +1,6 @@
 #!/bin/bash
-# Round-1 final GPU call: bench line, launch list, ncu captures of the default kernels, then the GPU test suite.
+# One GPU call that produces what a round needs: the bench line, the launch list, ncu captures of the default
+# kernel, then the GPU test suite (BUDGET = seconds of run time the call may use; the tail is optional).
 mkdir -p gpurun_out
 BUDGET=${BUDGET:-175}
 timeout 150 python bench.py > gpurun_out/g_bench_n1.json 2> gpurun_out/g_bench_n1.err
