@@ -145,6 +145,12 @@ extern "C" int ns3d_destroy(ns3d_ctx* ctx)
     if (ctx->dp_shadow) cudaFree(ctx->dp_shadow);
     cudaFree(ctx->d_maxbits);
     cudaFreeHost(ctx->h_maxbits);
+    for (int b = 0; b < ns3d_ctx::MAX_BANDS; ++b) {
+        if (ctx->band_stream[b]) cudaStreamDestroy(ctx->band_stream[b]);
+        for (int q = 0; q < 2; ++q)
+            if (ctx->band_ev[q][b]) cudaEventDestroy(ctx->band_ev[q][b]);
+    }
+    if (ctx->band_fork) cudaEventDestroy(ctx->band_fork);
     cudaEventDestroy(ctx->ev_a);
     cudaEventDestroy(ctx->ev_b);
     cudaStreamDestroy(ctx->stream);
@@ -191,6 +197,12 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
     }
     if (!strcmp(name, "tb2_np")) {
         ctx->opt_tb2_np = value != 0;
+        return NS3D_OK;
+    }
+    if (!strcmp(name, "pt_bands")) {
+        if (value != 0 && (value < 2 || value > ns3d_ctx::MAX_BANDS))
+            return ns3d_fail(ctx, NS3D_EINVAL, "pt_bands must be 0 or 2..%d", ns3d_ctx::MAX_BANDS);
+        ctx->opt_pt_bands = value;
         return NS3D_OK;
     }
     if (!strcmp(name, "tb2_pairbar")) {

@@ -21,6 +21,13 @@ struct ns3d_ctx {
     cudaStream_t stream = nullptr;       // all operators run here
     cudaStream_t comm_stream = nullptr;  // halo exchange, overlapped with interior compute
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    // z-band pipelining of the two-iteration launches (option "pt_bands", candidate): one stream per
+    // band, events [launch parity][band], created on first use
+    static const int MAX_BANDS = 8;
+    cudaStream_t band_stream[MAX_BANDS] = {};
+    cudaEvent_t band_ev[2][MAX_BANDS] = {};
+    cudaEvent_t band_fork = nullptr;
+    int bands_ready = 0;
     long long launches = 0;
     std::string err;
     std::unordered_map<void*, size_t> allocs;
@@ -52,6 +59,8 @@ struct ns3d_ctx {
     int opt_tb2_pf = 1;       // pt_tb2s_kernel: planes of software prefetch into L2 ahead of the register prefetch (0..2)
     int opt_tb2_np = 1;       // pt_tb2s_kernel: in-plane neighbours of the next plane loaded one step ahead
     int opt_tb2_spec = 1;     // pt_tb2s_kernel: use the compile-time-stride instantiation when the grid has one
+    int opt_pt_bands = 0;     // >= 2: split every two-iteration launch into that many z-bands with band-to-band
+                              // dependencies, so that launch n+1 starts while launch n drains (candidate, single rank)
     int opt_tb2_pb = 0;       // pt_tb2s_kernel: pairwise row barriers instead of __syncthreads (candidate)
     int opt_tb2_dual = 0;     // pt_tb2d_kernel (two tile rows per thread) for plain launches: 0 off, 2 = CTAs per SM
     int opt_tb2_slim = 1;     // plain two-iteration launches use pt_tb2s_kernel (0 = pt_tb2_kernel)

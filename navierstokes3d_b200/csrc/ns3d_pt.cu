@@ -435,12 +435,80 @@ struct PtGraphCache {
     int next = 0;
 };
 
+// ---- z-band pipelining (option "pt_bands" = NB >= 2, single rank; CANDIDATE, not yet run on a device) ----
+// One launch per two iterations leaves the SMs idle while its last CTAs drain and the next launch
+// ramps up (ncu: ~10 % of a launch at 255x153x153).  Here every launch is split into NB z-bands on
+// NB streams, and band b of launch n+1 depends only on bands b-1, b, b+1 of launch n -- the planes
+// it reads reach two planes into the adjacent bands, and those same launches are the last readers
+// of what it overwrites (the WAR dependency is the RAW dependency one launch later).  Band kernels
+// of consecutive launches then overlap like a wavefront; inside a captured chunk the dependencies
+// become graph edges.  Plane ranges compose exactly (tests/test_kernel_emu.py, split launches).
+int bands_prepare(ns3d_ctx* ctx, int nb)
+{
+    if (ctx->bands_ready >= nb) return NS3D_OK;
+    if (!ctx->band_fork) NS3D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->band_fork, cudaEventDisableTiming));
+    for (int b = ctx->bands_ready; b < nb; ++b) {
+        NS3D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->band_stream[b], cudaStreamNonBlocking));
+        for (int q = 0; q < 2; ++q) NS3D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->band_ev[q][b], cudaEventDisableTiming));
+    }
+    ctx->bands_ready = nb;
+    return NS3D_OK;
+}
+
+// n2 double launches (2*n2 iterations) as NB pipelined bands; the ping-pong pointers advance as in run_direct.
+int run_bands(ns3d_ctx* ctx, const PtK& k2, int nb, double*& cur, double*& nxt, double*& dP, double*& dPn,
+              const double* divV, int n2, int iter0, const PeerBufs& pb, const double* Pr_user)
+{
+    NS3D_TRY(bands_prepare(ctx, nb));
+    const int planes = k2.kend - k2.kbeg;
+    const int nchunks = (planes + k2.zchunk - 1) / k2.zchunk;
+    const int per_band = (nchunks + nb - 1) / nb * k2.zchunk;  // bands are whole chunks (the last one may be shorter)
+    NS3D_CUDA(ctx, cudaEventRecord(ctx->band_fork, ctx->stream));
+    for (int b = 0; b < nb; ++b) NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->band_stream[b], ctx->band_fork, 0));
+    for (int q = 0; q < n2; ++q) {
+        const int par = q & 1;
+        for (int b = 0; b < nb; ++b) {
+            PtK kb = k2;
+            kb.kbeg = k2.kbeg + b * per_band;
+            kb.kend = std::min(kb.kbeg + per_band, k2.kend);
+            if (kb.kbeg >= kb.kend) continue;  // nb was clamped so that this cannot happen; belt and braces
+            kb.reverse = k2.serpentine && (((iter0 >> 1) + q) & 1);
+            if (q > 0) {  // launch q-1 of the adjacent bands (this band's own is ordered by its stream)
+                if (b > 0) NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->band_stream[b], ctx->band_ev[1 - par][b - 1], 0));
+                if (b < nb - 1) NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->band_stream[b], ctx->band_ev[1 - par][b + 1], 0));
+            }
+            NS3D_TRY(launch_tb2(ctx, ctx->band_stream[b], kb, cur, nxt, dP, dPn, divV, pb, Pr_user, false));
+            NS3D_CUDA(ctx, cudaEventRecord(ctx->band_ev[par][b], ctx->band_stream[b]));
+        }
+        double* t = cur; cur = nxt; nxt = t;
+        t = dP; dP = dPn; dPn = t;
+    }
+    const int last = (n2 - 1) & 1;
+    for (int b = 0; b < nb; ++b) NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->band_ev[last][b], 0));  // join
+    return NS3D_OK;
+}
+
 int run_direct(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double*& dP, double*& dPn, const double* divV, int n,
                int iter0, const PeerBufs& pb, const double* Pr_user)
 {
     NS3D_TRY(pt_begin(ctx));
     int q = 0;
-    if (dPn) {  // two iterations per launch; Pr and dPrdτ both ping-pong
+    if (dPn && ctx->opt_pt_bands >= 2 && ctx->nranks == 1 && n >= 2) {
+        PtK k2 = k;
+        k2.zchunk = k.zchunk_tb;
+        balance_chunks(k2);
+        const int nchunks = (k2.kend - k2.kbeg + k2.zchunk - 1) / k2.zchunk;
+        const int nb = std::min(ctx->opt_pt_bands, nchunks);  // every band gets at least one chunk
+        const int per_band_chunks = (nchunks + nb - 1) / nb;
+        const int nb_eff = (nchunks + per_band_chunks - 1) / per_band_chunks;
+        // a band must hold two planes at least: a launch reads two planes beyond its own range, and only
+        // the ADJACENT bands of the previous launch are waited for
+        if (nb_eff >= 2 && per_band_chunks * k2.zchunk >= 2) {
+            NS3D_TRY(run_bands(ctx, k2, nb_eff, cur, nxt, dP, dPn, divV, n / 2, iter0, pb, Pr_user));
+            q = n & ~1;
+        }
+    }
+    if (dPn && q == 0) {  // two iterations per launch; Pr and dPrdτ both ping-pong
         PtK k2 = k;
         k2.zchunk = k.zchunk_tb;
         const bool peer = pb.on && pb.tb2;
@@ -486,6 +554,8 @@ int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double*& d
     // NCCL send/recv captured in a graph drags host-callback nodes along (proxy progress) and
     // replays slower than the stream version (measured 55.9 vs 44.9 us/iteration on 2 GPUs), so
     // only kernel-only iterations are replayed as graphs.
+    // streams and events of the band pipeline are created outside any capture
+    if (ctx->opt_pt_bands >= 2 && ctx->nranks == 1) NS3D_TRY(bands_prepare(ctx, ctx->opt_pt_bands));
     const bool graphable = ctx->opt_graphs && n >= 8 && (ctx->nranks == 1 || pb.on);
     if (!graphable) return run_direct(ctx, k, cur, nxt, dP, dPn, divV, n, iter0, pb, Pr_user);
     if (!ctx->pt_graphs) ctx->pt_graphs = new PtGraphCache();
@@ -495,7 +565,8 @@ int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double*& d
     key.reverse = 0;
     // every tuning option that selects a kernel or its launch shape is part of the key
     const int opts = ctx->opt_tb2 | (ctx->opt_tb2_slim << 1) | (ctx->opt_tb2_np << 2) | (ctx->opt_tb2_pf << 3) |
-                     (ctx->opt_tb2_spec << 5) | (ctx->opt_tb2_dual << 6) | (ctx->opt_tb2_ty << 8) | (ctx->opt_tb2_pb << 16);
+                     (ctx->opt_tb2_spec << 5) | (ctx->opt_tb2_dual << 6) | (ctx->opt_tb2_ty << 8) | (ctx->opt_tb2_pb << 16) |
+                     (ctx->opt_pt_bands << 20);
     PtGraph* g = nullptr;
     for (PtGraph& c : cache->slot)
         if (c.exec && c.cur == cur && c.nxt == nxt && c.dP == dP && c.dPn == dPn && c.divV == divV && c.n == n &&

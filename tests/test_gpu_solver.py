@@ -74,7 +74,8 @@ CANDIDATES = pytest.mark.skipif(not os.environ.get("NS3D_TEST_CANDIDATES"),
 @pytest.mark.parametrize("grid", [(3, 3, 3), (5, 4, 3), (4, 3, 6), (37, 23, 19), (63, 38, 38), (70, 47, 41)])
 @pytest.mark.parametrize("zchunk", [0, 1, 2, 7])
 @pytest.mark.parametrize("kern", ["tb2s_auto", "tb2s_16_nopf", "tb2s_8_pf2", "tb2_first",
-                                  pytest.param("tb2d", marks=CANDIDATES), pytest.param("tb2s_pairbar", marks=CANDIDATES)])
+                                  pytest.param("tb2d", marks=CANDIDATES), pytest.param("tb2s_pairbar", marks=CANDIDATES),
+                                  pytest.param("bands4", marks=CANDIDATES), pytest.param("bands2_nographs", marks=CANDIDATES)])
 def test_two_iterations_per_launch_bit_exact(O, ns, ctx, variant, grid, zchunk, kern):
     """Temporal blocking (option "tb2"): 2 PT iterations per launch, rims recomputed, Pr^(1) kept in
     shared memory.  Same per-cell arithmetic -> still bit-equal to the oracle; odd counts end with
@@ -86,7 +87,8 @@ def test_two_iterations_per_launch_bit_exact(O, ns, ctx, variant, grid, zchunk, 
     ctx.set_option("tb2", 1)
     for name, val in {"tb2s_auto": {}, "tb2s_16_nopf": {"tb2_ty": 16, "tb2_pf": 0, "tb2_np": 0},
                       "tb2s_8_pf2": {"tb2_ty": 8, "tb2_pf": 2}, "tb2_first": {"tb2_slim": 0, "tb2_ty": 16},
-                      "tb2d": {"tb2_dual": 2}, "tb2s_pairbar": {"tb2_pairbar": 1}}[kern].items():
+                      "tb2d": {"tb2_dual": 2}, "tb2s_pairbar": {"tb2_pairbar": 1}, "bands4": {"pt_bands": 4},
+                      "bands2_nographs": {"pt_bands": 2, "graphs": 0}}[kern].items():
         ctx.set_option(name, val)
     d = {k: ctx.from_host(f[k]) for k in ("Pr", "dPrdtau", "divV")}
     done = 0
