@@ -130,3 +130,27 @@ def test_compile_time_stride_instantiation(O):
     emu.pt_iterate("pt_tb2s", ns.PARITY, s.pt_params(), g["Pr"], g["dPrdtau"], g["divV"], 2, ty=8)
     oracle_iterations(O, p, f, 2)
     assert np.array_equal(g["Pr"], f["Pr"]) and np.array_equal(g["dPrdtau"], f["dPrdtau"])
+
+
+def test_random_small_grids(O):
+    """Seeded sweep over odd shapes: grids from 3^3 up (narrower than a tile, one-row last tiles,
+    nz below the chunk length), every chunking, the three tile heights, both BC variants, outlet guard
+    on and off -- the default kernel and the two candidates, bit-exact against the oracle."""
+    rng = np.random.default_rng(2024)
+    for case in range(36):
+        variant = ["M", "G"][case % 2]
+        grid = (int(rng.integers(3, 70)), int(rng.integers(3, 40)), int(rng.integers(3, 30)))
+        zchunk = int(rng.choice([0, 1, 2, 3, 5, 9]))
+        kernel = ["pt_tb2s", "pt_tb2d", "pt_tb2s_pb"][case % 3]
+        ty = int(rng.choice([8, 16] if kernel == "pt_tb2s_pb" else [8, 16, 32]))
+        n = int(rng.choice([2, 3, 4]))
+        p, f = problem(O, variant, grid, 100 + case)
+        s = setup_for(variant, grid)
+        if variant == "M" and case % 4 == 0:
+            p.outlet_guard = False
+            s.outlet_guard = False
+        g = {k: f[k].copy(order="F") for k in ("Pr", "dPrdtau", "divV")}
+        emu.pt_iterate(kernel, ns.PARITY, s.pt_params(zchunk), g["Pr"], g["dPrdtau"], g["divV"], n, ty=ty)
+        oracle_iterations(O, p, f, n)
+        assert np.array_equal(g["Pr"], f["Pr"]) and np.array_equal(g["dPrdtau"], f["dPrdtau"]), \
+            (case, variant, grid, zchunk, kernel, ty, n)
