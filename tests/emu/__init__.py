@@ -125,6 +125,9 @@ def slab_rank_main(rank, nranks, names, grid, kernel, mode, pt_bytes, n_iter, ke
         rc = lib().emu_pt_slab_iterate(KERNELS[kernel], mode, C.addressof(pt), rank, nranks, C.addressof(b), n_iter,
                                        KERNELS[kernel_mid], ty_mid, C.byref(wp), C.byref(wd))
         queue.put((rank, rc, wp.value, wd.value))
+        del b
+        for m in mem.values():
+            m.close()
     except BaseException as exc:  # noqa: BLE001
         queue.put((rank, -99, repr(exc), 0))
 

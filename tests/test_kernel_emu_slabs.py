@@ -31,6 +31,7 @@ def truth_iterations(O, vr, n):
     (2, (20, 12, 26), 5, "pt_tb2", "pt_tb2", 16),     # + odd tail: one peer-store pt_iter_kernel launch
     (3, (14, 10, 9), 6, "pt_tb2", "pt_tb2s", 8),      # thin slabs: unsplit peer launches; the middle rank has two neighbours
     (2, (14, 10, 9), 3, "pt_iter", "pt_iter", 8),     # one-iteration kernel with peer stores only
+    (4, (9, 7, 23), 6, "pt_tb2", "pt_tb2d", 16),      # four ranks, split launches, the dual-row candidate in the interior
 ])
 def test_slab_ranks_in_processes_match_igg_emulation(O, world, grid, n_iter, kernel, kernel_mid, ty_mid):
     nx, ny, nz = grid
