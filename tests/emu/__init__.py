@@ -155,3 +155,34 @@ def pt_iterate(kernel: str, mode: int, pt_params, Pr: np.ndarray, dP: np.ndarray
     if rc != 0:
         raise RuntimeError(f"emu_pt_iterate failed ({rc})")
     return nl.value
+
+
+# ---- the whole library on the CPU ------------------------------------------------------------------
+def emulated_library() -> C.CDLL:
+    """tests/emu/_build/libns3d_emu.so (see build_lib.py): libns3d.so's translation units compiled by
+    g++ against a fake CUDA runtime, typed like the real one (native.SIGNATURES)."""
+    from navierstokes3d_b200 import native
+    from . import build_lib
+    lib = C.CDLL(build_lib.build())
+    for name, (res, args) in native.SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+class use_emulated_library:
+    """``with use_emulated_library():`` -- inside the block ``navierstokes3d_b200.native`` drives the
+    CPU-emulated library instead of libns3d.so, so Context / Simulation / the drivers run without a
+    GPU.  Test-only: the product has no switch for this; the binding's module global is patched
+    from the outside and restored on exit."""
+
+    def __enter__(self):
+        from navierstokes3d_b200 import native
+        self._native, self._saved = native, native._lib
+        native._lib = emulated_library()
+        return native._lib
+
+    def __exit__(self, *exc):
+        self._native._lib = self._saved
+        return False

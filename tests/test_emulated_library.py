@@ -1,0 +1,108 @@
+"""The GPU parity tests, run on the CPU against the EMULATED library.
+
+tests/emu/build_lib.py compiles libns3d.so's own translation units -- kernels and host code -- with
+g++ against a fake CUDA runtime (device memory = host memory, streams execute in order, stream
+capture records and a graph launch replays, one host thread per CUDA thread where a kernel
+synchronises).  With the ctypes binding pointed at that library the ordinary test functions of
+test_gpu_kernels.py / test_gpu_solver.py / test_gpu_zz_output.py run unchanged: same Context, same
+entry points, same oracle comparisons, bit for bit -- including the host logic a kernel-only
+emulation cannot see (ping-pong bookkeeping across captured chunks, copy-back after odd counts, the
+residual loop, ns3d_step's composition).  The big cases stay GPU-only; what runs here is sized for
+a CPU.  This is test infrastructure: the product has no switch that selects the emulated library.
+"""
+import numpy as np
+import pytest
+
+import tests.test_gpu_kernels as K
+import tests.test_gpu_solver as S
+import tests.test_gpu_zz_output as Z
+from tests import emu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _emulated_library():
+    with emu.use_emulated_library():
+        yield
+
+
+# ---- level 1: every kernel test of test_gpu_kernels.py, unchanged ------------------------------------
+for _name in dir(K):
+    if _name.startswith("test_"):
+        globals()[_name] = getattr(K, _name)
+
+# ---- output path: the box tests of test_gpu_zz_output.py --------------------------------------------
+test_box_matches_numpy_slicing = Z.test_box_matches_numpy_slicing
+test_box_rejects_a_box_outside_the_array = Z.test_box_rejects_a_box_outside_the_array
+
+
+# ---- level 2 on CPU-sized grids ---------------------------------------------------------------------
+@pytest.mark.parametrize("variant", ["M", "G"])
+@pytest.mark.parametrize("grid", [(3, 3, 3), (5, 4, 3), (20, 12, 9)])
+@pytest.mark.parametrize("zchunk", [0, 5])
+def test_fused_iteration(O, ns, ctx, variant, grid, zchunk):
+    S.test_fused_iteration_bit_exact(O, ns, ctx, variant, grid, zchunk)
+
+
+@pytest.mark.parametrize("variant,grid,zchunk,kern", [
+    ("M", (3, 3, 3), 0, "tb2s_auto"), ("G", (4, 3, 6), 2, "tb2s_auto"), ("M", (37, 23, 19), 7, "tb2s_auto"),
+    ("G", (37, 23, 19), 0, "tb2s_16_nopf"), ("M", (20, 19, 11), 1, "tb2s_8_pf2"), ("G", (20, 12, 12), 0, "tb2_first"),
+    ("M", (20, 12, 12), 2, "tb2d"), ("G", (20, 19, 11), 0, "tb2s_pairbar"), ("M", (20, 12, 14), 3, "bands4"),
+    ("G", (20, 12, 9), 2, "bands2_nographs"),
+])
+def test_two_iterations_per_launch(O, ns, ctx, variant, grid, zchunk, kern):
+    """Every kernel variant behind the options, the candidates and the z-band pipeline included, through
+    ns3d_pt_iterate: 2, 1, 5 and 40 iterations (graph capture and replay from 8 iterations up)."""
+    S.test_two_iterations_per_launch_bit_exact(O, ns, ctx, variant, grid, zchunk, kern)
+
+
+def test_outlet_guard_off(O, ns, ctx):
+    S.test_outlet_guard_off(O, ns, ctx)
+
+
+def test_pt_solve_nonfinite_breaks(O, ns, ctx):
+    S.test_pt_solve_nonfinite_breaks(O, ns, ctx)
+
+
+@pytest.mark.parametrize("variant", ["M", "G"])
+def test_pt_solve_matches_oracle(O, ns, ctx, variant):
+    """The full loop with residual checks (test_gpu_solver.test_pt_solve_matches_oracle on a smaller grid):
+    same iteration count, same err history, bit-exact fields."""
+    grid = (16, 10, 10)
+    p, f = S.pt_problem(O, variant, grid, 13)
+    s = S.setup_for(ns, variant, grid[0], ny=grid[1], nz=grid[2])
+    f["Pr"][...] = 0.0
+    f["dPrdtau"][...] = 0.0
+    if variant == "G":   # start from the hydrostatic state so that the loop converges
+        f["Pr"][...] = O.initial_fields(p)["Pr"]
+    d = {k: ctx.from_host(f[k]) for k in ("Pr", "dPrdtau", "divV")}
+    it_o, hist_o = O.pt_solve(p, f)
+    it_g, hist_g = ctx.pt_solve(d["Pr"], d["dPrdtau"], d["divV"], s.pt_params())
+    assert it_g == it_o and it_o >= p.nchk and hist_g == hist_o
+    assert (d["Pr"].to_host() == f["Pr"]).all() and (d["dPrdtau"].to_host() == f["dPrdtau"]).all()
+
+
+@pytest.mark.parametrize("variant,nx,nt,how", [("M", 20, 3, "step"), ("G", 16, 1, "step"), ("M", 24, 2, "groups"),
+                                               ("G", 16, 1, "groups"), ("G", 16, 1, "level1")])
+def test_whole_time_steps(O, ns, variant, nx, nt, how):
+    """ns3d_step, its four level-2 groups, and the call-by-call level-1 loop: identical PT iteration counts
+    and err history, bit-exact fields."""
+    p = O.params_M(nx) if variant == "M" else O.params_G(nx)
+    f, iters_o, errs_o = O.run(p, nt)
+    sim = ns.Simulation(ns.setup_multi_gpu(nx) if variant == "M" else ns.setup_gpu(nx), ns.Context(0, ns.PARITY))
+    for _ in range(nt):
+        {"step": sim.step, "groups": sim.step_groups, "level1": sim.step_level1}[how]()
+    assert sim.iters == iters_o
+    assert np.array_equal(np.concatenate(sim.err_hist), np.concatenate(errs_o), equal_nan=True)
+    for name in ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C", "divV"):
+        got = sim.host(name)
+        assert ((got == f[name]) | (np.isnan(got) & np.isnan(f[name]))).all(), name
+    sim.ctx.close()
+
+
+def test_driver_returns_the_reference_test_call(O, ns):
+    """test/test3D.jl:6 through the drop-in driver (nx=63, nt=1: the degenerate first step, 37 iterations)."""
+    C, Pr, Vx, Vy, Vz = ns.run_navierstokes3D(do_vis=False, do_save=False, do_print=False, nx=63, nt=1, mode=ns.PARITY)
+    assert Pr.shape == (61, 36, 36) and (Pr == 0.0).all()
+    f, _, _ = O.run(O.params_M(63), 1)
+    for got, name in ((C, "C"), (Pr, "Pr"), (Vx, "Vx"), (Vy, "Vy"), (Vz, "Vz")):
+        assert np.array_equal(got, O.interior(f[name])), name
