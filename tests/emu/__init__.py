@@ -186,3 +186,70 @@ class use_emulated_library:
     def __exit__(self, *exc):
         self._native._lib = self._saved
         return False
+
+
+def multi_rank_main(rank, world, grid, nt, lz, how, options, uid_pipes, queue):
+    """Body of one rank PROCESS of an emulated multi-rank run (spawned with NS3D_EMU_SHARED_ARENA=1 and
+    LD_LIBRARY_PATH = tests/emu/_build): the library's own multi-GPU host path -- NCCL bootstrap, CUDA IPC
+    peer mappings, stream/event protocol, graph replay, halo exchanges, residual all-reduce -- over the fake
+    runtime, checked against the oracle's ImplicitGlobalGrid emulation for this rank."""
+    try:
+        import navierstokes3d_b200 as ns
+        from oracle import oracle as O
+        nx, ny, nz = grid
+        with use_emulated_library():
+            ctx = ns.Context(0, ns.PARITY)
+            if rank == 0:
+                uid = ctx.unique_id()
+                for p in uid_pipes:
+                    p.send(uid)
+            else:
+                uid = uid_pipes.recv()
+            ctx.comm_init(rank, world, uid)
+            for name, val in options.items():
+                ctx.set_option(name, val)
+            s = ns.setup_multi_gpu(nx, ny=ny, nz=nz, rank=rank, nranks=world, lz=lz)
+            sim = ns.Simulation(s, ctx)
+            truth = O.VirtualRanks(nx, ny, nz, (1, 1, world), lz=lz)
+            names = ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C", "divV")
+            if how == "pt_random":
+                # The script's flow is invariant along z for many steps, which would hide a wrong plane
+                # offset across a slab interface: the fused loop alone on random fields (same seed in
+                # every rank process -> the same global state; halos made consistent), nt iterations.
+                rng = np.random.default_rng(4321)
+                for f in truth.f:
+                    f["Pr"][...] = rng.uniform(-1, 1, size=f["Pr"].shape)
+                    f["dPrdtau"][...] = rng.uniform(-1, 1, size=f["dPrdtau"].shape)
+                    f["divV"][...] = rng.uniform(-1e-3, 1e-3, size=f["divV"].shape)
+                truth.update_halo("Pr")
+                truth.update_halo("divV")
+                names = ("Pr", "dPrdtau")
+                for name in names + ("divV",):
+                    sim.f[name].set(truth.f[rank][name])
+                ctx.pt_iterate(sim.f["Pr"], sim.f["dPrdtau"], sim.f["divV"], s.pt_params(), nt)
+                for _ in range(nt):
+                    truth.each(O.update_dPrdtau)   # M:459
+                    truth.each(O.update_Pr)        # M:461
+                    truth.update_halo("Pr")        # M:462
+                    truth.each(O.set_bc_Pr)        # M:463
+                    truth.update_halo("Pr")        # M:182
+                sim.iters, truth.iters = [nt], [nt]
+            else:
+                for _ in range(nt):
+                    {"step": sim.step, "level1": sim.step_level1, "groups": sim.step_groups}[how]()
+                for _ in range(nt):
+                    truth.step()
+            problems = []
+            for name in names:
+                got = sim.host(name)
+                bad = got != truth.f[rank][name]
+                if bad.any() or not np.isfinite(got).all():
+                    problems.append(f"{name}: {int(bad.sum())} values differ (planes {sorted(set(np.argwhere(bad)[:, 2].tolist()))})")
+            if sim.iters != truth.iters:
+                problems.append(f"iterations {sim.iters} != {truth.iters}")
+            p2p = bool(ctx.lib.ns3d_comm_size(ctx.h) == world)
+            queue.put((rank, problems, sim.iters, int(ctx.launch_count), p2p))
+            ctx.close()
+    except BaseException as exc:  # noqa: BLE001
+        import traceback
+        queue.put((rank, ["exception: " + repr(exc) + "\n" + traceback.format_exc()], None, 0, False))

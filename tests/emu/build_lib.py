@@ -108,7 +108,8 @@ def rewrite_launches(src: str) -> str:
 def build(force: bool = False) -> str:
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
     deps += [os.path.join(HERE, "cuda_host_shim.h"), os.path.join(HERE, "fake_cuda", "cuda_runtime.h"),
-             os.path.join(HERE, "fake_cuda", "nccl.h"), os.path.join(ROOT, "include", "ns3d.h"), __file__]
+             os.path.join(HERE, "fake_cuda", "nccl.h"), os.path.join(HERE, "fake_nccl.cpp"),
+             os.path.join(ROOT, "include", "ns3d.h"), __file__]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     os.makedirs(OUT, exist_ok=True)
@@ -134,9 +135,16 @@ def build(force: bool = False) -> str:
             errs.append(f"--- {name}\n{err[-6000:]}")
     if errs:
         raise RuntimeError("g++ failed building the emulated library:\n" + "\n".join(errs))
-    res = subprocess.run(["g++", "-shared", "-pthread", *objs, "-o", LIB, "-ldl"], capture_output=True, text=True, env=env)
+    res = subprocess.run(["g++", "-shared", "-pthread", *objs, "-o", LIB, "-ldl", "-lrt"], capture_output=True, text=True,
+                         env=env)
     if res.returncode != 0:
         raise RuntimeError("linking the emulated library failed:\n" + res.stderr[-4000:])
+    # the fake NCCL the emulated library dlopens in multi-rank runs (LD_LIBRARY_PATH = this directory)
+    res = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-pthread",
+                          os.path.join(HERE, "fake_nccl.cpp"), "-o", os.path.join(OUT, "libnccl.so.2"), "-lrt"],
+                         capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        raise RuntimeError("building the fake NCCL failed:\n" + res.stderr[-4000:])
     return LIB
 
 

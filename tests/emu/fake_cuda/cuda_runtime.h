@@ -9,7 +9,12 @@
 
 #include "../cuda_host_shim.h"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
 #include <functional>
+#include <map>
 #include <string>
 
 typedef int cudaError_t;
@@ -70,16 +75,71 @@ inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { re
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new FakeEvent{0}; return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+// Multi-rank emulation (ranks = processes, tests/test_emulated_multi_rank.py): with
+// NS3D_EMU_SHARED_ARENA=1 "device" memory comes from a per-process POSIX shared-memory arena, so
+// that cudaIpcGetMemHandle / cudaIpcOpenMemHandle can hand a peer process a mapping of it -- what
+// CUDA IPC does between GPUs of one box.  A bump allocator: cudaFree is a no-op there.
+namespace emu {
+struct Arena {
+    char* base = nullptr;
+    size_t size = 0, used = 0;
+    std::string name;
+};
+inline Arena& arena()
+{
+    static Arena a;
+    if (!a.base && std::getenv("NS3D_EMU_SHARED_ARENA")) {
+        a.size = (size_t)1 << 30;  // sparse: pages exist once touched
+        a.name = "/ns3d_emu_" + std::to_string((long)getpid());
+        const int fd = shm_open(a.name.c_str(), O_CREAT | O_RDWR, 0600);
+        if (fd < 0 || ftruncate(fd, (off_t)a.size) != 0) {
+            std::perror("emu arena");
+            std::abort();
+        }
+        a.base = (char*)mmap(nullptr, a.size, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_NORESERVE, fd, 0);
+        close(fd);
+        if (a.base == MAP_FAILED) {
+            std::perror("emu arena mmap");
+            std::abort();
+        }
+        std::atexit([]() { shm_unlink(arena().name.c_str()); });
+    }
+    return a;
+}
+struct IpcHandle {  // the 64 bytes of a cudaIpcMemHandle_t
+    unsigned long long magic;
+    long pid;
+    unsigned long long offset;
+};
+inline std::map<long, char*>& peer_arenas()
+{
+    static std::map<long, char*> m;
+    return m;
+}
+}  // namespace emu
+
 inline cudaError_t cudaMalloc(void** p, size_t n)
 {
-    *p = std::aligned_alloc(256, (n + 255) / 256 * 256);
-    if (!*p) return cudaErrorMemoryAllocation;
+    emu::Arena& a = emu::arena();
+    if (a.base) {
+        const size_t off = (a.used + 255) / 256 * 256;
+        if (off + n > a.size) return cudaErrorMemoryAllocation;
+        *p = a.base + off;
+        a.used = off + n;
+    } else {
+        *p = std::aligned_alloc(256, (n + 255) / 256 * 256);
+        if (!*p) return cudaErrorMemoryAllocation;
+    }
     std::memset(*p, 0xff, n);  // NaN patterns: uninitialised device memory must not look like zeros
     return cudaSuccess;
 }
 template <class T>
 inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
-inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaFree(void* p)
+{
+    if (!emu::arena().base) std::free(p);
+    return cudaSuccess;
+}
 inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = std::malloc(n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 template <class T>
 inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMallocHost((void**)p, n); }
@@ -125,7 +185,34 @@ inline cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t)
     for (auto& f : *e) emu::enqueue(f);
     return cudaSuccess;
 }
-// no peers in the emulated box
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+// peers exist only in shared-arena mode (see emu::arena)
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p)
+{
+    emu::Arena& a = emu::arena();
+    if (!a.base || (char*)p < a.base || (char*)p >= a.base + a.size) return cudaErrorNotSupported;
+    emu::IpcHandle ih{0x4e533344454d55ULL, (long)getpid(), (unsigned long long)((char*)p - a.base)};
+    std::memset(h, 0, sizeof *h);
+    std::memcpy(h, &ih, sizeof ih);
+    return cudaSuccess;
+}
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned)
+{
+    emu::IpcHandle ih;
+    std::memcpy(&ih, &h, sizeof ih);
+    if (ih.magic != 0x4e533344454d55ULL) return cudaErrorInvalidValue;
+    char*& base = emu::peer_arenas()[ih.pid];
+    if (!base) {
+        const std::string name = "/ns3d_emu_" + std::to_string(ih.pid);
+        const int fd = shm_open(name.c_str(), O_RDWR, 0600);
+        if (fd < 0) return cudaErrorInvalidValue;
+        base = (char*)mmap(nullptr, (size_t)1 << 30, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_NORESERVE, fd, 0);
+        close(fd);
+        if (base == MAP_FAILED) {
+            base = nullptr;
+            return cudaErrorInvalidValue;
+        }
+    }
+    *p = base + ih.offset;
+    return cudaSuccess;
+}
 inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }

@@ -1,0 +1,71 @@
+"""The library's multi-GPU host path on the CPU: one PROCESS per rank, the emulated library in each.
+
+"Device" memory is a POSIX shared-memory arena per process, so the fake runtime's cudaIpcGetMemHandle /
+cudaIpcOpenMemHandle give a rank a real mapping of its neighbours' fields and mailboxes; a fake
+libnccl.so.2 (tests/emu/fake_nccl.cpp) carries ncclSend/Recv/AllReduce over shared-memory rings.
+Everything else is libns3d.so's own code: ns3d_comm_init (NCCL bootstrap, mailbox exchange, the
+min-all-reduce that makes all ranks agree on the peer-memory path), peer_prepare, the split
+interface/interior launches with their event protocol, graph capture and replay, the once-per-step
+halo exchanges over NCCL, the residual max-all-reduce.  Truth: the oracle's ImplicitGlobalGrid
+emulation (tests/test_gpu_multi.py runs the same comparison on real GPUs).  Bit-exact.
+"""
+import multiprocessing as mp
+import os
+
+import pytest
+
+from tests import emu
+from tests.emu import build_lib
+
+
+def run_ranks(world, grid, nt, lz, how="step", options=None):
+    build_lib.build()
+    saved = {k: os.environ.get(k) for k in ("NS3D_EMU_SHARED_ARENA", "LD_LIBRARY_PATH")}
+    os.environ["NS3D_EMU_SHARED_ARENA"] = "1"
+    os.environ["LD_LIBRARY_PATH"] = build_lib.OUT + os.pathsep + (saved["LD_LIBRARY_PATH"] or "")
+    try:
+        ctx = mp.get_context("spawn")     # fresh processes: the dynamic loader reads LD_LIBRARY_PATH at start-up
+        queue = ctx.Queue()
+        pipes = [ctx.Pipe(duplex=False) for _ in range(world - 1)]   # rank 0 -> the others: the NCCL unique id
+        procs = []
+        for r in range(world):
+            ends = [w for _, w in pipes] if r == 0 else pipes[r - 1][0]
+            procs.append(ctx.Process(target=emu.multi_rank_main,
+                                     args=(r, world, grid, nt, lz, how, options or {}, ends, queue)))
+        for p in procs:
+            p.start()
+        results = {}
+        for _ in range(world):
+            rank, problems, iters, launches, _ = queue.get(timeout=600)
+            results[rank] = (problems, iters, launches)
+        for p in procs:
+            p.join(timeout=60)
+        return results
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("world,grid,nt,lz,how,options", [
+    (2, (20, 12, 9), 2, None, "step", {}),                        # thin slabs: unsplit peer launches
+    (2, (16, 10, 26), 2, 50 / 16, "step", {}),                     # split launches: interface chunks + slim interior
+    (3, (16, 10, 8), 2, 20 / 16, "step", {"tb2": 0}),              # one-iteration kernel, peer stores, three ranks
+    (2, (16, 10, 9), 2, None, "step", {"p2p_halo": 0}),            # NCCL send/recv halo path instead of peer memory
+    (2, (16, 10, 9), 1, None, "level1", {}),                       # the call-by-call level-1 loop over NCCL
+    # the fused loop alone on RANDOM fields (the script's flow is z-invariant and would hide a wrong plane offset)
+    (2, (16, 10, 26), 12, 50 / 16, "pt_random", {}),               # split launches, graph replay (>= 8 iterations)
+    (3, (14, 10, 9), 7, 23 / 14, "pt_random", {}),                 # unsplit peer launches + odd tail, three ranks
+    (2, (14, 10, 9), 5, None, "pt_random", {"tb2": 0}),            # one-iteration kernel with peer stores
+    (2, (14, 10, 9), 5, None, "pt_random", {"p2p_halo": 0}),       # NCCL send/recv halo exchange
+    (4, (12, 9, 23), 6, 86 / 12, "pt_random", {"tb2_dual": 2}),    # four ranks, the dual-row candidate in the interior
+])
+def test_rank_processes_match_igg_emulation(world, grid, nt, lz, how, options):
+    results = run_ranks(world, grid, nt, lz, how, options)
+    for r in range(world):
+        problems, iters, launches = results[r]
+        assert not problems, f"rank {r}: " + "; ".join(problems)
+        assert launches > 0 and iters is not None
+    assert len({tuple(results[r][1]) for r in range(world)}) == 1   # every rank saw the same iteration counts
