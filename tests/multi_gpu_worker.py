@@ -29,22 +29,47 @@ def main():
     s = ns.setup_multi_gpu(nx, ny=ny, nz=nz, rank=rank, nranks=world, lz=lz)
     ctx = ns.Context(local, ns.PARITY)
     attach_communicator(ctx, rank, world)
-    ctx.set_option("tb2", 1 if tb2 else 0)
+    pt_random = len(sys.argv) > 6 and sys.argv[6] == "pt_random"
+    ctx.set_option("tb2", 1 if (tb2 or pt_random) else 0)
     sim = ns.Simulation(s, ctx)
-    for _ in range(nt):
-        sim.step_level1() if level1 else sim.step()
     truth = O.VirtualRanks(nx, ny, nz, (1, 1, world), lz=lz)
-    for _ in range(nt):
-        truth.step()
+    names = ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C", "divV")
+    if pt_random:
+        # The script's flow is invariant along z for many steps, which would hide a wrong plane offset
+        # across a slab interface: the fused loop alone on random fields (same seed on every rank ->
+        # the same global state; halos made consistent), nt iterations (tests/emu runs the same on the CPU).
+        rng = np.random.default_rng(4321)
+        for f in truth.f:
+            f["Pr"][...] = rng.uniform(-1, 1, size=f["Pr"].shape)
+            f["dPrdtau"][...] = rng.uniform(-1, 1, size=f["dPrdtau"].shape)
+            f["divV"][...] = rng.uniform(-1e-3, 1e-3, size=f["divV"].shape)
+        truth.update_halo("Pr")
+        truth.update_halo("divV")
+        names = ("Pr", "dPrdtau")
+        for name in names + ("divV",):
+            sim.f[name].set(truth.f[rank][name])
+        ctx.pt_iterate(sim.f["Pr"], sim.f["dPrdtau"], sim.f["divV"], s.pt_params(), nt)
+        for _ in range(nt):
+            truth.each(O.update_dPrdtau)   # M:459
+            truth.each(O.update_Pr)        # M:461
+            truth.update_halo("Pr")        # M:462
+            truth.each(O.set_bc_Pr)        # M:463
+            truth.update_halo("Pr")        # M:182
+        sim.iters, truth.iters = [nt], [nt]
+    else:
+        for _ in range(nt):
+            sim.step_level1() if level1 else sim.step()
+        for _ in range(nt):
+            truth.step()
     problems = []
-    for name in ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C", "divV"):
+    for name in names:
         got = sim.host(name)
         bad = (got != truth.f[rank][name])
         if bad.any() or not np.isfinite(got).all():
             problems.append(f"rank {rank}: {name}: {bad.sum()} values differ (planes {sorted(set(np.argwhere(bad)[:, 2].tolist()))})")
     assert sim.iters == truth.iters and not problems, (sim.iters, truth.iters, problems)
     # gather!(A_inn, A_v): interior of the global field on rank 0
-    for name in ("Pr", "Vz", "C"):
+    for name in (() if pt_random else ("Pr", "Vz", "C")):
         g = gather_interior(sim, name)
         if rank == 0:
             want = truth.assemble(name)[1:-1, 1:-1, 1:-1]

@@ -28,7 +28,11 @@ def free_port():
                                                      (2, (40, 24, 13), 4, None, "tb2"), (2, (40, 24, 26), 3, 50 / 40, "tb2"),
                                                      (4, (40, 24, 10), 3, 34 / 40, "tb2"),
                                                      (8, (40, 24, 6), 3, 34 / 40, "tb2"),
-                                                     (4, (40, 24, 10), 3, 34 / 40, "fused"), (8, (40, 24, 6), 3, 34 / 40, "fused")])
+                                                     (4, (40, 24, 10), 3, 34 / 40, "fused"), (8, (40, 24, 6), 3, 34 / 40, "fused"),
+                                                     # the fused loop alone on random fields: catches plane-offset
+                                                     # errors the z-invariant flow would hide
+                                                     (2, (40, 24, 26), 12, 50 / 40, "pt_random"),
+                                                     (4, (40, 24, 10), 7, 34 / 40, "pt_random")])
 def test_slabs_match_igg_emulation(world, grid, nt, lz, level):
     if gpu_count() < world:
         pytest.skip(f"needs {world} GPUs")
