@@ -36,7 +36,6 @@ struct dim3 {
 namespace emu {
 inline thread_local dim3 tls_threadIdx, tls_blockIdx;
 inline dim3 g_blockDim, g_gridDim;
-inline pthread_barrier_t g_barrier;
 inline pthread_barrier_t g_named[16];      // bar.sync id, count: initialised on first use within a block
 inline int g_named_count[16];
 inline pthread_mutex_t g_named_lock = PTHREAD_MUTEX_INITIALIZER;
@@ -50,14 +49,7 @@ inline bool g_serial = false;              // the running launch has no host thr
 using std::max;
 using std::min;
 
-inline void __syncthreads()
-{
-    if (emu::g_serial) {
-        std::fprintf(stderr, "emu: __syncthreads() inside a kernel that was launched without threads\n");
-        std::abort();
-    }
-    pthread_barrier_wait(&emu::g_barrier);
-}
+inline void __syncthreads();
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline long long clock64()  // 10 ns ticks: the kernels' spin limits (8e9 "cycles") become 80 s, generous for a loaded CI box
 {
@@ -119,72 +111,106 @@ inline unsigned linear_tid()
     return tls_threadIdx.x + g_blockDim.x * (tls_threadIdx.y + g_blockDim.y * tls_threadIdx.z);
 }
 
-struct ThreadArg {
-    void (*fn)(void*);
-    void* ctx;
-    dim3 tid;
-    dim3 grid;
+// One host thread per CUDA thread of a block.  The threads live in a POOL per block size and are
+// reused by every launch of that size (creating 256-512 threads per launch dominated the run time
+// of many-launch tests): a launch publishes its job, releases the pool through a start barrier and
+// waits for it at a done barrier.  Inside a launch each pool thread runs its CUDA thread of every
+// block in turn, with a block-wide barrier between blocks (blocks execute one after the other, so
+// function-local `static` really is per-block shared memory).
+struct Job {
+    void (*fn)(void*) = nullptr;
+    void* ctx = nullptr;
+    dim3 grid, block;
+};
+struct Pool {
+    unsigned nthreads = 0;
+    pthread_barrier_t start, done, sync;   // start/done: pool + launcher; sync: the pool (= __syncthreads)
+    Job job;
+    std::vector<WarpXchg> warps;
+};
+inline Pool* g_pool = nullptr;             // the pool of the running launch
+
+struct PoolThread {
+    Pool* pool;
+    unsigned tid;
 };
 
-// One host thread per CUDA thread of a block, alive for the whole launch: it runs its CUDA thread of
-// every block in turn, with a block-wide barrier between blocks (blocks execute one after the other,
-// so function-local `static` really is per-block shared memory).
-inline void* thread_main(void* a)
+inline void* pool_main(void* a)
 {
-    ThreadArg* t = (ThreadArg*)a;
-    tls_threadIdx = t->tid;
-    for (unsigned bz = 0; bz < t->grid.z; ++bz)
-        for (unsigned by = 0; by < t->grid.y; ++by)
-            for (unsigned bx = 0; bx < t->grid.x; ++bx) {
-                tls_blockIdx = dim3(bx, by, bz);
-                t->fn(t->ctx);
-                pthread_barrier_wait(&g_barrier);   // end of block: every thread is out of the kernel
-                if (t->tid.x == 0 && t->tid.y == 0 && t->tid.z == 0) {
-                    for (int id = 0; id < 16; ++id)
-                        if (g_named_count[id]) {
-                            pthread_barrier_destroy(&g_named[id]);
-                            g_named_count[id] = 0;
-                        }
+    PoolThread* me = (PoolThread*)a;
+    Pool* p = me->pool;
+    for (;;) {
+        pthread_barrier_wait(&p->start);
+        const Job& j = p->job;
+        const unsigned t = me->tid;
+        tls_threadIdx = dim3(t % j.block.x, (t / j.block.x) % j.block.y, t / (j.block.x * j.block.y));
+        for (unsigned bz = 0; bz < j.grid.z; ++bz)
+            for (unsigned by = 0; by < j.grid.y; ++by)
+                for (unsigned bx = 0; bx < j.grid.x; ++bx) {
+                    tls_blockIdx = dim3(bx, by, bz);
+                    j.fn(j.ctx);
+                    pthread_barrier_wait(&p->sync);   // end of block: every thread is out of the kernel
+                    if (t == 0) {
+                        for (int id = 0; id < 16; ++id)
+                            if (g_named_count[id]) {
+                                pthread_barrier_destroy(&g_named[id]);
+                                g_named_count[id] = 0;
+                            }
+                    }
+                    pthread_barrier_wait(&p->sync);
                 }
-                pthread_barrier_wait(&g_barrier);
-            }
+        pthread_barrier_wait(&p->done);
+    }
     return nullptr;
+}
+
+inline Pool* get_pool(unsigned nthreads)
+{
+    static std::vector<Pool*> pools;
+    for (Pool* p : pools)
+        if (p->nthreads == nthreads) return p;
+    Pool* p = new Pool();
+    p->nthreads = nthreads;
+    pthread_barrier_init(&p->start, nullptr, nthreads + 1);
+    pthread_barrier_init(&p->done, nullptr, nthreads + 1);
+    pthread_barrier_init(&p->sync, nullptr, nthreads);
+    p->warps.resize((nthreads + 31) / 32);
+    for (size_t w = 0; w < p->warps.size(); ++w)
+        pthread_barrier_init(&p->warps[w].bar, nullptr, std::min(32u, nthreads - 32u * (unsigned)w));
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    pthread_attr_setstacksize(&attr, 256 * 1024);
+    pthread_attr_setdetachstate(&attr, PTHREAD_CREATE_DETACHED);
+    for (unsigned t = 0; t < nthreads; ++t) {
+        pthread_t th;
+        if (pthread_create(&th, &attr, pool_main, new PoolThread{p, t}) != 0) {
+            std::fprintf(stderr, "emu: pthread_create failed\n");
+            std::abort();
+        }
+    }
+    pthread_attr_destroy(&attr);
+    pools.push_back(p);
+    return p;
 }
 
 // Runs `body()` once per CUDA thread of a grid x block launch, CUDA threads = host threads.
 template <class F>
 void launch(dim3 grid, dim3 block, F body)
 {
-    const unsigned nthreads = block.x * block.y * block.z;
+    Pool* p = get_pool(block.x * block.y * block.z);
     g_gridDim = grid;
     g_blockDim = block;
     g_serial = false;
-    std::vector<WarpXchg> warps((nthreads + 31) / 32);
-    for (size_t w = 0; w < warps.size(); ++w)
-        pthread_barrier_init(&warps[w].bar, nullptr, std::min(32u, nthreads - 32u * (unsigned)w));
-    g_warps = &warps;
-    pthread_attr_t attr;
-    pthread_attr_init(&attr);
-    pthread_attr_setstacksize(&attr, 256 * 1024);
-    std::vector<pthread_t> th(nthreads);
-    std::vector<ThreadArg> args(nthreads);
-    auto tramp = [](void* c) { (*(F*)c)(); };
-    pthread_barrier_init(&g_barrier, nullptr, nthreads);
-    unsigned t = 0;
-    for (unsigned tz = 0; tz < block.z; ++tz)
-        for (unsigned ty = 0; ty < block.y; ++ty)
-            for (unsigned tx = 0; tx < block.x; ++tx, ++t) {
-                args[t] = ThreadArg{tramp, &body, dim3(tx, ty, tz), grid};
-                if (pthread_create(&th[t], &attr, thread_main, &args[t]) != 0) {
-                    std::fprintf(stderr, "emu: pthread_create failed\n");
-                    std::abort();
-                }
-            }
-    for (unsigned q = 0; q < nthreads; ++q) pthread_join(th[q], nullptr);
-    pthread_barrier_destroy(&g_barrier);
-    for (auto& w : warps) pthread_barrier_destroy(&w.bar);
+    g_pool = p;
+    g_warps = &p->warps;
+    p->job.fn = [](void* c) { (*(F*)c)(); };
+    p->job.ctx = &body;
+    p->job.grid = grid;
+    p->job.block = block;
+    pthread_barrier_wait(&p->start);
+    pthread_barrier_wait(&p->done);
+    g_pool = nullptr;
     g_warps = nullptr;
-    pthread_attr_destroy(&attr);
 }
 
 // The same for kernels that never synchronise (no __syncthreads, shuffles or named barriers): the
@@ -210,6 +236,15 @@ void launch_serial(dim3 grid, dim3 block, F body)
 }
 
 }  // namespace emu
+
+inline void __syncthreads()
+{
+    if (emu::g_serial) {
+        std::fprintf(stderr, "emu: __syncthreads() inside a kernel that was launched without threads\n");
+        std::abort();
+    }
+    pthread_barrier_wait(&emu::g_pool->sync);
+}
 
 inline unsigned long long __shfl_xor_sync(unsigned, unsigned long long v, int lane_mask)
 {
