@@ -84,6 +84,8 @@ NS3D_API int ns3d_get_mode(const ns3d_ctx* ctx);
  *   "tb2_spec"    1* compile-time-stride instantiation when the grid's x-y extent has one
  *   "tb2_dual"    0* | 2: pt_tb2d_kernel, two tile rows per thread (value = CTAs per SM)       [candidate]
  *   "tb2_pairbar" 0* | 1: pairwise row barriers instead of __syncthreads in pt_tb2s_kernel     [candidate]
+ *   "tb2_slim_faces" 0* | 1: slab-interface chunks with pt_tb2sp_kernel (the slim pipeline with peer
+ *                 loads/stores) instead of pt_tb2_kernel<.,16,true>                            [candidate]
  *   "pt_bands"    0* | 2..8: split every two-iteration launch into z-bands with band-to-band dependencies
  *                 so that consecutive launches overlap (single rank)                           [candidate]
  *   "pt_minb"     CTAs per SM the one-iteration kernel is compiled for: 0* = per mode, 3..6

@@ -205,6 +205,10 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
         ctx->opt_pt_bands = value;
         return NS3D_OK;
     }
+    if (!strcmp(name, "tb2_slim_faces")) {
+        ctx->opt_tb2_slim_faces = value != 0;
+        return NS3D_OK;
+    }
     if (!strcmp(name, "tb2_pairbar")) {
         ctx->opt_tb2_pb = value != 0;
         return NS3D_OK;

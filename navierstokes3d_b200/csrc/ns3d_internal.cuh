@@ -61,6 +61,7 @@ struct ns3d_ctx {
     int opt_tb2_spec = 1;     // pt_tb2s_kernel: use the compile-time-stride instantiation when the grid has one
     int opt_pt_bands = 0;     // >= 2: split every two-iteration launch into that many z-bands with band-to-band
                               // dependencies, so that launch n+1 starts while launch n drains (candidate, single rank)
+    int opt_tb2_slim_faces = 0;  // slab-interface chunks with pt_tb2sp_kernel instead of pt_tb2_kernel<.,16,true> (candidate)
     int opt_tb2_pb = 0;       // pt_tb2s_kernel: pairwise row barriers instead of __syncthreads (candidate)
     int opt_tb2_dual = 0;     // pt_tb2d_kernel (two tile rows per thread) for plain launches: 0 off, 2 = CTAs per SM
     int opt_tb2_slim = 1;     // plain two-iteration launches use pt_tb2s_kernel (0 = pt_tb2_kernel)

@@ -202,7 +202,9 @@ int launch_tb2(ns3d_ctx* ctx, cudaStream_t st, const PtK& k_in, const double* cu
     // plain launches run the slim re-write (pt_tb2s_kernel, same results); chunks on a slab
     // interface need the peer loads/stores of pt_tb2_kernel<.,.,true>
     const bool slim = !k.mbox && ctx->opt_tb2_slim;
-    if (slim || dual) tb2s_set_offsets(k, cur, nxt, dpc, dpn, divV);
+    // round-2 candidate (off by default): the slim pipeline on the slab interfaces too
+    const bool slim_faces = k.mbox && ctx->opt_tb2_slim_faces;
+    if (slim || dual || slim_faces) tb2s_set_offsets(k, cur, nxt, dpc, dpn, divV);
     // Grids whose x-y extent has a compile-time instantiation (default variant only): the
     // reference scripts' nx = 255 and BASELINE.json's 511^2 / 1023x511 planes.
 #define TBS_ARGS <<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k)
@@ -231,7 +233,8 @@ int launch_tb2(ns3d_ctx* ctx, cudaStream_t st, const PtK& k_in, const double* cu
     } while (0)
 #define TB_LAUNCH(MODE)                                                                                        \
     do {                                                                                                       \
-        if (k.mbox) pt_tb2_kernel<MODE, 16, true><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);          \
+        if (slim_faces) pt_tb2sp_kernel<MODE, 16, 1><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);        \
+        else if (k.mbox) pt_tb2_kernel<MODE, 16, true><<<grd, blk, 0, st>>>(cur, nxt, dpc, dpn, divV, k);     \
         else if (dual) TBD_LAUNCH(MODE, 2);                                                                    \
         else if (slim && ty == 8) TBS_LAUNCH(MODE, 8);                                                         \
         else if (slim && ty == 32) TBS_LAUNCH(MODE, 32);                                                       \
@@ -566,7 +569,7 @@ int run_iterations(ns3d_ctx* ctx, PtK& k, double*& cur, double*& nxt, double*& d
     // every tuning option that selects a kernel or its launch shape is part of the key
     const int opts = ctx->opt_tb2 | (ctx->opt_tb2_slim << 1) | (ctx->opt_tb2_np << 2) | (ctx->opt_tb2_pf << 3) |
                      (ctx->opt_tb2_spec << 5) | (ctx->opt_tb2_dual << 6) | (ctx->opt_tb2_ty << 8) | (ctx->opt_tb2_pb << 16) |
-                     (ctx->opt_pt_bands << 20);
+                     (ctx->opt_pt_bands << 20) | (ctx->opt_tb2_slim_faces << 24);
     PtGraph* g = nullptr;
     for (PtGraph& c : cache->slot)
         if (c.exec && c.cur == cur && c.nxt == nxt && c.dP == dP && c.dPn == dPn && c.divV == divV && c.n == n &&

@@ -537,6 +537,22 @@ __device__ __forceinline__ void pt_update(const PtK& p, double L, double dq, dou
 // The mirror images of interior point (i,j) with new value u in plane k of PrN (bc_x!, bc_y!,
 // bc_x_Pr! / bc_xhydstatic! folded in), and -- when k_face >= 0 -- the whole set once more in the
 // z-face plane k_face (bc_z!).  Cold path: kept as a loop so that it costs little code.
+// One plane's worth of the same: `plane` is the base of the target x-y plane (this rank's, or a
+// neighbour's halo plane over peer memory), kk the plane index the x-face values are computed for.
+__device__ __forceinline__ void tb2s_images_into(const PtK& p, double* __restrict__ plane, int kk, int i, int j, double u,
+                                                 bool xl, bool xh, bool yl, bool yh)
+{
+    const double vlo = xface(p, false, kk, u), vhi = xface(p, true, kk, u);
+#pragma unroll 1
+    for (int r = 0; r < 3; ++r) {
+        if ((r == 1 && !yl) || (r == 2 && !yh)) continue;
+        double* row = plane + (ptrdiff_t)(r == 0 ? j : (r == 1 ? 0 : p.ny - 1)) * p.nx;
+        row[i] = u;
+        if (xl) row[0] = vlo;
+        if (xh) row[p.nx - 1] = vhi;
+    }
+}
+
 __device__ __forceinline__ void tb2s_images(const PtK& p, double* __restrict__ PrN, int i, int j, int k, int k_face,
                                             double u, bool xl, bool xh, bool yl, bool yh)
 {
@@ -565,6 +581,10 @@ struct Tb2sInv {
     int edge;      // owner next to an x/y face: mirror images to store
     int xfix;      // x-face column with a non-Neumann condition: stage-1 value is replaced
     int bx, by;    // tile origin (the slow paths re-derive i, j from it)
+    // P2P instantiation only: this CTA's chunk touches a slab interface; column offsets into the
+    // neighbours' planes (Pr layout / dPrdτ layout)
+    int lo_face, hi_face;
+    ptrdiff_t tcol, dcol;
 };
 
 // Keeps a per-thread value in a register: without it ptxas re-derives loop invariants from
@@ -632,7 +652,8 @@ struct Tb2sStride {
 };
 
 // PB: pairwise row barriers (row_barrier) instead of __syncthreads -- ROUND-2 CANDIDATE, unmeasured.
-template <int MODE, int TB_Y, int SLOT, int PF, bool NP, int NXC, int NYC, bool PB>
+// P2P: the chunk may touch a slab interface (see pt_tb2sp_kernel) -- ROUND-2 CANDIDATE, unmeasured.
+template <int MODE, int TB_Y, int SLOT, int PF, bool NP, int NXC, int NYC, bool PB, bool P2P = false>
 __device__ __forceinline__ void tb2s_step(const PtK& p, const Tb2sInv& v, const int s, const char*& c, const char*& d,
                                           double* __restrict__ sm, double& PM, double& PC, double& ZP, double& DQ,
                                           double& DVC, double& DV, double& DVN, double& QM, double& QC, double& QN,
@@ -660,8 +681,14 @@ __device__ __forceinline__ void tb2s_step(const PtK& p, const Tb2sInv& v, const 
     const double L1 = bracket<MODE>(p, PC, xm, xp, ym, yp, PM, ZP, DV);
     double D1N;
     pt_update<MODE>(p, L1, DQ, PC, D1N, QN);
-    PM = LD(a_zp2);               // PM and DQ are dead: reuse them for planes s+2 / s+1
-    DQ = LD(d + dplaneB);
+    if (P2P && v.hi_face && s == p.nz - 2) {
+        // plane nz and the dPrdτ of plane nz-1 live on the upper neighbour (its plane 2 / its first dPrdτ plane)
+        PM = __ldcv(p.peer_hi_cur + v.tcol);
+        DQ = __ldcv(p.peer_hi_dp + v.dcol);
+    } else {
+        PM = LD(a_zp2);           // PM and DQ are dead: reuse them for planes s+2 / s+1
+        DQ = LD(d + dplaneB);
+    }
     if (NP) {
         const char* cn = c + planeB;
         NB[0] = LD(cn - 8); NB[1] = LD(cn + 8); NB[2] = LD(cn - rowB); NB[3] = LD(cn + rowB);
@@ -686,10 +713,16 @@ __device__ __forceinline__ void tb2s_step(const PtK& p, const Tb2sInv& v, const 
         pt_update<MODE>(p, L2, D1C, QC, d2, u);
         *(double*)(const_cast<char*>(d) + p.oDP) = d2;
         *(double*)(const_cast<char*>(c) + p.oPr) = u;
-        if (v.edge | (k2 == 1)) {  // mirror images; bc_z! M:129 when plane 1 is next to a physical face
+        if (v.edge | (k2 == 1) | (P2P && k2 == p.nz - 2)) {  // mirror images; bc_z! M:129 when plane 1 is next to a physical face
             const int i = v.bx + (int)threadIdx.x, j = v.by + (int)threadIdx.y;
             tb2s_images(p, v.PrN, i, j, k2, (k2 == 1 && !p.zlo_halo) ? 0 : -1, u, i == 1, i == p.nx - 2, j == 1,
                         j == p.ny - 2);
+            if (P2P) {  // update_halo!(Pr): the planes a slab sends go straight into the neighbours' halo planes
+                if (k2 == 1 && p.zlo_halo)
+                    tb2s_images_into(p, p.peer_lo_plane, k2, i, j, u, i == 1, i == p.nx - 2, j == 1, j == p.ny - 2);
+                if (k2 == p.nz - 2 && p.zhi_halo)
+                    tb2s_images_into(p, p.peer_hi_plane, k2, i, j, u, i == 1, i == p.nx - 2, j == 1, j == p.ny - 2);
+            }
         }
     }
     if (s == 1 && !p.zlo_halo) QC = QN;  // bc_z!: q[0] is the image of q[1] (QC becomes QM of the next plane)
@@ -775,6 +808,98 @@ __global__ void __launch_bounds__(TB_X* TB_Y, 1024 / (TB_X * TB_Y)) pt_tb2s_kern
         tb2s_step<MODE, TB_Y, 2, PF, NP, NXC, NYC, PB>(p, v, s, c, d, sm, C, A, B, DQ, VC, VA, VB, QC, QA, QB, D1, NB);
         if (s == s1) break;
         ++s;
+    }
+}
+
+// pt_tb2sp_kernel: pt_tb2s_kernel for chunks on a slab interface -- what pt_tb2_kernel<.,.,true> does
+// (DESIGN.md 3.4), on the slim pipeline.  ROUND-2 CANDIDATE (option "tb2_slim_faces", off by default):
+// bit-exact in the single-process and multi-process emulations, not yet run on a device.  On an
+// interface the halo plane's first iteration is recomputed here (it is the neighbour's plane nz-2 / 1)
+// from the local halo plane plus one peer plane of the neighbour's current iterate and its dPrdτ
+// plane; the second-iteration planes 1 / nz-2 are also stored into the neighbour's halo plane;
+// hand-over through the mailbox exactly as in pt_tb2_kernel (wait at CTA start, signal at its end).
+template <int MODE, int TB_Y, int PF>
+__global__ void __launch_bounds__(TB_X* TB_Y, 1024 / (TB_X * TB_Y)) pt_tb2sp_kernel(const double* Pr, double* PrN, const double* dP,
+                                                                double* dPN, const double* divV, const PtK p)
+{
+    __shared__ double ring[3 * TB_Y * TB_X];
+    const int nx = p.nx, ny = p.ny, nz = p.nz;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.x * (TB_X - 2) + tx;
+    const int j = blockIdx.y * (TB_Y - 2) + ty;
+    const int ci = min(max(i, 1), nx - 2), cj = min(max(j, 1), ny - 2);
+    int bz = blockIdx.z;
+    if (!p.faces) {  // unsplit launch: the chunks next to a slab interface go first
+        const int nc = gridDim.z;
+        if (bz == 1) bz = nc - 1;
+        else if (bz >= 2) bz = p.reverse ? nc - bz : bz - 1;
+    }
+    // faces launch: only the two chunks of p.zchunk planes next to the z faces
+    const int kb = p.faces ? (bz == 0 ? 1 : nz - 1 - p.zchunk) : p.kbeg + bz * p.zchunk;
+    const int ke = p.faces ? kb + p.zchunk : min(kb + p.zchunk, p.kend);  // stage-2 planes [kb, ke)
+    const bool lo_face = p.zlo_halo && kb == 1;
+    const bool hi_face = p.zhi_halo && ke == nz - 1;
+    if (lo_face | hi_face) {
+        if (tx == 0 && ty == 0) {
+            if (lo_face) wait_neighbour(p.mbox, 0);
+            if (hi_face) wait_neighbour(p.mbox, 1);
+        }
+        __syncthreads();
+    }
+    const int s0 = lo_face ? 0 : max(kb - 1, 1);
+    const int s1 = hi_face ? nz - 1 : min(ke, nz - 2);  // stage-1 planes [s0, s1]
+    Tb2sInv v;
+    v.PrN = PrN;
+    v.bx = blockIdx.x * (TB_X - 2); v.by = blockIdx.y * (TB_Y - 2);
+    const bool owner = (ci == i) && (cj == j) && tx >= 1 && tx <= TB_X - 2 && ty >= 1 && ty <= TB_Y - 2;
+    v.kb_own = owner ? kb : 0x7fffffff;
+    v.top_own = (owner && !p.zhi_halo && ke == nz - 1) ? nz - 2 : -1;
+    v.edge = owner && ((i == 1) | (i == nx - 2) | (j == 1) | (j == ny - 2));
+    v.xfix = (i == 0 && p.xlo_kind != X_NEUMANN) ? 1 : ((i == nx - 1 && p.xhi_kind != X_NEUMANN) ? 2 : 0);
+    v.lo_face = lo_face; v.hi_face = hi_face;
+    v.tcol = (ptrdiff_t)cj * nx + ci;
+    v.dcol = (ptrdiff_t)(cj - 1) * (nx - 2) + (ci - 1);
+    NS3D_KEEP(v.kb_own); NS3D_KEEP(v.top_own); NS3D_KEEP(v.edge); NS3D_KEEP(v.xfix);
+    const char* c = (const char*)(Pr + (ptrdiff_t)s0 * nx * ny + v.tcol);
+    const char* d = (const char*)(dP + ((ptrdiff_t)s0 - 1) * (nx - 2) * (ny - 2) + v.dcol);
+    int tslot = ty * TB_X + tx;
+    NS3D_KEEP(tslot);
+    double* sm = ring + tslot;
+#define LD(ptr) (*(const double*)(ptr))
+    const long long rowB = p.rowB, planeB = p.planeB;
+    double A, DQ;
+    if (lo_face) {  // plane -1 and the dPrdτ of plane 0 live on the lower neighbour (its plane nz-3 / its last dPrdτ plane)
+        A = __ldcv(p.peer_lo_cur + v.tcol);
+        DQ = __ldcv(p.peer_lo_dp + v.dcol);
+    } else {
+        A = LD(c - planeB);
+        DQ = LD(d);
+    }
+    double B = LD(c), C = LD(c + planeB);
+    double VA = 0, VB = LD(c + p.oDV), VC = 0;
+    double QA = 0, QB = 0, QC = 0, D1 = 0;
+    double NB[4] = {LD(c - 8), LD(c + 8), LD(c - rowB), LD(c + rowB)};
+#undef LD
+    int s = s0;
+    while (true) {
+        tb2s_step<MODE, TB_Y, 0, PF, true, 0, 0, false, true>(p, v, s, c, d, sm, A, B, C, DQ, VA, VB, VC, QA, QB, QC, D1, NB);
+        if (s == s1) break;
+        ++s;
+        tb2s_step<MODE, TB_Y, 1, PF, true, 0, 0, false, true>(p, v, s, c, d, sm, B, C, A, DQ, VB, VC, VA, QB, QC, QA, D1, NB);
+        if (s == s1) break;
+        ++s;
+        tb2s_step<MODE, TB_Y, 2, PF, true, 0, 0, false, true>(p, v, s, c, d, sm, C, A, B, DQ, VC, VA, VB, QC, QA, QB, D1, NB);
+        if (s == s1) break;
+        ++s;
+    }
+    if (lo_face | hi_face) {
+        __threadfence_system();  // this thread's peer stores are performed before the flag can be seen
+        __syncthreads();
+        if (tx == 0 && ty == 0) {
+            const unsigned nface = gridDim.x * gridDim.y;
+            if (lo_face) signal_neighbour(p.mbox, 0, p.peer_lo_flag, nface);
+            if (hi_face) signal_neighbour(p.mbox, 1, p.peer_hi_flag, nface);
+        }
     }
 }
 

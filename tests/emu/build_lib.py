@@ -21,7 +21,7 @@ OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libns3d_emu.so")
 SOURCES = ["ns3d_core.cu", "ns3d_ops.cu", "ns3d_pt.cu", "ns3d_out.cu"]
 # kernels that synchronise (__syncthreads, named barriers, warp shuffles): one host thread per CUDA thread
-THREADED = ("pt_tb2_kernel", "pt_tb2s_kernel", "pt_tb2d_kernel", "pt_residual_kernel", "max_abs_kernel")
+THREADED = ("pt_tb2_kernel", "pt_tb2s_kernel", "pt_tb2sp_kernel", "pt_tb2d_kernel", "pt_residual_kernel", "max_abs_kernel")
 
 
 def _match_back_template(s: str, end: int) -> int:

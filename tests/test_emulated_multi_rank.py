@@ -61,6 +61,10 @@ def run_ranks(world, grid, nt, lz, how="step", options=None):
     (2, (14, 10, 9), 5, None, "pt_random", {"tb2": 0}),            # one-iteration kernel with peer stores
     (2, (14, 10, 9), 5, None, "pt_random", {"p2p_halo": 0}),       # NCCL send/recv halo exchange
     (4, (12, 9, 23), 6, 86 / 12, "pt_random", {"tb2_dual": 2}),    # four ranks, the dual-row candidate in the interior
+    # candidate: the slim pipeline on the slab interfaces too (pt_tb2sp_kernel)
+    (2, (16, 10, 26), 12, 50 / 16, "pt_random", {"tb2_slim_faces": 1}),   # split launches
+    (3, (14, 10, 9), 7, 23 / 14, "pt_random", {"tb2_slim_faces": 1}),     # unsplit launches, three ranks
+    (2, (16, 10, 26), 2, 50 / 16, "step", {"tb2_slim_faces": 1}),         # whole time steps
 ])
 def test_rank_processes_match_igg_emulation(world, grid, nt, lz, how, options):
     results = run_ranks(world, grid, nt, lz, how, options)
