@@ -195,6 +195,12 @@ NS3D_API int ns3d_allreduce_max(ns3d_ctx* ctx, double* h_inout);
  * the box [1,sx-1) x [1,sy-1) x [1,sz-1); a plane is a box one point thick.  Synchronises.    */
 NS3D_API int ns3d_box_d2h(ns3d_ctx* ctx, const double* A, int sx, int sy, int sz, int x0, int x1, int y0, int y1,
                           int z0, int z1, void* h_out, int f32);
+/* gather!(A_inn, A_v) (M:399-403, 481-485, 528-532) on z-slabs: every rank passes the box of its local array
+ * that belongs to the global array (same x-y extent on every rank; nplanes_all[r] = z1 - z0 of rank r,
+ * the same list on every rank); the boxes are packed on the devices, sent to rank 0 over NCCL and
+ * concatenated along z in h_out (rank 0 only; ignored elsewhere).  COLLECTIVE.  One rank: ns3d_box_d2h. */
+NS3D_API int ns3d_gather_box(ns3d_ctx* ctx, const double* A, int sx, int sy, int sz, int x0, int x1, int y0, int y1,
+                             int z0, int z1, const int* nplanes_all, void* h_out, int f32);
 
 /* ---- level 2: fused fast path ------------------------------------------------- */
 typedef struct ns3d_pt_params {

@@ -14,7 +14,7 @@ export Ctx, DevArray, zeros3, to_host, set!, set_mode!, PARITY, FAST, FASTEST,
        update_τ!, predict_V!, update_∇V!, update_dPrdτ!, update_Pr!, compute_res!, max_g_abs, correct_V!,
        bc_x!, bc_y!, bc_z!, bc_x_Vx!, bc_x_Pr!, bc_zV!, bc_xhydstatic!, set_bc_Vel_M!, set_bc_Vel_G!,
        set_bc_Pr_M!, set_bc_Pr_G!, advect!, set_cylinder_M!, set_cylinder_G!, update_halo!, copy!,
-       comm_init_mpi!, PtParams, pt_solve!, inner, inner32, plane_xy, plane_xz,
+       comm_init_mpi!, PtParams, pt_solve!, inner, inner32, plane_xy, plane_xz, gather_inner,
        Fields, StepParams, predictor!, corrector!, advect_swap!, step!
 
 const LIB = get(ENV, "NS3D_LIB", joinpath(@__DIR__, "..", "navierstokes3d_b200", "csrc", "libns3d.so"))
@@ -80,6 +80,16 @@ end
 inner(c::Ctx, a::DevArray) = box(c, a, 2:a.dims[1]-1, 2:a.dims[2]-1, 2:a.dims[3]-1, Float64)
 "`convert.(Float32, Array(A)[2:end-1,2:end-1,2:end-1])` (M:408): converted on the device"
 inner32(c::Ctx, a::DevArray) = box(c, a, 2:a.dims[1]-1, 2:a.dims[2]-1, 2:a.dims[3]-1, Float32)
+"`gather!(A_inn, A_v)` (M:399-403) on z-slabs: the global interior on rank 0 (`nothing` elsewhere).
+ `nplanes[r+1]` = interior planes rank r contributes (nz-2; for `Vz` nz-1 on the last rank only)."
+function gather_inner(c::Ctx, a::DevArray, me::Integer, nplanes::Vector{<:Integer}, ::Type{T}=Float64) where {T<:Union{Float64,Float32}}
+    counts = Cint.(nplanes)
+    h = me == 0 ? Array{T,3}(undef, a.dims[1] - 2, a.dims[2] - 2, sum(nplanes)) : nothing
+    check(c, ccall((:ns3d_gather_box, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Cint, Ptr{Cint}, Ptr{Cvoid}, Cint),
+                   c.h, a.p, a.dims..., 1, a.dims[1] - 1, 1, a.dims[2] - 1, 1, 1 + nplanes[me+1], counts,
+                   h === nothing ? C_NULL : pointer(h), T == Float32))
+    return h
+end
 "`A_v[:, :, k]` / `A_v[:, j, :]` of the interior (heat-map planes, M:422-431); k, j index the interior"
 plane_xy(c::Ctx, a::DevArray, k::Integer) = box(c, a, 2:a.dims[1]-1, 2:a.dims[2]-1, k+1:k+1, Float64)[:, :, 1]
 plane_xz(c::Ctx, a::DevArray, j::Integer) = box(c, a, 2:a.dims[1]-1, j+1:j+1, 2:a.dims[3]-1, Float64)[:, 1, :]

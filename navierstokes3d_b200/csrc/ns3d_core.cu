@@ -486,6 +486,28 @@ int ns3d_internal_p2p_map(ns3d_ctx* ctx, const void* local_base, void** peer_lo,
     return NS3D_OK;
 }
 
+// Gathers one block of bytes per rank on rank 0 (device memory on both sides): rank r sends `bytes`
+// bytes from d_send, rank 0 receives rank r's block at d_recv + offs[r] (its own block is copied).
+// COLLECTIVE over the communicator; `bytes_all` (length nranks) is meaningful on rank 0 only.
+int ns3d_internal_gather_bytes(ns3d_ctx* ctx, const void* d_send, size_t bytes, void* d_recv, const size_t* bytes_all)
+{
+    if (!ctx->nccl) return ns3d_fail(ctx, NS3D_ECOMM, "gather: no communicator attached");
+    ncclComm_t comm = (ncclComm_t)ctx->nccl;
+    if (ctx->rank != 0) {
+        if (bytes) NS3D_NCCL(ctx, g_nccl.Send(d_send, bytes, ncclUint8, 0, comm, ctx->stream));
+        return NS3D_OK;
+    }
+    if (bytes) NS3D_CUDA(ctx, cudaMemcpyAsync(d_recv, d_send, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    size_t off = bytes_all[0];
+    NS3D_NCCL(ctx, g_nccl.GroupStart());
+    for (int r = 1; r < ctx->nranks; ++r) {
+        if (bytes_all[r]) NS3D_NCCL(ctx, g_nccl.Recv((char*)d_recv + off, bytes_all[r], ncclUint8, r, comm, ctx->stream));
+        off += bytes_all[r];
+    }
+    NS3D_NCCL(ctx, g_nccl.GroupEnd());
+    return NS3D_OK;
+}
+
 extern "C" int ns3d_comm_rank(const ns3d_ctx* ctx) { return ctx ? ctx->rank : NS3D_EINVAL; }
 extern "C" int ns3d_comm_size(const ns3d_ctx* ctx) { return ctx ? ctx->nranks : NS3D_EINVAL; }
 

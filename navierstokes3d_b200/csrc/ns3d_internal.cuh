@@ -39,6 +39,8 @@ struct ns3d_ctx {
     size_t dp_shadow_count = 0;
     void* out_stage = nullptr;    // device staging of the output path (ns3d_box_d2h)
     size_t out_stage_bytes = 0;
+    void* gather_stage = nullptr;  // rank 0: where the ranks' boxes land (ns3d_gather_box)
+    size_t gather_stage_bytes = 0;
     unsigned long long* d_maxbits = nullptr;  // device accumulator of max |x| bit patterns
     unsigned long long* h_maxbits = nullptr;  // pinned host mirror
     // communicator (z-slabs, one rank per GPU)
@@ -141,6 +143,7 @@ __device__ __forceinline__ void block_max_to_global(unsigned long long v, unsign
 int ns3d_internal_p2p_map(ns3d_ctx* ctx, const void* local_base, void** peer_lo, void** peer_hi);
 void ns3d_internal_pt_free_graphs(ns3d_ctx* ctx);
 void ns3d_internal_out_free(ns3d_ctx* ctx);
+int ns3d_internal_gather_bytes(ns3d_ctx* ctx, const void* d_send, size_t bytes, void* d_recv, const size_t* bytes_all);
 int ns3d_internal_max_abs_async(ns3d_ctx* ctx, const double* A, size_t count);  // result -> ctx->d_maxbits
 int ns3d_internal_read_max(ns3d_ctx* ctx, double* h_out);                       // sync + allreduce
 int ns3d_internal_halo_z(ns3d_ctx* ctx, cudaStream_t s, double* const* fields, const int* sx,

@@ -282,15 +282,14 @@ def gather_interior(sim: Simulation, name: str, dtype=np.float64) -> np.ndarray 
     """
     s = sim.s
     world, rank = s.grid.nranks, s.grid.rank
-    a = sim.interior(name, dtype, drop_last_z=(world > 1 and name == "Vz" and rank < world - 1))
     if world == 1:
-        return a
-    import torch.distributed as dist
-    parts = [None] * world if rank == 0 else None
-    dist.gather_object(np.ascontiguousarray(a), parts, dst=0)
-    if rank != 0:
-        return None
-    return np.asfortranarray(np.concatenate(parts, axis=2))
+        return sim.interior(name, dtype)
+    # every rank packs its interior planes on its device; the blocks go to rank 0 over NCCL
+    # (ns3d_gather_box) and arrive concatenated along z
+    a = sim.f[name]
+    sx, sy, sz = a.shape
+    nplanes = [(sz - 2) - int(name == "Vz" and r < world - 1) for r in range(world)]
+    return sim.ctx.gather_box(a, (1, sx - 1), (1, sy - 1), (1, 1 + nplanes[rank]), nplanes, dtype)
 
 
 def save_mat(fname: str, sim: Simulation):

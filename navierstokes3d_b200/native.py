@@ -72,6 +72,7 @@ SIGNATURES = {
     "ns3d_launch_count": (C.c_longlong, [_P]),
     "ns3d_stream": (_P, [_P]),
     "ns3d_box_d2h": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I]),
+    "ns3d_gather_box": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, c_int_p, _P, _I]),
     "ns3d_zeros": (_I, [_P, _I, _I, _I, C.POINTER(_P)]),
     "ns3d_free": (_I, [_P, _P]),
     "ns3d_h2d": (_I, [_P, _P, _P, _Z]),
@@ -271,6 +272,21 @@ class Context:
         out = np.empty((max(x1 - x0, 0), max(y1 - y0, 0), max(z1 - z0, 0)), dtype=dtype, order="F")
         self._ck(self.lib.ns3d_box_d2h(self.h, src.ptr, sx, sy, sz, x0, x1, y0, y1, z0, z1, out.ctypes.data,
                                        int(dtype == np.dtype(np.float32))), "ns3d_box_d2h")
+        return out
+
+    def gather_box(self, src: DeviceArray, xr, yr, zr, nplanes_all, dtype=np.float64):
+        """``gather!`` of z-slabs (``ns3d_gather_box``): every rank passes its box, rank 0 gets the boxes
+        concatenated along z (other ranks get None).  ``nplanes_all[r]`` = planes rank r contributes."""
+        sx, sy, sz = src.shape
+        dtype = np.dtype(dtype)
+        if dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise ValueError("gather_box: dtype must be float64 or float32")
+        rank = self.lib.ns3d_comm_rank(self.h)
+        counts = (C.c_int * len(nplanes_all))(*nplanes_all)
+        out = np.empty((xr[1] - xr[0], yr[1] - yr[0], int(sum(nplanes_all))), dtype=dtype, order="F") if rank == 0 else None
+        self._ck(self.lib.ns3d_gather_box(self.h, src.ptr, sx, sy, sz, xr[0], xr[1], yr[0], yr[1], zr[0], zr[1], counts,
+                                          out.ctypes.data if out is not None else None,
+                                          int(dtype == np.dtype(np.float32))), "ns3d_gather_box")
         return out
 
     def d2h_raw(self, host_ptr: int, src_ptr: int, count: int):

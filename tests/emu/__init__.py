@@ -247,6 +247,17 @@ def multi_rank_main(rank, world, grid, nt, lz, how, options, uid_pipes, queue):
                     problems.append(f"{name}: {int(bad.sum())} values differ (planes {sorted(set(np.argwhere(bad)[:, 2].tolist()))})")
             if sim.iters != truth.iters:
                 problems.append(f"iterations {sim.iters} != {truth.iters}")
+            if how != "pt_random":   # gather!(A_inn, A_v): the global interior on rank 0, over the (fake) NCCL
+                from navierstokes3d_b200.driver import gather_interior
+                for name in ("Pr", "Vz", "C"):
+                    for dtype in (np.float64, np.float32):
+                        g = gather_interior(sim, name, dtype)
+                        if rank == 0:
+                            want = truth.assemble(name)[1:-1, 1:-1, 1:-1].astype(dtype)
+                            if g is None or g.shape != want.shape or not np.array_equal(g, want):
+                                problems.append(f"gather {name} {np.dtype(dtype).name}")
+                        elif g is not None:
+                            problems.append(f"gather {name}: rank {rank} got an array")
             p2p = bool(ctx.lib.ns3d_comm_size(ctx.h) == world)
             queue.put((rank, problems, sim.iters, int(ctx.launch_count), p2p))
             ctx.close()
