@@ -102,9 +102,13 @@ const USE_FUSED_PT = true     # false: the reference's loop, call site by call s
             end
         end
     end
-    # return value (M:528-535): interior arrays, extracted on the device (ns3d_box_d2h); gathering
-    # over ranks is left to MPI.Gatherv here
-    return inner(ctx, C), inner(ctx, Pr), inner(ctx, Vx), inner(ctx, Vy), inner(ctx, Vz)
+    # return value (M:528-535): gather!(A_inn, A_v) for every field -- the interior planes are packed on
+    # each device and travel to rank 0 over NCCL (ns3d_gather_box); Vz, staggered along the split
+    # dimension, takes its extra plane from the last rank only
+    np_c = fill(nz - 2, dims[3])
+    np_z = [nz - 2 + (r == dims[3] - 1 ? 1 : 0) for r in 0:dims[3]-1]
+    return gather_inner(ctx, C, me, np_c), gather_inner(ctx, Pr, me, np_c), gather_inner(ctx, Vx, me, np_c),
+           gather_inner(ctx, Vy, me, np_c), gather_inner(ctx, Vz, me, np_z)
 end
 
 if abspath(PROGRAM_FILE) == @__FILE__
