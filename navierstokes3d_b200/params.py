@@ -149,36 +149,55 @@ class Setup:
         return s
 
 
-def _common():
-    lx, rho, vin, mu = 1.0, 1000.0, 1.0, 0.001          # M:290-293 / G:15-18
-    psc = rho * vin * vin                               # M:296
-    beta = 0 * math.pi / 6                              # M:309
-    return lx, rho, vin, mu, psc, math.sin(beta), math.cos(beta)
+@dataclass(frozen=True)
+class Physics:
+    """The literals the reference's run functions hard-code (M:290-335 / G:15-56), as a config
+    (SURVEY.md 8f row 3).  ``None`` = the script's value, which differs between the two scripts for
+    ``ox_lx`` (M: -0.4, G: -0.3) and gravity (M: Fr = Inf, i.e. g = 0; G: g = 9.81)."""
+    rho: float = 1000.0                  # density                       M:291
+    vin: float = 1.0                     # inflow velocity               M:292
+    mu: float = 0.001                    # dynamic viscosity             M:293  (Re = rho*vin*lx/mu)
+    a_lx: float = 0.05                   # obstacle half-axes / lx       M:304-305
+    b_lx: float = 0.05
+    ox_lx: float | None = None           # obstacle centre / lx          M:307-308 / G:29-30
+    oy_lx: float = 0.0
+    beta: float = 0 * math.pi / 6        # obstacle rotation             M:309
+    g: float | None = None               # gravity                       M:316 / G:38
+    cfl_tau: float = 1.0 / math.sqrt(3.1)   # pseudo-time step           M:333
+    cfl_visc: float = 1 / 4.1            # viscous time-step limit       M:334
+    cfl_adv: float = 1.0                 # advective time-step limit     M:335
 
 
-def _time_steps(dx, dy, dz, rho, mu, vin):
+def _common(ph: Physics):
+    lx = 1.0                                            # M:290 / G:15
+    psc = ph.rho * ph.vin * ph.vin                      # M:296
+    return lx, ph.rho, ph.vin, ph.mu, psc, math.sin(ph.beta), math.cos(ph.beta)
+
+
+def _time_steps(dx, dy, dz, ph: Physics):
     dmax = max(dx, dy, dz)
-    cfl_tau, cfl_visc, cfl_adv = 1.0 / math.sqrt(3.1), 1 / 4.1, 1.0       # M:333-335
-    dt = min(cfl_visc * (dmax * dmax) * rho / mu, cfl_adv * dmax / vin)   # M:339
-    return dt, cfl_tau * dmax                                             # M:341
+    dt = min(ph.cfl_visc * (dmax * dmax) * ph.rho / ph.mu, ph.cfl_adv * dmax / ph.vin)   # M:339
+    return dt, ph.cfl_tau * dmax                                                         # M:341
 
 
 def setup_multi_gpu(nx: int = 255, *, ny: int | None = None, nz: int | None = None, rank: int = 0,
                     nranks: int = 1, eps_it: float = 1e-3, niter: int | None = None, nchk: int | None = None,
-                    ly: float | None = None, lz: float | None = None) -> Setup:
+                    ly: float | None = None, lz: float | None = None, physics: Physics | None = None) -> Setup:
     """Scalars of ``run_navierstokes3D`` (M:290-341) on one rank of a (1,1,nranks) process grid.
 
     ``ny, nz, ly, lz, niter, nchk, eps_it`` default to the script's rules; the overrides exist for
-    the benchmark configurations that name explicit sizes (511^3, 1023x511x511) or fixed work.
+    the benchmark configurations that name explicit sizes (511^3, 1023x511x511) or fixed work;
+    ``physics`` replaces the literals of M:290-335 (density, viscosity, obstacle, CFL numbers).
     """
-    lx, rho, vin, mu, psc, sinb, cosb = _common()
+    ph = physics or Physics()
+    lx, rho, vin, mu, psc, sinb, cosb = _common(ph)
     ly_lx = lz_lx = 0.6
     ly = ly_lx * lx if ly is None else ly
     lz = lz_lx * lx if lz is None else lz
-    ox, oy = -0.4 * lx, 0.0 * lx                        # M:307-308,314-315
-    g = 1 / (math.inf * math.inf) * (vin * vin) / lx    # Fr = Inf -> 0.0  (M:301,316)
-    a2 = (0.05 * lx) * (0.05 * lx)                      # M:317
-    b2 = (0.05 * lx) * (0.05 * lx)
+    ox, oy = (-0.4 if ph.ox_lx is None else ph.ox_lx) * lx, ph.oy_lx * lx   # M:307-308,314-315
+    g = 1 / (math.inf * math.inf) * (vin * vin) / lx if ph.g is None else ph.g   # Fr = Inf -> 0.0  (M:301,316)
+    a2 = (ph.a_lx * lx) * (ph.a_lx * lx)                # M:317
+    b2 = (ph.b_lx * lx) * (ph.b_lx * lx)
     if ny is None:
         ny = math.ceil(nx * ly_lx)                      # M:323
     if nz is None:
@@ -189,7 +208,7 @@ def setup_multi_gpu(nx: int = 255, *, ny: int | None = None, nz: int | None = No
     if nchk is None:
         nchk = grid.ny_g - 1                                # M:329
     dx, dy, dz = lx / grid.nx_g, ly / grid.ny_g, lz / grid.nz_g   # M:338
-    dt, dtau = _time_steps(dx, dy, dz, rho, mu, vin)
+    dt, dtau = _time_steps(dx, dy, dz, ph)
     damp = 2 / nx                                       # M:340: the LOCAL nx
     xco_g = grid.x_g(1, dx, nx, 0) - (lx - dx) / 2      # M:363
     yco_g = grid.x_g(1, dy, ny, 1) - (ly - dy) / 2      # M:364
@@ -204,14 +223,15 @@ def setup_multi_gpu(nx: int = 255, *, ny: int | None = None, nz: int | None = No
 
 
 def setup_gpu(nx: int = 255, *, ny: int | None = None, nz: int | None = None, eps_it: float = 1e-3,
-              niter: int | None = None, nchk: int | None = None) -> Setup:
+              niter: int | None = None, nchk: int | None = None, physics: Physics | None = None) -> Setup:
     """Scalars of ``runme`` (G:15-61); the script hard-codes nx = 255 (G:44)."""
-    lx, rho, vin, mu, psc, sinb, cosb = _common()
+    ph = physics or Physics()
+    lx, rho, vin, mu, psc, sinb, cosb = _common(ph)
     ly, lz = 0.6 * lx, 0.6 * lx                         # G:34-35
-    ox, oy = -0.3 * lx, 0.0 * lx                        # G:29-30,36-37
-    g = 9.81                                            # G:38
-    a2 = (0.05 * lx) * (0.05 * lx)
-    b2 = (0.05 * lx) * (0.05 * lx)
+    ox, oy = (-0.3 if ph.ox_lx is None else ph.ox_lx) * lx, ph.oy_lx * lx   # G:29-30,36-37
+    g = 9.81 if ph.g is None else ph.g                  # G:38
+    a2 = (ph.a_lx * lx) * (ph.a_lx * lx)
+    b2 = (ph.b_lx * lx) * (ph.b_lx * lx)
     if ny is None:
         ny = math.ceil(nx * 0.6)                        # G:45
     if nz is None:
@@ -221,7 +241,7 @@ def setup_gpu(nx: int = 255, *, ny: int | None = None, nz: int | None = None, ep
     if nchk is None:
         nchk = ny - 1                                   # G:49
     dx, dy, dz = lx / nx, ly / ny, lz / nz              # G:58
-    dt, dtau = _time_steps(dx, dy, dz, rho, mu, vin)    # G:59,61
+    dt, dtau = _time_steps(dx, dy, dz, ph)              # G:59,61
     return Setup(variant=native.VARIANT_G, grid=SlabGrid(nx, ny, nz), lx=lx, ly=ly, lz=lz, dx=dx, dy=dy, dz=dz,
                  dt=dt, dtau=dtau, damp=2 / nx, rho=rho, mu=mu, g=g, vin=vin, psc=psc, a2=a2, b2=b2, ox=ox,
                  oy=oy, sinb=sinb, cosb=cosb, xco_g=0.0, yco_g=0.0, zco_g=0.0, eps_it=eps_it, niter=niter,

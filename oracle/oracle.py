@@ -175,27 +175,31 @@ class Params:
 
 def params_M(nx: int = 255, ny: int | None = None, nz: int | None = None, dims=(1, 1, 1),
              coords=(0, 0, 0), eps_it: float = 1e-3, niter: int | None = None,
-             nchk: int | None = None, ly: float | None = None, lz: float | None = None) -> Params:
+             nchk: int | None = None, ly: float | None = None, lz: float | None = None, **lit) -> Params:
     """Literal restatement of M:290-341 + M:363-367 for one rank of an IGG grid.
 
     ``ny``/``nz``/``ly``/``lz``/``niter``/``nchk`` overrides exist only for the BASELINE configs
-    that give explicit dims (511^3, 1023x511x511); left as None they follow the script.
+    that give explicit dims (511^3, 1023x511x511); left as None they follow the script.  ``lit``
+    replaces literals of the script (rho, vin, mu, a_lx, b_lx, ox_lx, oy_lx, beta, g, cfl_tau,
+    cfl_visc, cfl_adv) -- what one edits in the source to run another case.
     """
+    unknown = set(lit) - {"rho", "vin", "mu", "a_lx", "b_lx", "ox_lx", "oy_lx", "beta", "g", "cfl_tau", "cfl_visc", "cfl_adv"}
+    assert not unknown, unknown
     lx = 1.0
-    rho = 1000.0
-    vin = 1.0
-    mu = 0.001
+    rho = lit.get("rho", 1000.0)
+    vin = lit.get("vin", 1.0)
+    mu = lit.get("mu", 0.001)
     psc = rho * vin * vin                      # M:296  ρ*vin^2
     Fr = math.inf                              # M:301
     ly_lx, lz_lx = 0.6, 0.6                    # M:302-303
-    a_lx = b_lx = 0.05                         # M:304-305
-    ox_lx, oy_lx = -0.4, 0.0                   # M:307-308
-    beta = 0 * math.pi / 6                     # M:309
+    a_lx, b_lx = lit.get("a_lx", 0.05), lit.get("b_lx", 0.05)   # M:304-305
+    ox_lx, oy_lx = lit.get("ox_lx", -0.4), lit.get("oy_lx", 0.0)   # M:307-308
+    beta = lit.get("beta", 0 * math.pi / 6)    # M:309
     ly_ = ly_lx * lx if ly is None else ly     # M:312
     lz_ = lz_lx * lx if lz is None else lz     # M:313
     ox = ox_lx * lx
     oy = oy_lx * lx
-    g = 1 / (Fr * Fr) * (vin * vin) / lx       # M:316 -> 0.0
+    g = lit["g"] if "g" in lit else 1 / (Fr * Fr) * (vin * vin) / lx   # M:316 -> 0.0
     a2 = (a_lx * lx) * (a_lx * lx)             # M:317
     b2 = (b_lx * lx) * (b_lx * lx)
     sinb, cosb = math.sin(beta), math.cos(beta)
@@ -208,9 +212,9 @@ def params_M(nx: int = 255, ny: int | None = None, nz: int | None = None, dims=(
         niter = 50 * max(nxg, nyg, nzg)        # M:328
     if nchk is None:
         nchk = 1 * (nyg - 1)                   # M:329
-    CFLtau = 1.0 / math.sqrt(3.1)              # M:333
-    CFL_visc = 1 / 4.1                         # M:334
-    CFL_adv = 1.0                              # M:335
+    CFLtau = lit.get("cfl_tau", 1.0 / math.sqrt(3.1))   # M:333
+    CFL_visc = lit.get("cfl_visc", 1 / 4.1)    # M:334
+    CFL_adv = lit.get("cfl_adv", 1.0)          # M:335
     dx, dy, dz = lx / nxg, ly_ / nyg, lz_ / nzg                    # M:338
     dmax = max(dx, dy, dz)
     dt = min(CFL_visc * (dmax * dmax) * rho / mu, CFL_adv * dmax / vin)   # M:339
@@ -230,22 +234,24 @@ def params_M(nx: int = 255, ny: int | None = None, nz: int | None = None, dims=(
 
 
 def params_G(nx: int = 255, ny: int | None = None, nz: int | None = None, eps_it: float = 1e-3,
-             niter: int | None = None, nchk: int | None = None) -> Params:
-    """Literal restatement of G:15-61 (nx is hard-coded to 255 in the script, G:44)."""
+             niter: int | None = None, nchk: int | None = None, **lit) -> Params:
+    """Literal restatement of G:15-61 (nx is hard-coded to 255 in the script, G:44); ``lit`` as in params_M."""
+    unknown = set(lit) - {"rho", "vin", "mu", "a_lx", "b_lx", "ox_lx", "oy_lx", "beta", "g", "cfl_tau", "cfl_visc", "cfl_adv"}
+    assert not unknown, unknown
     lx = 1.0
-    rho = 1000.0
-    vin = 1.0
-    mu = 0.001
+    rho = lit.get("rho", 1000.0)
+    vin = lit.get("vin", 1.0)
+    mu = lit.get("mu", 0.001)
     psc = rho * vin * vin
     ly_lx, lz_lx = 0.6, 0.6
-    a_lx = b_lx = 0.05
-    ox_lx, oy_lx = -0.3, 0.0                   # G:29-30
-    beta = 0 * math.pi / 6
+    a_lx, b_lx = lit.get("a_lx", 0.05), lit.get("b_lx", 0.05)
+    ox_lx, oy_lx = lit.get("ox_lx", -0.3), lit.get("oy_lx", 0.0)   # G:29-30
+    beta = lit.get("beta", 0 * math.pi / 6)
     ly = ly_lx * lx
     lz = lz_lx * lx
     ox = ox_lx * lx
     oy = oy_lx * lx
-    g = 9.81                                   # G:38
+    g = lit.get("g", 9.81)                     # G:38
     a2 = (a_lx * lx) * (a_lx * lx)
     b2 = (b_lx * lx) * (b_lx * lx)
     sinb, cosb = math.sin(beta), math.cos(beta)
@@ -257,9 +263,9 @@ def params_G(nx: int = 255, ny: int | None = None, nz: int | None = None, eps_it
         niter = 50 * max(ny, nz)               # G:48
     if nchk is None:
         nchk = 1 * (ny - 1)                    # G:49
-    CFLtau = 1.0 / math.sqrt(3.1)
-    CFL_visc = 1 / 4.1
-    CFL_adv = 1.0
+    CFLtau = lit.get("cfl_tau", 1.0 / math.sqrt(3.1))
+    CFL_visc = lit.get("cfl_visc", 1 / 4.1)
+    CFL_adv = lit.get("cfl_adv", 1.0)
     dx, dy, dz = lx / nx, ly / ny, lz / nz     # G:58
     dmax = max(dx, dy, dz)
     dt = min(CFL_visc * (dmax * dmax) * rho / mu, CFL_adv * dmax / vin)   # G:59

@@ -106,3 +106,27 @@ def test_driver_returns_the_reference_test_call(O, ns):
     f, _, _ = O.run(O.params_M(63), 1)
     for got, name in ((C, "C"), (Pr, "Pr"), (Vx, "Vx"), (Vy, "Vy"), (Vz, "Vz")):
         assert np.array_equal(got, O.interior(f[name])), name
+
+
+@pytest.mark.parametrize("variant,nx,nt", [("M", 20, 3), ("G", 16, 1)])
+def test_other_physics_than_the_scripts_literals(O, ns, variant, nx, nt):
+    """`Physics` replaces the literals of M:290-335 / G:15-56: a rotated elliptic obstacle somewhere else,
+    another Reynolds number, inflow speed, gravity and CFL numbers -- kernel arguments the scripts'
+    defaults never exercise (sin(beta) != 0, a != b).  Same setup on the oracle: bit-exact."""
+    lit = dict(rho=900.0, vin=0.8, mu=2e-3, a_lx=0.11, b_lx=0.06, ox_lx=-0.15, oy_lx=0.04, beta=np.pi / 6,
+               g=(0.3 if variant == "M" else 9.0), cfl_tau=0.5, cfl_visc=0.2, cfl_adv=0.9)
+    p = O.params_M(nx, **lit) if variant == "M" else O.params_G(nx, **lit)
+    f, iters_o, errs_o = O.run(p, nt)
+    s = (ns.setup_multi_gpu if variant == "M" else ns.setup_gpu)(nx, physics=ns.Physics(**lit))
+    for k in ("dt", "dtau", "damp", "a2", "b2", "ox", "oy", "sinb", "cosb", "g", "rho", "mu", "vin", "psc"):
+        assert getattr(s, k) == getattr(p, k), k
+    sim = ns.Simulation(s, ns.Context(0, ns.PARITY))
+    for _ in range(nt):
+        sim.step()
+    assert (f["C"] > 0.5).sum() > 8                  # the obstacle is there (script G masks inside the loop only)
+    assert sim.iters == iters_o
+    assert np.array_equal(np.concatenate(sim.err_hist), np.concatenate(errs_o), equal_nan=True)
+    for name in ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C", "divV"):
+        assert np.array_equal(sim.host(name), f[name]), name
+    assert all(np.isfinite(f[k]).all() for k in ("Pr", "Vx", "C"))
+    sim.ctx.close()
