@@ -214,6 +214,152 @@ def pt_only(args, ns, ctx, s, stream, rank, world, barrier):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+TOL = 1e-10   # north_star: "fields within a stated FP64 relative tolerance (e.g. 1e-10 after N steps)"; N = --steps
+
+
+def kernel_key(workload: str, mode: str, opts) -> str:
+    """Key of profiles/traffic.json: the ncu DRAM-traffic figure is only valid for the kernel source it
+    was captured on, so the key carries a hash of the device code and every tuning option."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in ("ns3d_pt_kernels.cuh", "ns3d_pt.cu"):
+        with open(os.path.join(ROOT, "navierstokes3d_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return f"{workload}:{mode}:{','.join(sorted(opts))}:{h.hexdigest()[:12]}"
+
+
+def bind_numa(local: int) -> str:
+    """Pin this rank to the CPUs next to its GPU (NVML affinity) BEFORE any pinned host buffer exists, so
+    that first-touch places the e2e staging buffers on the GPU's NUMA node (round 1: all 8 ranks pinned on
+    node 0 -> host copies 8.5 ms/step at N=1 but 35 ms/step at N=8)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else cpus
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus near gpu{local}"
+    except Exception as exc:  # noqa: BLE001
+        return f"not bound ({type(exc).__name__})"
+    return "not bound"
+
+
+class Rig:
+    """rank / world / barrier / reductions shared by every leg of the GPU arm."""
+
+    def __init__(self, args):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}")
+        self.numa = bind_numa(self.local)
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, vals, op: str):
+        """element-wise max / min / sum over ranks of a list of floats"""
+        if not self.dist:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op={"max": self.dist.ReduceOp.MAX, "min": self.dist.ReduceOp.MIN,
+                                    "sum": self.dist.ReduceOp.SUM}[op])
+        return [float(v) for v in t]
+
+    def event(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+
+def make_sim(ns, rig, args, workload, variant, mode, fixed_iters=0):
+    from navierstokes3d_b200.driver import attach_communicator
+    _, nx, ny, nz = WORKLOADS[workload]
+    kw = {}
+    if fixed_iters:
+        kw = dict(eps_it=0.0, niter=fixed_iters, nchk=max(fixed_iters // 2, 1))
+    if variant == "G":
+        s = ns.setup_gpu(nx, ny=ny, nz=nz, **kw)
+    else:
+        # weak scaling (SURVEY.md 8d, config E): the domain grows in z with the number of slabs so
+        # that dz stays equal to dx and every GPU does the same work; the cylinder is z-invariant.
+        probe = ns.setup_multi_gpu(nx, ny=ny, nz=nz, rank=rig.rank, nranks=rig.world, **kw)
+        if rig.world > 1 or (ny is not None):
+            kw = dict(kw, ly=probe.ny * probe.dx, lz=probe.grid.nz_g * probe.dx)
+        s = ns.setup_multi_gpu(nx, ny=ny, nz=nz, rank=rig.rank, nranks=rig.world, **kw)
+    ctx = ns.Context(rig.local, getattr(ns, mode))
+    attach_communicator(ctx, rig.rank, rig.world)
+    for o in args.opt:
+        name, val = o.split("=")
+        ctx.set_option(name, int(val))
+    sim = ns.Simulation(s, ctx, zchunk=args.zchunk)
+    stream = rig.torch.cuda.ExternalStream(ctx.stream, device=rig.local)
+    return s, ctx, sim, stream
+
+
+def timed_steps(rig, sim, stream, steps):
+    """exactly `steps` time steps between CUDA events on the library's stream, barrier + sync on both sides;
+    returns (seconds = max over ranks of max(device, wall), bytes summed over ranks, iters, checks) of THIS rank's run"""
+    s = sim.s
+    n_cells = s.nx * s.ny * s.nz
+    rig.barrier()
+    ev0, ev1 = rig.event(), rig.event()
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    iters, checks = [], []
+    for _ in range(steps):
+        it, hist = sim.step()
+        iters.append(it)
+        checks.append(len(hist))
+    ev1.record(stream)
+    rig.barrier()
+    wall = time.perf_counter() - t0
+    dev_s = ev0.elapsed_time(ev1) / 1e3
+    bytes_rank = sum(a_eff_bytes(n_cells, i, c) for i, c in zip(iters, checks))
+    t_all = rig.reduce([max(dev_s, wall)], "max")[0]
+    bytes_all = rig.reduce([bytes_rank], "sum")[0]
+    return t_all, bytes_all, iters, checks
+
+
+STATE = ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C")
+
+
+def field_diffs(a: dict, ref: dict) -> dict:
+    """max |a - ref| per field over the field's scale; velocities share ONE scale (SURVEY.md "Hard parts":
+    Vz is rounding noise in variant M, so a per-component relative error is meaningless)."""
+    vscale = max(float(np.abs(ref[v]).max()) for v in ("Vx", "Vy", "Vz"))
+    return {k: float(np.abs(a[k] - ref[k]).max() / (vscale if k[0] == "V" else max(float(np.abs(ref[k]).max()), 1e-300)))
+            for k in a}
+
+
+def extra_workload(ns, rig, args, workload, variant, mode, steps, warmup, fixed_iters):
+    """one more configuration measured in the same run (device-resident T_eff only)"""
+    s, ctx, sim, stream = make_sim(ns, rig, args, workload, variant, mode, fixed_iters)
+    for _ in range(warmup):
+        sim.step()
+    t_all, bytes_all, iters, checks = timed_steps(rig, sim, stream, steps)
+    out = {"workload": workload_name(workload, variant, s), "decomposition": f"z-slabs x{rig.world}", "mode": mode,
+           "value": bytes_all / t_all / 1e9, "unit": "GB/s", "steps": steps, "warmup": warmup,
+           "ms_per_step": t_all / steps * 1e3, "time_steps_per_s": steps / t_all,
+           "t_eff_per_gpu": bytes_all / t_all / 1e9 / rig.world,
+           "us_per_pt_iteration_whole_step": t_all / max(sum(iters), 1) * 1e6,
+           "pt_iters_per_step": iters, "residual_checks_per_step": checks}
+    ctx.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -221,12 +367,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="B", choices=sorted(WORKLOADS))
-    ap.add_argument("--mode", default="FASTEST", choices=["PARITY", "FAST", "FASTEST"])
+    ap.add_argument("--mode", default="FAST", choices=["PARITY", "FAST", "FASTEST"],
+                    help="arithmetic of the fused PT loop: FAST (default) is bit-identical to PARITY = the CPU oracle; "
+                         "FASTEST trades that for FMA chains under the 1e-10 tolerance contract")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library tuning option name=value (ns3d_set_option)")
     ap.add_argument("--zchunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra legs of the default run (other arithmetic modes, variant M at N=1, config E)")
     ap.add_argument("--sample-seconds", type=float, default=8.0,
                     help="--impl reference: CPU seconds of the bounded sample that makes one step")
     ap.add_argument("--pt-only", type=int, default=0,
@@ -238,49 +388,19 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    import torch
-
     import navierstokes3d_b200 as ns
-    from navierstokes3d_b200.driver import attach_communicator
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rig = Rig(args)
+    rank, world, local = rig.rank, rig.world, rig.local
+    torch = rig.torch
+    barrier = rig.barrier
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    variant, nx, ny, nz = WORKLOADS[args.workload]
+    variant = WORKLOADS[args.workload][0]
     if world > 1:
         variant = "M"   # the G script is single-GPU; z-slabs follow the multi-GPU script
-    kw = {}
-    if args.fixed_iters:
-        kw = dict(eps_it=0.0, niter=args.fixed_iters, nchk=max(args.fixed_iters // 2, 1))
-    if variant == "G":
-        s = ns.setup_gpu(nx, ny=ny, nz=nz, **kw)
-    else:
-        # weak scaling: the domain grows in z with the number of slabs so
-        # that dz stays equal to dx and every GPU does the same work; the cylinder is z-invariant.
-        probe = ns.setup_multi_gpu(nx, ny=ny, nz=nz, rank=rank, nranks=world, **kw)
-        if world > 1 or (ny is not None):
-            kw = dict(kw, ly=probe.ny * probe.dx, lz=probe.grid.nz_g * probe.dx)
-        s = ns.setup_multi_gpu(nx, ny=ny, nz=nz, rank=rank, nranks=world, **kw)
-    ctx = ns.Context(local, getattr(ns, args.mode))
-    attach_communicator(ctx, rank, world)
-    for o in args.opt:
-        name, val = o.split("=")
-        ctx.set_option(name, int(val))
-    sim = ns.Simulation(s, ctx, zchunk=args.zchunk)
+    s, ctx, sim, stream = make_sim(ns, rig, args, args.workload, variant, args.mode, args.fixed_iters)
+    _, nx, ny, nz = WORKLOADS[args.workload]
     n_cells = s.nx * s.ny * s.nz
-    stream = torch.cuda.ExternalStream(ctx.stream, device=local)
 
     if args.pt_only:
         return pt_only(args, ns, ctx, s, stream, rank, world, barrier)
@@ -288,50 +408,35 @@ def main():
     # ---- device-resident timing: W warm-up steps, then exactly K steps -------------------------
     for _ in range(args.warmup):
         sim.step()
-    state_names = ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C")
-    snapshot = {k: sim.host(k) for k in state_names}   # for the e2e leg: same K steps again
+    snapshot = {k: sim.host(k) for k in STATE}   # for the e2e and parity legs: the same K steps again
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = ctx.launch_count
-    ev0.record(stream)
-    t0 = time.perf_counter()
-    iters, checks = [], []
-    for _ in range(args.steps):
-        it, hist = sim.step()
-        iters.append(it)
-        checks.append(len(hist))
-    ev1.record(stream)
-    barrier()
-    wall = time.perf_counter() - t0
+    t_all, bytes_all, iters, checks = timed_steps(rig, sim, stream, args.steps)
     clocks = sampler.stop()
     launches = ctx.launch_count - l0
-    dev_s = ev0.elapsed_time(ev1) / 1e3
-    bytes_rank = sum(a_eff_bytes(n_cells, i, c) for i, c in zip(iters, checks))
     final = {k: sim.host(k) for k in ("Pr", "Vx", "Vy", "Vz", "C")} if not args.no_parity_check else None
 
     # ---- the dominant kernel, live: nchk fused PT iterations between events ----------------------
-    n_probe = max(s.nchk, 50) & ~1   # even: the ping-pong buffers end where they started (graph cache hit)
     pt = s.pt_params(args.zchunk)
+    per_launch = ctx.pt_iters_per_launch(pt)
+    n_probe = max(s.nchk, 48)
+    n_probe -= n_probe % (2 * per_launch)   # the ping-pong buffers end where they started (graph cache hit)
     ctx.pt_iterate(sim.f["Pr"], sim.f["dPrdtau"], sim.f["divV"], pt, n_probe)   # untimed: builds this chunk's CUDA graph
     ctx.sync()
     barrier()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0, k1 = rig.event(), rig.event()
     k0.record(stream)
     ctx.pt_iterate(sim.f["Pr"], sim.f["dPrdtau"], sim.f["divV"], pt, n_probe)
     k1.record(stream)
     ctx.sync()
-    t_launch = k0.elapsed_time(k1) / 1e3 / n_probe
+    t_launch = k0.elapsed_time(k1) / 1e3 / n_probe * per_launch
     peak, peak_src = hbm_peak()
-    tb2_on = "tb2=0" not in args.opt     # default path: pt_tb2_kernel, two PT iterations per launch
-    per_launch = 2 if tb2_on else 1
-    t_launch *= per_launch
     achieved = 40.0 * per_launch * n_cells / t_launch / 1e9
-    traffic = None
+    traffic, tkey = None, kernel_key(args.workload, args.mode, args.opt)
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get(f"{args.workload}:{args.mode}" + (":tb2" if tb2_on else ""))
+            traffic = json.load(fh).get(tkey)
     except Exception:  # noqa: BLE001
         pass
 
@@ -341,7 +446,7 @@ def main():
         pinned = {k: torch.from_numpy(np.ascontiguousarray(v.ravel(order="F"))).pin_memory() for k, v in snapshot.items()}
         h2d_b = d2h_b = sum(t.numel() * 8 for t in pinned.values())
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = rig.event(), rig.event()
         e0.record(stream)
         tw = time.perf_counter()
         e_iters, e_checks = [], []
@@ -358,54 +463,68 @@ def main():
         e_wall = time.perf_counter() - tw
         e_dev = max(e0.elapsed_time(e1) / 1e3, e_wall)   # host-blocking copies: wall clock is the honest one
         e_bytes = sum(a_eff_bytes(n_cells, i, c) for i, c in zip(e_iters, e_checks))
-        e2e = [e_bytes, e_dev, h2d_b, d2h_b, e_iters]
+        e_t = rig.reduce([e_dev], "max")[0]
+        e_bytes_all = rig.reduce([e_bytes], "sum")[0]
+        e2e = {"value": e_bytes_all / e_t / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+               "ms_per_step": e_t / args.steps * 1e3, "time_steps_per_s": args.steps / e_t, "host_numa": rig.numa}
 
-    # ---- parity of the timed steps: the same K steps again in PARITY mode (bit-equal to the CPU
-    # oracle, tests/test_gpu_solver.py): iteration counts must be identical, fields within 1e-10 ----
-    parity = None
+    # ---- parity of the timed steps: the same K steps again in PARITY mode (bit-equal to the CPU oracle,
+    # tests/test_gpu_solver.py): PT iteration counts must be identical on EVERY rank and every field of EVERY
+    # rank's slab within TOL of the common scale after these K steps.  A miss makes the run fail (rc 3). ----
+    parity, parity_ok = None, True
     if final is not None:
-        for k, v in snapshot.items():
-            sim.f[k].set(v)
-        ctx.set_mode(ns.PARITY)
-        p_iters = [sim.step()[0] for _ in range(args.steps)]
-        ctx.set_mode(getattr(ns, args.mode))
-        ref = {k: sim.host(k) for k in final}
-        vscale = max(float(np.abs(ref[v]).max()) for v in ("Vx", "Vy", "Vz"))
-        diffs = {k: float(np.abs(final[k] - ref[k]).max() / (vscale if k[0] == "V" else max(float(np.abs(ref[k]).max()), 1e-300)))
-                 for k in final}
-        parity = {"against": "the same steps in PARITY mode (IEEE division, no FMA; bit-equal to the CPU oracle in tests/)",
-                  "pt_iters_identical": p_iters == iters, "max_rel_diff": diffs, "tolerance": 1e-10,
-                  "within_tolerance": max(diffs.values()) <= 1e-10}
-        if args.mode == "FASTEST":
-            # the same steps once more in FAST mode (reference arithmetic via corrected reciprocal
-            # division): what the bit-identical path costs
+        def rerun(mode):
             for k, v in snapshot.items():
                 sim.f[k].set(v)
-            ctx.set_mode(ns.FAST)
+            ctx.set_mode(getattr(ns, mode))
             ctx.sync()
-            tf = time.perf_counter()
-            f_res = [sim.step() for _ in range(args.steps)]
+            barrier()
+            t0 = time.perf_counter()
+            res = [sim.step() for _ in range(args.steps)]
             ctx.sync()
-            tf = time.perf_counter() - tf
-            ctx.set_mode(ns.FASTEST)
-            f_bytes = sum(a_eff_bytes(n_cells, it, len(h)) for it, h in f_res)
-            fdiff = max(float(np.abs(sim.host(k) - ref[k]).max()) for k in final)
-            parity["fast_mode"] = {"value": f_bytes / tf / 1e9 * world, "unit": "GB/s (per-rank wall clock x ranks)",
-                                   "pt_iters_identical": [r[0] for r in f_res] == p_iters,
-                                   "max_abs_diff_vs_parity": fdiff}
+            barrier()
+            dt = time.perf_counter() - t0
+            ctx.set_mode(getattr(ns, args.mode))
+            return res, dt, {k: sim.host(k) for k in final}
 
-    # ---- reduce over ranks: max time, summed bytes ----------------------------------------------
-    t_rank = max(dev_s, wall)
-    if world > 1:
-        v = torch.tensor([t_rank, e2e[1] if e2e else 0.0], device="cuda", dtype=torch.float64)
-        dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        b = torch.tensor([bytes_rank, e2e[0] if e2e else 0.0], device="cuda", dtype=torch.float64)
-        dist.all_reduce(b, op=dist.ReduceOp.SUM)
-        t_all, e_t = float(v[0]), float(v[1])
-        bytes_all, e_bytes_all = float(b[0]), float(b[1])
-    else:
-        t_all, bytes_all = t_rank, bytes_rank
-        e_t, e_bytes_all = (e2e[1], e2e[0]) if e2e else (0.0, 0.0)
+        p_res, _, ref = rerun("PARITY")
+        p_iters = [r[0] for r in p_res]
+        diffs = field_diffs(final, ref)
+        names = sorted(diffs)
+        worst = dict(zip(names, rig.reduce([diffs[k] for k in names], "max")))
+        same = rig.reduce([float(p_iters == iters)], "min")[0] == 1.0
+        within = max(worst.values()) <= TOL
+        parity_ok = same and within
+        parity = {"against": "the same steps in PARITY mode (IEEE division, no FMA; bit-equal to the CPU oracle in tests/)",
+                  "horizon_steps": args.steps, "ranks_checked": world,
+                  "pt_iters_identical": same, "max_rel_diff": worst, "tolerance": TOL, "within_tolerance": within,
+                  "bit_identical": max(worst.values()) == 0.0}
+        if not args.no_extras:
+            # what the other arithmetic costs / buys: the same steps once more in the other non-PARITY mode
+            other = "FASTEST" if args.mode != "FASTEST" else "FAST"
+            o_res, o_dt, o_fields = rerun(other)
+            o_dt = rig.reduce([o_dt], "max")[0]
+            o_bytes = rig.reduce([sum(a_eff_bytes(n_cells, it, len(h)) for it, h in o_res)], "sum")[0]
+            od = field_diffs(o_fields, ref)
+            o_worst = dict(zip(names, rig.reduce([od[k] for k in names], "max")))
+            parity["other_mode"] = {"mode": other, "value": o_bytes / o_dt / 1e9, "unit": "GB/s (wall clock, max over ranks)",
+                                    "pt_iters_identical": rig.reduce([float([r[0] for r in o_res] == p_iters)], "min")[0] == 1.0,
+                                    "max_rel_diff_vs_parity": o_worst, "within_tolerance": max(o_worst.values()) <= TOL}
+
+    share = (sum(iters) / args.steps) * (t_launch / per_launch) / (t_all / args.steps)
+    desc = ctx.pt_kernel_name(pt)
+    ctx.close()
+
+    # ---- extra legs of the default run (each on a fresh context; the B fields are freed above) ----
+    extras = {}
+    if not args.no_extras and args.workload == "B" and not args.fixed_iters:
+        if world == 1:
+            # like-with-like base of the weak-scaling curve: N > 1 runs variant M (the multi-GPU script),
+            # so here is variant M on ONE GPU, same grid, same step counts
+            extras["variant_M_n1"] = extra_workload(ns, rig, args, "B", "M", args.mode, args.steps, args.warmup, 0)
+        # BASELINE configs[4]: 511^3 cells per GPU, fixed PT work (eps_it = 0, 1020 iterations,
+        # residual check + allreduce every 510), nt = 3
+        extras["config_E"] = extra_workload(ns, rig, args, "E", "M", args.mode, 3, 1, 1020)
 
     if rank == 0:
         teff = bytes_all / t_all / 1e9
@@ -424,33 +543,32 @@ def main():
             "t_eff_per_gpu": teff / world, "frac_of_hbm_peak_per_gpu": teff / world / peak,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm",
-                         "kernel": ("pt_tb2s_kernel (two fused PT iterations per launch: 2 x (K5+K6+set_bc_Pr!)"
-                                    + ("; slab-interface chunks: pt_tb2_kernel<.,16,true>)" if world > 1 else ")") if tb2_on
-                                    else "pt_iter_kernel (fused K5+K6+set_bc_Pr!)"),
+            "roofline": {"bound": "hbm", "kernel": desc,
                          "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "us_per_launch": t_launch * 1e6,
+                         "traffic": traffic, "traffic_key": tkey, "us_per_launch": t_launch * 1e6,
+                         "pt_iterations_per_launch": per_launch,
                          # what actually crossed the DRAM interface (ncu) over the same launch time: the
-                         # kernel keeps Pr^(1) and dPrdtau^(1) on chip, so this is well below `achieved`
+                         # kernel keeps the intermediate iterates on chip, so this is well below `achieved`
                          "dram_achieved": (traffic / t_launch / 1e9) if traffic else None,
                          "dram_frac": (traffic / t_launch / 1e9 / peak) if traffic else None,
                          "algorithmic_bytes_per_launch": 40.0 * per_launch * n_cells,
-                         "share_of_step": (sum(iters) / args.steps) * (t_launch / per_launch) / (t_all / args.steps)},
+                         "share_of_step": share},
         }
         if parity:
             line["parity_check"] = parity
         if e2e:
-            line["e2e"] = {"value": e_bytes_all / e_t / 1e9, "unit": "GB/s", "h2d_bytes_per_step": e2e[2],
-                           "d2h_bytes_per_step": e2e[3], "ms_per_step": e_t / args.steps * 1e3,
-                           "time_steps_per_s": args.steps / e_t}
+            line["e2e"] = e2e
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             cv, cores, sample, _, _ = oracle_sample(variant, nx, ny, nz)
             line["cpu_baseline"] = {"value": cv, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
-        dist.destroy_process_group()
+        rig.dist.destroy_process_group()
+    if not parity_ok:
+        sys.stderr.write("bench.py: PARITY CHECK FAILED (iteration counts differ or a field is outside the tolerance)\n")
+        sys.exit(3)
 
 
 if __name__ == "__main__":

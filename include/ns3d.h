@@ -229,6 +229,11 @@ NS3D_API int ns3d_pt_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const dou
 NS3D_API int ns3d_pt_iterate(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const double* divV,
                     const ns3d_pt_params* p, int n);
 
+/* Which kernel the fused loop launches for these parameters on this context (mode, options, communicator):
+ * a NUL-terminated description into buf (capacity cap) and the number of PT iterations one launch of
+ * it performs -- what bench.py divides launch times by.  No reference counterpart (diagnostics).      */
+NS3D_API int ns3d_pt_describe(ns3d_ctx* ctx, const ns3d_pt_params* p, char* buf, int cap, int* iters_per_launch);
+
 typedef struct ns3d_fields {
     double *Pr, *dPrdtau, *C, *C_o, *txx, *tyy, *tzz, *txy, *txz, *tyz;
     double *Vx, *Vy, *Vz, *Vx_o, *Vy_o, *Vz_o, *divV, *Rp;

@@ -719,6 +719,25 @@ extern "C" int ns3d_pt_iterate(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const
     return NS3D_OK;
 }
 
+extern "C" int ns3d_pt_describe(ns3d_ctx* ctx, const ns3d_pt_params* p, char* buf, int cap, int* iters_per_launch)
+{
+    NS3D_CHECK_CTX(ctx);
+    PtK k;
+    NS3D_TRY(make_ptk(ctx, p, &k));
+    const bool slabs = ctx->nranks > 1;
+    const bool tb2 = use_tb2(ctx, p, !slabs || (ctx->opt_p2p && ctx->p2p_ready && k.nz >= 6));
+    const char* mode = ctx->mode == NS3D_PARITY ? "PARITY" : (ctx->mode == NS3D_FAST ? "FAST" : "FASTEST");
+    if (buf && cap > 0) {
+        if (tb2)
+            snprintf(buf, cap, "pt_tb2s_kernel<%s,TY=%d> (two fused PT iterations per launch: 2 x (K5+K6+set_bc_Pr!), %d-plane chunks%s)",
+                     mode, k.tb_ty, k.zchunk_tb, slabs ? "; slab-interface chunks: pt_tb2_kernel<.,16,true> with update_halo!(Pr) over peer memory" : "");
+        else
+            snprintf(buf, cap, "pt_iter_kernel<%s> (fused K5+K6+set_bc_Pr!, one PT iteration per launch)", mode);
+    }
+    if (iters_per_launch) *iters_per_launch = tb2 ? 2 : 1;
+    return NS3D_OK;
+}
+
 // ---- level 2: the three once-per-step groups around the PT loop, and the whole step ---------------
 namespace {
 int step_cylinder(ns3d_ctx* ctx, const ns3d_fields* f, const ns3d_step_params* sp)

@@ -292,15 +292,22 @@ def gather_interior(sim: Simulation, name: str, dtype=np.float64) -> np.ndarray 
     return sim.ctx.gather_box(a, (1, sx - 1), (1, sy - 1), (1, 1 + nplanes[rank]), nplanes, dtype)
 
 
-def save_mat(fname: str, sim: Simulation):
-    """``matwrite("out_save/step_$it.mat", Dict("Pr"=>Array(Pr), "Vx"=>..., "Vy"=>..., "Vy"=>Array(Vz),
-    "C"=>..., "dx"=>dx, "dy"=>dy, "dz"=>dz); compress=true)`` (G:169).  The reference's Dict literal names
-    the key "Vy" twice, so its file holds Vz under "Vy" and no Vy at all; the
-    same content is written here, plus the lost field under "Vy_true"."""
+def save_mat(fname: str, sim: Simulation, initial: bool = False):
+    """The single-GPU script's ``.mat`` dumps.
+
+    Periodic frames, ``matwrite("out_save/step_$it.mat", Dict("Pr"=>Array(Pr), "Vx"=>Array(Vx), "Vy"=>Array(Vy),
+    "Vz"=>Array(Vz), "C"=>Array(C), "dx"=>dx, "dy"=>dy, "dz"=>dz))`` (G:169): eight distinct keys.
+    ``initial=True`` is ``step_0.mat`` (G:89), whose Dict literal names the key "Vy" twice -- Julia keeps
+    the last pair, so that file holds ``Vz`` under "Vy" and has neither the true ``Vy`` nor a "Vz" key
+    (SURVEY.md quirk 9); reproduced as written.  Neither call compresses."""
     from scipy.io import savemat
     s = sim.s
-    savemat(fname, {"Pr": sim.host("Pr"), "Vx": sim.host("Vx"), "Vy": sim.host("Vz"), "C": sim.host("C"),
-                    "Vy_true": sim.host("Vy"), "dx": s.dx, "dy": s.dy, "dz": s.dz}, do_compression=True)
+    d = {"Pr": sim.host("Pr"), "Vx": sim.host("Vx"), "C": sim.host("C"), "dx": s.dx, "dy": s.dy, "dz": s.dz}
+    if initial:
+        d["Vy"] = sim.host("Vz")
+    else:
+        d["Vy"], d["Vz"] = sim.host("Vy"), sim.host("Vz")
+    savemat(fname, d)
 
 
 def runme(*, do_vis: bool = True, do_save: bool = False, nx: int = 255, nt: int = 10000, mode: int = native.FAST,
@@ -308,6 +315,9 @@ def runme(*, do_vis: bool = True, do_save: bool = False, nx: int = 255, nt: int 
     """Drop-in for ``runme`` of the single-GPU script (G:12); ``nx``/``nt`` are literals there (G:44,51)."""
     s = setup_gpu(nx)
     sim = Simulation(s, native.Context(_dist_env()[2], mode))
+    if do_save:                                                          # G:89
+        os.makedirs("out_save", exist_ok=True)
+        save_mat("out_save/step_0.mat", sim, initial=True)
     for it in range(1, nt + 1):
         if do_print:
             print(f"#it = {it}")                                         # G:125

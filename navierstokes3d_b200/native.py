@@ -110,6 +110,7 @@ SIGNATURES = {
     "ns3d_allreduce_max": (_I, [_P, c_double_p]),
     "ns3d_pt_solve": (_I, [_P, _P, _P, _P, C.POINTER(PtParams), c_int_p, c_double_p, _I, c_int_p]),
     "ns3d_pt_iterate": (_I, [_P, _P, _P, _P, C.POINTER(PtParams), _I]),
+    "ns3d_pt_describe": (_I, [_P, C.POINTER(PtParams), C.c_char_p, _I, c_int_p]),
     "ns3d_step": (_I, [_P, C.POINTER(Fields), C.POINTER(StepParams), c_int_p, c_double_p, _I, c_int_p]),
     "ns3d_predictor": (_I, [_P, C.POINTER(Fields), C.POINTER(StepParams)]),
     "ns3d_corrector": (_I, [_P, C.POINTER(Fields), C.POINTER(StepParams)]),
@@ -342,6 +343,18 @@ class Context:
     def pt_iterate(self, Pr, dPrdtau, divV, p: PtParams, n: int):
         self._ck(self.lib.ns3d_pt_iterate(self.h, _ptr(Pr), _ptr(dPrdtau), _ptr(divV), C.byref(p), n),
                  "ns3d_pt_iterate")
+
+    def _describe(self, p: PtParams):
+        buf, n = C.create_string_buffer(512), C.c_int(0)
+        self._ck(self.lib.ns3d_pt_describe(self.h, C.byref(p), buf, 512, C.byref(n)), "ns3d_pt_describe")
+        return buf.value.decode(), n.value
+
+    def pt_kernel_name(self, p: PtParams) -> str:
+        """The kernel the fused loop launches for ``p`` on this context (``ns3d_pt_describe``)."""
+        return self._describe(p)[0]
+
+    def pt_iters_per_launch(self, p: PtParams) -> int:
+        return self._describe(p)[1]
 
     def predictor(self, fields: Fields, sp: StepParams):
         """M:449-455: update_τ!, predict_V!, set_cylinder!, update_∇V! + halo updates."""

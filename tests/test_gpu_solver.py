@@ -284,3 +284,34 @@ def test_compile_time_stride_kernels(O, ns, variant, grid):
     assert (out[1][0] == f["Pr"]).all() and (out[1][1] == f["dPrdtau"]).all()
     assert (out[0][0] == out[1][0]).all() and (out[0][1] == out[1][1]).all()
     ctx.close()
+
+
+def test_config_B_whole_time_steps_vs_oracle(O, ns):
+    """BASELINE configs[1] at FULL size -- 255x153x153, variant G (scripts/NavierStokes3D_gpu.jl as
+    shipped, G:119-142), nt = 2, about 6 500 PT iterations: about 20 s of oracle on 16 host threads.
+    PARITY: bit-exact fields, identical PT iteration counts and identical `err` history.
+    FAST: the same, bit for bit (it is the bench default).  FASTEST: identical counts, fields within
+    1e-10 of the common scale after these 2 steps (north_star's tolerance, horizon stated)."""
+    nt = 2
+    O.lib().ns3d_oracle_set_num_threads(len(os.sched_getaffinity(0)))
+    p = O.params_G(255)
+    f, iters_o, errs_o = O.run(p, nt)
+    assert (p.nx, p.ny, p.nz) == (255, 153, 153) and all(it > 1000 for it in iters_o)
+    fields = ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C")
+    vscale = max(np.abs(f[v]).max() for v in ("Vx", "Vy", "Vz"))
+    for mode in ("PARITY", "FAST", "FASTEST"):
+        c = ns.Context(0, getattr(ns, mode))
+        sim = ns.Simulation(ns.setup_gpu(255), c)
+        for _ in range(nt):
+            sim.step()
+        assert sim.iters == iters_o, (mode, sim.iters, iters_o)
+        if mode != "FASTEST":
+            assert sim.err_hist == errs_o, mode
+            for name in fields:
+                got = sim.host(name)
+                assert (got == f[name]).all(), f"{mode}: {name}: {(got != f[name]).sum()} values differ"
+        else:
+            for name in fields:
+                scale = vscale if name[0] == "V" else None
+                assert rel_inf(sim.host(name), f[name], scale) <= TOL_FASTEST, (mode, name)
+        c.close()

@@ -56,16 +56,24 @@ def test_interior_and_planes_of_a_simulation(ns, variant):
     sim.ctx.close()
 
 
-def test_runme_do_save_writes_the_mat_file(ns, tmp_path, monkeypatch):
-    """G:168-170: every 10th step -> out_save/step_$it.mat with the script's (quirky) key set."""
+def test_runme_do_save_writes_the_mat_files(ns, tmp_path, monkeypatch):
+    """G:168-170: every 10th step -> out_save/step_$it.mat with the eight keys of the script's Dict
+    (Pr, Vx, Vy, Vz, C, dx, dy, dz); G:89: out_save/step_0.mat, whose Dict literal repeats the key "Vy"
+    (the second pair, Array(Vz), wins: no true Vy, no "Vz" key -- SURVEY.md quirk 9)."""
     from scipy.io import loadmat
     monkeypatch.chdir(tmp_path)
     sim = ns.runme(do_vis=False, do_save=True, nx=40, nt=10, mode=ns.PARITY, do_print=False, return_sim=True)
     m = loadmat(tmp_path / "out_save" / "step_10.mat")
-    assert np.array_equal(m["Pr"], sim.host("Pr")) and np.array_equal(m["Vx"], sim.host("Vx"))
-    assert np.array_equal(m["Vy"], sim.host("Vz"))        # quirk 9: the second "Vy" => Array(Vz) wins
-    assert np.array_equal(m["Vy_true"], sim.host("Vy")) and np.array_equal(m["C"], sim.host("C"))
-    assert m["dx"].item() == sim.s.dx and m["dz"].item() == sim.s.dz
+    assert {k for k in m if not k.startswith("__")} == {"Pr", "Vx", "Vy", "Vz", "C", "dx", "dy", "dz"}
+    for k in ("Pr", "Vx", "Vy", "Vz", "C"):
+        assert np.array_equal(m[k], sim.host(k)), k
+    assert m["dx"].item() == sim.s.dx and m["dy"].item() == sim.s.dy and m["dz"].item() == sim.s.dz
+    m0 = loadmat(tmp_path / "out_save" / "step_0.mat")
+    assert {k for k in m0 if not k.startswith("__")} == {"Pr", "Vx", "Vy", "C", "dx", "dy", "dz"}
+    fresh = ns.Simulation(ns.setup_gpu(40), ns.Context(0, ns.PARITY))
+    assert np.array_equal(m0["Vy"], fresh.host("Vz")) and np.array_equal(m0["Vx"], fresh.host("Vx"))
+    assert np.array_equal(m0["Pr"], fresh.host("Pr"))
+    fresh.ctx.close()
     sim.ctx.close()
 
 
