@@ -131,6 +131,7 @@ extern "C" int ns3d_destroy(ns3d_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->comm_stream);
     ns3d_internal_pt_free_graphs(ctx);
+    ns3d_internal_ptv_release(ctx);
     ns3d_internal_out_free(ctx);
     for (auto& kv : ctx->p2p_map) {
         if (kv.second.first) cudaIpcCloseMemHandle(kv.second.first);
@@ -184,6 +185,25 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
         ctx->opt_tb2 = value != 0;
         return NS3D_OK;
     }
+    if (!strcmp(name, "ptv")) { ctx->opt_ptv = value != 0; return NS3D_OK; }
+    if (!strcmp(name, "ptv_k")) {
+        if (value < 0 || value > 3) return ns3d_fail(ctx, NS3D_EINVAL, "ptv_k must be 0 (default) .. 3");
+        ctx->opt_ptv_k = value;
+        return NS3D_OK;
+    }
+    if (!strcmp(name, "ptv_ns")) {
+        if (value != 0 && (value < 3 || value > 8)) return ns3d_fail(ctx, NS3D_EINVAL, "ptv_ns must be 0 (default) or 3 .. 8");
+        ctx->opt_ptv_ns = value;
+        return NS3D_OK;
+    }
+    if (!strcmp(name, "ptv_tma")) { ctx->opt_ptv_tma = value != 0; return NS3D_OK; }
+    if (!strcmp(name, "ptv_lb")) {
+        if (value < -1 || value > 4) return ns3d_fail(ctx, NS3D_EINVAL, "ptv_lb must be -1 (default) or 0 .. 4");
+        ctx->opt_ptv_lb = value;
+        return NS3D_OK;
+    }
+    if (!strcmp(name, "ptv_pxt")) { ctx->opt_ptv_pxt = value < 0 ? 0 : value; return NS3D_OK; }
+    if (!strcmp(name, "ptv_bty")) { ctx->opt_ptv_bty = value < 0 ? 0 : value; return NS3D_OK; }
     if (!strcmp(name, "tb2_ty")) {
         if (value != 0 && value != 8 && value != 16 && value != 32)
             return ns3d_fail(ctx, NS3D_EINVAL, "tb2_ty must be 0 (auto), 8, 16 or 32");
@@ -283,6 +303,15 @@ extern "C" int ns3d_free(ns3d_ctx* ctx, double* dptr)
     if (it == ctx->allocs.end()) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_free: pointer not owned by this context");
     NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
     NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
+    // nothing may keep the pointer: captured graphs of the fused loop and peer mappings of this block go first
+    ns3d_internal_pt_free_graphs(ctx);
+    auto pm = ctx->p2p_map.find((const void*)dptr);
+    if (pm != ctx->p2p_map.end()) {
+        if (pm->second.first) cudaIpcCloseMemHandle(pm->second.first);
+        if (pm->second.second) cudaIpcCloseMemHandle(pm->second.second);
+        ctx->p2p_map.erase(pm);
+    }
     NS3D_CUDA(ctx, cudaFree(dptr));
     ctx->bytes -= it->second;
     ctx->allocs.erase(it);
@@ -422,20 +451,17 @@ extern "C" int ns3d_comm_init(ns3d_ctx* ctx, int rank, int nranks, const char id
     ctx->p2p_map.erase(ctx->mbox);
     ctx->peer_mbox[0] = (unsigned long long*)lo;
     ctx->peer_mbox[1] = (unsigned long long*)hi;
-    // all ranks must agree on the path: min-reduce the local outcome
-    ctx->h_maxbits[2] = rc == NS3D_OK ? 1ULL : 0ULL;
-    NS3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_maxbits + 2, ctx->h_maxbits + 2, 8, cudaMemcpyHostToDevice, ctx->stream));
-    NS3D_NCCL(ctx, g_nccl.AllReduce(ctx->d_maxbits + 2, ctx->d_maxbits + 2, 1, ncclUint64, ncclMin, comm, ctx->stream));
-    NS3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_maxbits + 2, ctx->d_maxbits + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->p2p_ready = ctx->h_maxbits[2] == 1ULL;
+    ctx->p2p_ready = rc == NS3D_OK;   // agreed on by all ranks inside ns3d_internal_p2p_map
     ctx->err.clear();
     return NS3D_OK;
 }
 
 // Exchanges the CUDA IPC handle of `local_base` (the base of a cudaMalloc block) with both slab
 // neighbours and maps theirs.  COLLECTIVE: every rank must call it at the same point with its
-// corresponding buffer.  Cached per local pointer.
+// corresponding buffer, and every rank takes part in the whole exchange even when something failed
+// locally (it then sends a null handle): the outcome is agreed on with a min-all-reduce, so either
+// every rank returns NS3D_OK or every rank returns an error -- nobody is left waiting in a send/recv
+// group.  Cached per local pointer; entries are dropped when the block is freed.
 int ns3d_internal_p2p_map(ns3d_ctx* ctx, const void* local_base, void** peer_lo, void** peer_hi)
 {
     auto it = ctx->p2p_map.find(local_base);
@@ -447,38 +473,66 @@ int ns3d_internal_p2p_map(ns3d_ctx* ctx, const void* local_base, void** peer_lo,
     *peer_lo = *peer_hi = nullptr;
     if (!ctx->nccl) return ns3d_fail(ctx, NS3D_ECOMM, "p2p_map: no communicator");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
-    cudaIpcMemHandle_t mine;
-    NS3D_CUDA(ctx, cudaIpcGetMemHandle(&mine, const_cast<void*>(local_base)));
-    unsigned char* stage = nullptr;  // [0,64) mine, [64,128) from lower, [128,192) from upper
-    NS3D_CUDA(ctx, cudaMalloc(&stage, 192));
-    NS3D_CUDA(ctx, cudaMemcpyAsync(stage, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
     ncclComm_t comm = (ncclComm_t)ctx->nccl;
     const int lo = ctx->rank - 1, hi = ctx->rank + 1;
-    NS3D_NCCL(ctx, g_nccl.GroupStart());
+    int rc = NS3D_OK;            // first local failure; the collective steps below run regardless
+    auto note_cuda = [&](cudaError_t e, const char* what) {
+        if (e == cudaSuccess) return;
+        cudaGetLastError();
+        if (rc == NS3D_OK) rc = ns3d_fail(ctx, NS3D_ECOMM, "p2p_map: %s failed: %s", what, cudaGetErrorString(e));
+    };
+    auto note_nccl = [&](ncclResult_t r, const char* what) {
+        if (r != ncclSuccess && rc == NS3D_OK) rc = ns3d_fail(ctx, NS3D_ECOMM, "p2p_map: %s failed: %s", what, g_nccl.GetErrorString(r));
+    };
+    // [0,64) mine, [64,128) from lower, [128,192) from upper, [192,200) outcome: scratch behind the reduction words
+    unsigned char* stage = (unsigned char*)(ctx->d_maxbits + 8);
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    note_cuda(cudaIpcGetMemHandle(&mine, const_cast<void*>(local_base)), "cudaIpcGetMemHandle");
+    if (rc != NS3D_OK) memset(&mine, 0, sizeof mine);
+    note_cuda(cudaMemcpyAsync(stage, &mine, 64, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpyAsync");
+    note_nccl(g_nccl.GroupStart(), "ncclGroupStart");
     if (lo >= 0) {
-        NS3D_NCCL(ctx, g_nccl.Send(stage, 64, ncclUint8, lo, comm, ctx->stream));
-        NS3D_NCCL(ctx, g_nccl.Recv(stage + 64, 64, ncclUint8, lo, comm, ctx->stream));
+        note_nccl(g_nccl.Send(stage, 64, ncclUint8, lo, comm, ctx->stream), "ncclSend");
+        note_nccl(g_nccl.Recv(stage + 64, 64, ncclUint8, lo, comm, ctx->stream), "ncclRecv");
     }
     if (hi < ctx->nranks) {
-        NS3D_NCCL(ctx, g_nccl.Send(stage, 64, ncclUint8, hi, comm, ctx->stream));
-        NS3D_NCCL(ctx, g_nccl.Recv(stage + 128, 64, ncclUint8, hi, comm, ctx->stream));
+        note_nccl(g_nccl.Send(stage, 64, ncclUint8, hi, comm, ctx->stream), "ncclSend");
+        note_nccl(g_nccl.Recv(stage + 128, 64, ncclUint8, hi, comm, ctx->stream), "ncclRecv");
     }
-    NS3D_NCCL(ctx, g_nccl.GroupEnd());
+    note_nccl(g_nccl.GroupEnd(), "ncclGroupEnd");   // the group is closed on every path
     cudaIpcMemHandle_t theirs[2];
-    NS3D_CUDA(ctx, cudaMemcpyAsync(theirs, stage + 64, 128, cudaMemcpyDeviceToHost, ctx->stream));
-    NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(stage);
+    memset(theirs, 0, sizeof theirs);
+    note_cuda(cudaMemcpyAsync(theirs, stage + 64, 128, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpyAsync");
+    note_cuda(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
     ctx->halo_calls++;
     void* mapped[2] = {nullptr, nullptr};
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < 2 && rc == NS3D_OK; ++q) {
         const int nb = q == 0 ? lo : hi;
         if (nb < 0 || nb >= ctx->nranks) continue;
         cudaError_t e = cudaIpcOpenMemHandle(&mapped[q], theirs[q], cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
             cudaGetLastError();
-            return ns3d_fail(ctx, NS3D_ECOMM, "cudaIpcOpenMemHandle (rank %d -> %d) failed: %s", ctx->rank, nb,
-                             cudaGetErrorString(e));
+            mapped[q] = nullptr;
+            rc = ns3d_fail(ctx, NS3D_ECOMM, "cudaIpcOpenMemHandle (rank %d -> %d) failed: %s", ctx->rank, nb, cudaGetErrorString(e));
         }
+    }
+    // agree on the outcome
+    ctx->h_maxbits[4] = rc == NS3D_OK ? 1ULL : 0ULL;
+    int rc2 = NS3D_OK;
+    if (cudaMemcpyAsync(ctx->d_maxbits + 4, ctx->h_maxbits + 4, 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        g_nccl.AllReduce(ctx->d_maxbits + 4, ctx->d_maxbits + 4, 1, ncclUint64, ncclMin, comm, ctx->stream) != ncclSuccess ||
+        cudaMemcpyAsync(ctx->h_maxbits + 4, ctx->d_maxbits + 4, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        cudaGetLastError();
+        rc2 = NS3D_ECOMM;
+    }
+    if (rc == NS3D_OK && (rc2 != NS3D_OK || ctx->h_maxbits[4] != 1ULL))
+        rc = ns3d_fail(ctx, NS3D_ECOMM, "p2p_map: a neighbour could not share or map its buffer");
+    if (rc != NS3D_OK) {
+        for (int q = 0; q < 2; ++q)
+            if (mapped[q]) cudaIpcCloseMemHandle(mapped[q]);
+        return rc;
     }
     ctx->p2p_map[local_base] = {mapped[0], mapped[1]};
     *peer_lo = mapped[0];

@@ -70,6 +70,19 @@ struct ns3d_ctx {
     int opt_graphs = 1;       // replay chunks of PT iterations as CUDA graphs
     long long halo_calls = 0; // uncaptured halo exchanges so far (NCCL peers connected)
     void* pt_graphs = nullptr;  // graph cache owned by ns3d_pt.cu
+    // the fused loop's pitched working copies (ns3d_ptv.cu): Pr x2, dPrdtau x2 (ping-pong), divV
+    double* ptv_raw[5] = {};    // cudaMalloc blocks
+    double* ptv[5] = {};        // element (0,0,0) inside them (front padding skipped)
+    int ptv_nx = 0, ptv_ny = 0, ptv_nz = 0;
+    bool ptv_peers_mapped = false;
+    void* ptv_graphs = nullptr;  // graph cache owned by ns3d_ptv.cu
+    int opt_ptv = 1;          // the fused loop runs ptv_kernel on the pitched copies (0 = the round-1 kernels on the caller's arrays)
+    int opt_ptv_k = 0;        // PT iterations per launch (0 = default)
+    int opt_ptv_ns = 0;       // staging slots of the TMA ring (0 = default 4; >= 3)
+    int opt_ptv_tma = 1;      // stage the z-plane tiles with the TMA unit (0 = plain loads by all threads)
+    int opt_ptv_lb = -1;      // launch-bounds variant (threads / CTAs per SM): 0 = 256/2, 1 = 256/3, 2 = 256/4, 3 = 512/1, 4 = 512/2 (-1 = default)
+    int opt_ptv_pxt = 0;      // thread columns per tile (0 = balanced automatically)
+    int opt_ptv_bty = 0;      // thread rows per tile (0 = as many as the CTA has threads for)
     size_t l2_bytes = 0;
 };
 
@@ -142,6 +155,12 @@ __device__ __forceinline__ void block_max_to_global(unsigned long long v, unsign
 // internal cross-TU entry points
 int ns3d_internal_p2p_map(ns3d_ctx* ctx, const void* local_base, void** peer_lo, void** peer_hi);
 void ns3d_internal_pt_free_graphs(ns3d_ctx* ctx);
+void ns3d_internal_ptv_free(ns3d_ctx* ctx);     // graph cache of ns3d_ptv.cu
+void ns3d_internal_ptv_release(ns3d_ctx* ctx);  // ... and its buffers
+int ns3d_internal_ptv_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const double* divV, const ns3d_pt_params* p, int* h_iters,
+                            double* h_err_hist, int err_cap, int* h_nchecks);
+int ns3d_internal_ptv_iterate(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const double* divV, const ns3d_pt_params* p, int n_iter);
+int ns3d_internal_ptv_describe(ns3d_ctx* ctx, const ns3d_pt_params* p, char* buf, int cap, int* iters_per_launch);
 void ns3d_internal_out_free(ns3d_ctx* ctx);
 int ns3d_internal_gather_bytes(ns3d_ctx* ctx, const void* d_send, size_t bytes, void* d_recv, const size_t* bytes_all);
 int ns3d_internal_max_abs_async(ns3d_ctx* ctx, const double* A, size_t count);  // result -> ctx->d_maxbits

@@ -644,6 +644,7 @@ extern "C" int ns3d_pt_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const d
     PtK k;
     NS3D_TRY(make_ptk(ctx, p, &k));
     if (p->nchk <= 0 || p->niter < 0) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_pt_solve: bad niter/nchk");
+    if (ctx->opt_ptv) return ns3d_internal_ptv_solve(ctx, Pr, dPrdtau, divV, p, h_iters, h_err_hist, err_cap, h_nchecks);
     NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t n = (size_t)p->nx * p->ny * p->nz;
     NS3D_TRY(check_owned(ctx, Pr, dPrdtau, divV));
@@ -696,6 +697,7 @@ extern "C" int ns3d_pt_iterate(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const
     if (!Pr || !dPrdtau || !divV || n_iter < 0) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_pt_iterate: bad argument");
     PtK k;
     NS3D_TRY(make_ptk(ctx, p, &k));
+    if (ctx->opt_ptv) return ns3d_internal_ptv_iterate(ctx, Pr, dPrdtau, divV, p, n_iter);
     NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t n = (size_t)p->nx * p->ny * p->nz;
     NS3D_TRY(check_owned(ctx, Pr, dPrdtau, divV));
@@ -724,6 +726,7 @@ extern "C" int ns3d_pt_describe(ns3d_ctx* ctx, const ns3d_pt_params* p, char* bu
     NS3D_CHECK_CTX(ctx);
     PtK k;
     NS3D_TRY(make_ptk(ctx, p, &k));
+    if (ctx->opt_ptv) return ns3d_internal_ptv_describe(ctx, p, buf, cap, iters_per_launch);
     const bool slabs = ctx->nranks > 1;
     const bool tb2 = use_tb2(ctx, p, !slabs || (ctx->opt_p2p && ctx->p2p_ready && k.nz >= 6));
     const char* mode = ctx->mode == NS3D_PARITY ? "PARITY" : (ctx->mode == NS3D_FAST ? "FAST" : "FASTEST");

@@ -19,11 +19,9 @@
 // thread marched along z with the z neighbours in registers (2.5-D blocking).
 #pragma once
 
-#include "ns3d_shared.cuh"
+#include "ns3d_pt_common.cuh"
 
 namespace {
-
-enum { X_NEUMANN = 0, X_DIRICHLET = 1, X_HYDRO = 2 };
 
 struct PtK {
     int nx, ny, nz;
@@ -72,14 +70,6 @@ struct PtK {
     long long oDP;    // dPN - dP - one dPrdτ plane   : d + oDP is the stage-2 store of plane s-1
     long long oDPt;   // dPN - dP                     : top-face store of plane s
 };
-
-// a / b with y = RN(1/b): one multiply + two FMAs (Markstein's correction step).
-__device__ __forceinline__ double div3(double a, double b, double y)
-{
-    const double q = a * y;
-    const double r = fma(-b, q, a);
-    return fma(r, y, q);
-}
 
 template <int MODE>
 __device__ __forceinline__ double bracket(const PtK& p, double pc, double xm, double xp, double ym, double yp,
@@ -142,80 +132,6 @@ __device__ __forceinline__ void store_plane(const PtK& p, double* __restrict__ p
 struct StreamRegs {
     double zp, dq, dv;
 };
-
-// ---- peer-memory halo protocol (device side) --------------------------------------------------
-#ifdef NS3D_HOST_EMU  // host emulation of the kernels (tests/emu/): the same orderings with GCC atomics
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
-{
-    emu::spin_pause();  // only ever polled in a spin loop: let the other ranks' threads run
-    return __atomic_load_n(p, __ATOMIC_ACQUIRE);
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
-{
-    __atomic_store_n(p, v, __ATOMIC_RELEASE);
-}
-__device__ __forceinline__ unsigned long long atom_add_acq_rel_gpu(unsigned long long* p, unsigned long long v)
-{
-    return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL);
-}
-#else
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long atom_add_acq_rel_gpu(unsigned long long* p, unsigned long long v)
-{
-    unsigned long long old;
-    asm volatile("atom.add.acq_rel.gpu.global.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
-    return old;
-}
-#endif
-
-// Spins until the neighbour on `side` (0 lower, 1 upper) has finished the face work of every
-// launch this rank has finished: then its stores into our halo plane have landed and it no
-// longer reads the halo plane of its own that we are about to overwrite.  Bounded: a
-// neighbour that never answers raises NS3D_MB_ERROR instead of hanging the GPU.
-__device__ __forceinline__ void wait_neighbour(unsigned long long* mbox, int side)
-{
-    const unsigned long long need = ld_acquire_sys(mbox + NS3D_MB_EPOCH_LO + side);
-    const long long t0 = clock64();
-    while (ld_acquire_sys(mbox + NS3D_MB_FLAG_LO + side) < need) {
-        if (clock64() - t0 > 8000000000LL) {  // ~4 s
-            mbox[NS3D_MB_ERROR] = 1ULL + side;
-            break;
-        }
-    }
-}
-
-// Last face CTA of this launch on `side`: close the epoch and tell the neighbour.
-__device__ __forceinline__ void signal_neighbour(unsigned long long* mbox, int side, unsigned long long* peer_flag,
-                                                 unsigned nface)
-{
-    const unsigned long long old = atom_add_acq_rel_gpu(mbox + NS3D_MB_ARRIVE_LO + side, 1ULL);
-    if (old + 1 == nface) {
-        mbox[NS3D_MB_ARRIVE_LO + side] = 0ULL;
-        const unsigned long long e = mbox[NS3D_MB_EPOCH_LO + side] + 1ULL;
-        mbox[NS3D_MB_EPOCH_LO + side] = e;
-        __threadfence_system();
-        st_release_sys(peer_flag, e);
-    }
-}
-
-// After a chunk of launches: the halo planes of the current iterate are complete once both
-// neighbours have signalled the epoch this rank has reached.
-__global__ void pt_halo_wait_kernel(unsigned long long* mbox, int has_lo, int has_hi)
-{
-    if (threadIdx.x == 0) {
-        if (has_lo) wait_neighbour(mbox, 0);
-        if (has_hi) wait_neighbour(mbox, 1);
-    }
-}
 
 // P2P = true: the CTAs that update plane 1 / nz-2 of a slab also store the new values -- with
 // their x/y mirror images -- straight into the neighbour's halo plane over NVLink (mapped peer

@@ -1,0 +1,71 @@
+// Instantiations of ptv_kernel for ONE arithmetic mode and their dispatch (included by ns3d_ptv_mode*.cu).
+#pragma once
+
+#include "ns3d_internal.cuh"
+#include "ns3d_ptv_kernels.cuh"
+
+namespace {
+
+template <int MODE, int K, bool P2P, bool TMA, int PXT, int BTY, int NT, int MINB>
+int ptv_launch_t(ns3d_ctx* ctx, cudaStream_t st, const PtV& k, const PtvMaps& maps, dim3 grid, size_t smem)
+{
+    auto ptv_kernel_fn = ptv_kernel<MODE, K, P2P, TMA, PXT, BTY, NT, MINB>;
+    static size_t s_smem_set[64] = {};  // per instantiation and device: dynamic shared memory the function may use
+    if (smem > 48 * 1024 && smem > s_smem_set[ctx->device & 63]) {
+        NS3D_CUDA(ctx, cudaFuncSetAttribute(ptv_kernel_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        s_smem_set[ctx->device & 63] = smem;
+    }
+    ptv_kernel_fn<<<grid, dim3(ptv_threads(k), 1, 1), smem, st>>>(k, maps);
+    NS3D_LAUNCH_CHECK(ctx);
+    return NS3D_OK;
+}
+
+// launch bounds: lb 0 = 256 threads / 2 CTAs per SM, 1 = 256 / 3, 3 = 512 / 1, 4 = 512 / 2
+template <int MODE, int K, bool P2P, bool TMA, int PXT, int BTY>
+int ptv_launch_lb(ns3d_ctx* ctx, cudaStream_t st, const PtV& k, const PtvMaps& maps, int lb, dim3 grid, size_t smem)
+{
+    if (PXT * BTY == 512 || (PXT == 0 && lb >= 3)) {
+        if (lb == 4) return ptv_launch_t<MODE, K, P2P, TMA, PXT, BTY, 512, 2>(ctx, st, k, maps, grid, smem);
+        return ptv_launch_t<MODE, K, P2P, TMA, PXT, BTY, 512, 1>(ctx, st, k, maps, grid, smem);
+    }
+    if (lb == 0) return ptv_launch_t<MODE, K, P2P, TMA, PXT, BTY, 256, 2>(ctx, st, k, maps, grid, smem);
+    return ptv_launch_t<MODE, K, P2P, TMA, PXT, BTY, 256, 3>(ctx, st, k, maps, grid, smem);
+}
+
+// Tile shapes with a compile-time instantiation (every shared-memory stride an immediate); any other shape runs the
+// instantiation that takes the geometry from the kernel parameters.
+template <int MODE, int K>
+int ptv_launch_shape(ns3d_ctx* ctx, cudaStream_t st, const PtV& k, const PtvMaps& maps, int lb, dim3 grid, size_t smem)
+{
+    if (k.ns == 4) {
+        if (k.pxt == 16 && k.bty == 16) return ptv_launch_lb<MODE, K, false, true, 16, 16>(ctx, st, k, maps, lb, grid, smem);
+        if (k.pxt == 32 && k.bty == 8) return ptv_launch_lb<MODE, K, false, true, 32, 8>(ctx, st, k, maps, lb, grid, smem);
+        if (k.pxt == 32 && k.bty == 16) return ptv_launch_lb<MODE, K, false, true, 32, 16>(ctx, st, k, maps, lb, grid, smem);
+        if (k.pxt == 16 && k.bty == 32) return ptv_launch_lb<MODE, K, false, true, 16, 32>(ctx, st, k, maps, lb, grid, smem);
+    }
+    return ptv_launch_lb<MODE, K, false, true, 0, 0>(ctx, st, k, maps, lb, grid, smem);
+}
+
+// tma: the staging ring is filled by the TMA unit (plain launches on a device); otherwise by plain loads (slab-interface
+// chunks, whose first / last planes live in a neighbour's memory, and the host emulation of the library)
+template <int MODE>
+int ptv_launch_m(ns3d_ctx* ctx, cudaStream_t st, const PtV& k, const PtvMaps& maps, const PtvPlan& pl, int K, bool p2p, bool tma,
+                 dim3 grid, size_t smem)
+{
+    if (p2p) {
+        if (K == 1) return ptv_launch_lb<MODE, 1, true, false, 0, 0>(ctx, st, k, maps, pl.lb, grid, smem);
+        return ptv_launch_lb<MODE, 2, true, false, 0, 0>(ctx, st, k, maps, pl.lb, grid, smem);
+    }
+#ifndef NS3D_HOST_EMU
+    if (tma) {
+        if (K == 1) return ptv_launch_shape<MODE, 1>(ctx, st, k, maps, pl.lb, grid, smem);
+        if (K == 2) return ptv_launch_shape<MODE, 2>(ctx, st, k, maps, pl.lb, grid, smem);
+        return ptv_launch_shape<MODE, 3>(ctx, st, k, maps, pl.lb, grid, smem);
+    }
+#endif
+    if (K == 1) return ptv_launch_lb<MODE, 1, false, false, 0, 0>(ctx, st, k, maps, pl.lb, grid, smem);
+    if (K == 2) return ptv_launch_lb<MODE, 2, false, false, 0, 0>(ctx, st, k, maps, pl.lb, grid, smem);
+    return ptv_launch_lb<MODE, 3, false, false, 0, 0>(ctx, st, k, maps, pl.lb, grid, smem);
+}
+
+}  // namespace

@@ -19,9 +19,9 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "navierstokes3d_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libns3d_emu.so")
-SOURCES = ["ns3d_core.cu", "ns3d_ops.cu", "ns3d_pt.cu", "ns3d_out.cu"]
+SOURCES = ["ns3d_core.cu", "ns3d_ops.cu", "ns3d_pt.cu", "ns3d_ptv.cu", "ns3d_ptv_mode0.cu", "ns3d_ptv_mode1.cu", "ns3d_ptv_mode2.cu", "ns3d_out.cu"]
 # kernels that synchronise (__syncthreads, named barriers, warp shuffles): one host thread per CUDA thread
-THREADED = ("pt_tb2_kernel", "pt_tb2s_kernel", "pt_tb2sp_kernel", "pt_tb2d_kernel", "pt_residual_kernel", "max_abs_kernel")
+THREADED = ("ptv_kernel_fn", "ptv_residual_kernel", "pt_tb2_kernel", "pt_tb2s_kernel", "pt_tb2sp_kernel", "pt_tb2d_kernel", "pt_residual_kernel", "max_abs_kernel")
 
 
 def _match_back_template(s: str, end: int) -> int:
@@ -120,7 +120,14 @@ def build(force: bool = False) -> str:
     for name in SOURCES:
         cpp = os.path.join(OUT, name.replace(".cu", "_emu.cpp"))
         with open(os.path.join(CSRC, name)) as fh:
-            text = rewrite_launches(fh.read())
+            text = fh.read()
+        # headers that launch kernels themselves (ns3d_ptv_launch.cuh) are inlined so that their launches are rewritten too
+        for inc in re.findall(r'#include "(\w+\.cuh)"', text):
+            with open(os.path.join(CSRC, inc)) as fh:
+                body = fh.read()
+            if "<<<" in body:
+                text = text.replace(f'#include "{inc}"', body.replace("#pragma once", ""))
+        text = rewrite_launches(text)
         with open(cpp, "w") as fh:
             fh.write(f'#line 1 "{os.path.join(CSRC, name)}"\n' + text)
         obj = cpp[:-4] + ".o"

@@ -86,6 +86,16 @@ inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v)
 namespace emu {
 
 inline void spin_pause() { sched_yield(); }
+inline unsigned long long wall_ns()
+{
+    return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+// dynamic shared memory (`extern __shared__`): blocks run one after the other, so one buffer serves them all
+inline void* dyn_smem()
+{
+    alignas(16) static char buf[1 << 20];
+    return buf;
+}
 
 // `bar.sync id, count` (PTX named barrier): every participating thread passes the same count.
 inline void named_barrier(int id, int count)

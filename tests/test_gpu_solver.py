@@ -65,6 +65,50 @@ def test_fused_iteration_bit_exact(O, ns, ctx, variant, grid, zchunk):
             assert (got == f[name]).all(), f"{name} differs after {done} iterations ({(got != f[name]).sum()} values)"
 
 
+PTV_CONFIGS = {
+    # name: options of the pitched-layout kernel (ptv_kernel): iterations per launch, launch-bounds variant,
+    # thread columns / rows of a tile (0 = chosen by the library), staging slots, TMA or plain-load staging
+    "auto": {},
+    "k1": {"ptv_k": 1},
+    "k2_lb0": {"ptv_k": 2, "ptv_lb": 0},
+    "k2_lb4_ns3": {"ptv_k": 2, "ptv_lb": 4, "ptv_ns": 3},
+    "k3_lb0": {"ptv_k": 3, "ptv_lb": 0, "ptv_ns": 5},
+    "k2_tiles": {"ptv_k": 2, "ptv_pxt": 5, "ptv_bty": 6},      # several small tiles in x and y
+    "k3_tiles": {"ptv_k": 3, "ptv_pxt": 6, "ptv_bty": 7},
+    "k2_coop_nographs": {"ptv_k": 2, "ptv_tma": 0, "graphs": 0, "serpentine": 1},
+    "k1_coop_tiles": {"ptv_k": 1, "ptv_tma": 0, "ptv_pxt": 4, "ptv_bty": 3},
+}
+
+
+@pytest.mark.parametrize("variant", ["M", "G"])
+@pytest.mark.parametrize("grid", [(3, 3, 3), (5, 4, 3), (4, 3, 6), (16, 9, 8), (37, 23, 19), (63, 38, 38), (70, 47, 41)])
+@pytest.mark.parametrize("zchunk", [0, 1, 2, 7])
+@pytest.mark.parametrize("cfg", sorted(PTV_CONFIGS))
+def test_ptv_kernel_bit_exact(O, ns, ctx, variant, grid, zchunk, cfg):
+    """The default fused loop: ptv_kernel, K PT iterations per launch on the library's pitched copies (two columns
+    per thread, 128-bit accesses, K-stage pipeline over z with the intermediate iterates in registers and shared
+    memory).  Same per-cell arithmetic as the reference's K5 + K6 + set_bc_Pr! -> bit-equal to the oracle for every
+    K, rows per thread, tile shape (one tile, several tiles with rims, even and odd nx) and chunking; counts that
+    are not multiples of K end with shorter launches; 40 iterations replay a captured CUDA graph."""
+    p, f = pt_problem(O, variant, grid, 15)
+    s = setup_for(ns, variant, grid[0], ny=grid[1], nz=grid[2])
+    for name, val in PTV_CONFIGS[cfg].items():
+        ctx.set_option(name, val)
+    d = {k: ctx.from_host(f[k]) for k in ("Pr", "dPrdtau", "divV")}
+    done = 0
+    for n in (2, 1, 5, 40):
+        ctx.pt_iterate(d["Pr"], d["dPrdtau"], d["divV"], s.pt_params(zchunk), n)
+        for _ in range(n):
+            O.update_dPrdtau(p, f)
+            O.update_Pr(p, f)
+            O.set_bc_Pr(p, f)
+        done += n
+        for name in ("Pr", "dPrdtau"):
+            got = d[name].to_host()
+            bad = np.argwhere(got != f[name])
+            assert len(bad) == 0, f"{name} differs after {done} iterations: {len(bad)} values, first {bad[:3].tolist()}"
+
+
 CANDIDATES = pytest.mark.skipif(not os.environ.get("NS3D_TEST_CANDIDATES"),
                                 reason="round-2 candidate kernels (emulation-verified, not yet run on a device): "
                                        "set NS3D_TEST_CANDIDATES=1")
@@ -84,6 +128,7 @@ def test_two_iterations_per_launch_bit_exact(O, ns, ctx, variant, grid, zchunk, 
     instantiations, and the first version pt_tb2_kernel (still the one on slab interfaces)."""
     p, f = pt_problem(O, variant, grid, 15)
     s = setup_for(ns, variant, grid[0], ny=grid[1], nz=grid[2])
+    ctx.set_option("ptv", 0)
     ctx.set_option("tb2", 1)
     for name, val in {"tb2s_auto": {}, "tb2s_16_nopf": {"tb2_ty": 16, "tb2_pf": 0, "tb2_np": 0},
                       "tb2s_8_pf2": {"tb2_ty": 8, "tb2_pf": 2}, "tb2_first": {"tb2_slim": 0, "tb2_ty": 16},
