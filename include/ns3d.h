@@ -100,6 +100,24 @@ NS3D_API long long ns3d_launch_count(const ns3d_ctx* ctx);
 /* The context's CUDA stream (a cudaStream_t), so callers can record events on it. */
 NS3D_API void* ns3d_stream(ns3d_ctx* ctx);
 
+/* Device-side initialisers.  The scripts build their initial arrays on the host and upload them:
+ *   G:86   Vx = [vin*(7/6)*((zc[iz]+lz/2)/lz)^(1/6) + 0*yc[iy] + 0*xv[ix] ...]   G:87 / M:370   Pr = [-(z - ..)*ρ*g ...]
+ *   M:369  Vy[1,:,:] .= vin
+ * Every comprehension depends on iz alone: ns3d_fill_profile_z sets A[ix,iy,iz] = h_profile[iz] from sz host values
+ * (the power law's `^(1/6)` is evaluated on the host, whose libm CUDA's pow does not match to the last bit), and
+ * ns3d_fill_plane_x sets A[ix,:,:] = value (ix 0-based).  No 3-D array exists on the host.                        */
+NS3D_API int ns3d_fill_profile_z(ns3d_ctx* ctx, double* A, int sx, int sy, int sz, const double* h_profile);
+NS3D_API int ns3d_fill_plane_x(ns3d_ctx* ctx, double* A, int sx, int sy, int sz, int ix, double value);
+/* Asynchronous host <-> device copies for a driver that overlaps the traffic of one time step with the computation
+ * of another (the reference's `Data.Array(x)` / `Array(A)` are blocking; nothing in it corresponds to these).  Uploads
+ * run on the context's upload stream, downloads on its download stream; host buffers must be page-locked and stay
+ * valid until the copy has completed.  ns3d_stream_wait(ctx, waiter, signaller) makes everything enqueued on `waiter`
+ * from now on wait for what has been enqueued on `signaller` so far; ns3d_stream_sync blocks the host.            */
+enum { NS3D_STREAM_COMPUTE = 0, NS3D_STREAM_H2D = 1, NS3D_STREAM_D2H = 2 };
+NS3D_API int ns3d_h2d_async(ns3d_ctx* ctx, double* dptr, const double* h_pinned_src, size_t count);
+NS3D_API int ns3d_d2h_async(ns3d_ctx* ctx, double* h_pinned_dst, const double* dptr, size_t count);
+NS3D_API int ns3d_stream_wait(ns3d_ctx* ctx, int waiter, int signaller);
+NS3D_API int ns3d_stream_sync(ns3d_ctx* ctx, int which);
 /* ---- device field allocator  (replaces @zeros M:343-360, Data.Array M:370, Array() M:399) */
 NS3D_API int ns3d_zeros(ns3d_ctx* ctx, int sx, int sy, int sz, double** dptr);
 NS3D_API int ns3d_free(ns3d_ctx* ctx, double* dptr);

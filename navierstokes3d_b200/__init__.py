@@ -6,7 +6,7 @@ The product is ``csrc/libns3d.so`` (hand-written CUDA kernels behind the C ABI o
 reference's run-script surface (``driver.run_navierstokes3D``, ``driver.runme``).
 """
 from . import native, params  # noqa: F401
-from .driver import Simulation, run_navierstokes3D, runme  # noqa: F401
+from .driver import Simulation, StreamedSteps, run_navierstokes3D, runme  # noqa: F401
 from .native import FAST, FASTEST, PARITY, VARIANT_G, VARIANT_M, Context, NS3DError  # noqa: F401
 from .params import Physics, Setup, SlabGrid, setup_gpu, setup_multi_gpu  # noqa: F401
 

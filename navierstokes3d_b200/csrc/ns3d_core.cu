@@ -65,6 +65,9 @@ extern "C" int ns3d_create(int device, ns3d_ctx** out)
     CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CREATE_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, lo));
     CREATE_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_xfer, cudaEventDisableTiming));
     CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
     CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
     CREATE_CUDA(cudaMalloc(&ctx->d_maxbits, 64 * sizeof(unsigned long long)));
@@ -130,7 +133,6 @@ extern "C" int ns3d_destroy(ns3d_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->comm_stream);
-    ns3d_internal_pt_free_graphs(ctx);
     ns3d_internal_ptv_release(ctx);
     ns3d_internal_out_free(ctx);
     for (auto& kv : ctx->p2p_map) {
@@ -142,18 +144,13 @@ extern "C" int ns3d_destroy(ns3d_ctx* ctx)
     if (ctx->mbox) cudaFree(ctx->mbox);
     if (ctx->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl);
     for (auto& kv : ctx->allocs) cudaFree(kv.first);
-    if (ctx->pr_shadow) cudaFree(ctx->pr_shadow);
-    if (ctx->dp_shadow) cudaFree(ctx->dp_shadow);
     cudaFree(ctx->d_maxbits);
     cudaFreeHost(ctx->h_maxbits);
-    for (int b = 0; b < ns3d_ctx::MAX_BANDS; ++b) {
-        if (ctx->band_stream[b]) cudaStreamDestroy(ctx->band_stream[b]);
-        for (int q = 0; q < 2; ++q)
-            if (ctx->band_ev[q][b]) cudaEventDestroy(ctx->band_ev[q][b]);
-    }
-    if (ctx->band_fork) cudaEventDestroy(ctx->band_fork);
     cudaEventDestroy(ctx->ev_a);
     cudaEventDestroy(ctx->ev_b);
+    if (ctx->ev_xfer) cudaEventDestroy(ctx->ev_xfer);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->comm_stream);
     delete ctx;
@@ -172,20 +169,9 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
 {
     NS3D_CHECK_CTX(ctx);
     if (!name) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_set_option: NULL name");
-    if (!strcmp(name, "pt_minb")) {
-        if (value != 0 && (value < 3 || value > 6)) return ns3d_fail(ctx, NS3D_EINVAL, "pt_minb must be 0 (auto) or 3..6");
-        ctx->opt_pt_minb = value;
-        return NS3D_OK;
-    }
-    if (!strcmp(name, "p2p_halo")) {
-        ctx->opt_p2p = value != 0;
-        return NS3D_OK;
-    }
-    if (!strcmp(name, "tb2")) {
-        ctx->opt_tb2 = value != 0;
-        return NS3D_OK;
-    }
-    if (!strcmp(name, "ptv")) { ctx->opt_ptv = value != 0; return NS3D_OK; }
+    // the peer-memory halo path of the fused loop on z-slabs (0: NCCL send/recv after every iteration)
+    if (!strcmp(name, "p2p_halo")) { ctx->opt_p2p = value != 0; return NS3D_OK; }
+    // ptv_kernel: PT iterations per launch (0 = default 2; z-slabs: at most 2)
     if (!strcmp(name, "ptv_k")) {
         if (value < 0 || value > 3) return ns3d_fail(ctx, NS3D_EINVAL, "ptv_k must be 0 (default) .. 3");
         ctx->opt_ptv_k = value;
@@ -198,62 +184,14 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
     }
     if (!strcmp(name, "ptv_tma")) { ctx->opt_ptv_tma = value != 0; return NS3D_OK; }
     if (!strcmp(name, "ptv_lb")) {
-        if (value < -1 || value > 4) return ns3d_fail(ctx, NS3D_EINVAL, "ptv_lb must be -1 (default) or 0 .. 4");
+        if (value < -1 || value > 4 || value == 2) return ns3d_fail(ctx, NS3D_EINVAL, "ptv_lb must be -1 (default), 0, 1, 3 or 4");
         ctx->opt_ptv_lb = value;
         return NS3D_OK;
     }
     if (!strcmp(name, "ptv_pxt")) { ctx->opt_ptv_pxt = value < 0 ? 0 : value; return NS3D_OK; }
     if (!strcmp(name, "ptv_bty")) { ctx->opt_ptv_bty = value < 0 ? 0 : value; return NS3D_OK; }
-    if (!strcmp(name, "tb2_ty")) {
-        if (value != 0 && value != 8 && value != 16 && value != 32)
-            return ns3d_fail(ctx, NS3D_EINVAL, "tb2_ty must be 0 (auto), 8, 16 or 32");
-        ctx->opt_tb2_ty = value;
-        return NS3D_OK;
-    }
-    if (!strcmp(name, "tb2_pf")) {
-        if (value < 0 || value > 2) return ns3d_fail(ctx, NS3D_EINVAL, "tb2_pf must be 0, 1 or 2");
-        ctx->opt_tb2_pf = value;
-        return NS3D_OK;
-    }
-    if (!strcmp(name, "tb2_np")) {
-        ctx->opt_tb2_np = value != 0;
-        return NS3D_OK;
-    }
-    if (!strcmp(name, "pt_bands")) {
-        if (value != 0 && (value < 2 || value > ns3d_ctx::MAX_BANDS))
-            return ns3d_fail(ctx, NS3D_EINVAL, "pt_bands must be 0 or 2..%d", ns3d_ctx::MAX_BANDS);
-        ctx->opt_pt_bands = value;
-        return NS3D_OK;
-    }
-    if (!strcmp(name, "tb2_slim_faces")) {
-        ctx->opt_tb2_slim_faces = value != 0;
-        return NS3D_OK;
-    }
-    if (!strcmp(name, "tb2_pairbar")) {
-        ctx->opt_tb2_pb = value != 0;
-        return NS3D_OK;
-    }
-    if (!strcmp(name, "tb2_dual")) {
-        if (value != 0 && value != 2) return ns3d_fail(ctx, NS3D_EINVAL, "tb2_dual must be 0 or 2 (CTAs per SM)");
-        ctx->opt_tb2_dual = value;
-        return NS3D_OK;
-    }
-    if (!strcmp(name, "tb2_spec")) {
-        ctx->opt_tb2_spec = value != 0;
-        return NS3D_OK;
-    }
-    if (!strcmp(name, "tb2_slim")) {
-        ctx->opt_tb2_slim = value != 0;
-        return NS3D_OK;
-    }
-    if (!strcmp(name, "graphs")) {
-        ctx->opt_graphs = value != 0;
-        return NS3D_OK;
-    }
-    if (!strcmp(name, "serpentine")) {
-        ctx->opt_serpentine = value < 0 ? -1 : (value != 0);
-        return NS3D_OK;
-    }
+    if (!strcmp(name, "graphs")) { ctx->opt_graphs = value != 0; return NS3D_OK; }
+    if (!strcmp(name, "serpentine")) { ctx->opt_serpentine = value < 0 ? -1 : (value != 0); return NS3D_OK; }
     return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_set_option: unknown option '%s'", name);
 }
 
@@ -265,6 +203,8 @@ extern "C" int ns3d_sync(ns3d_ctx* ctx)
     NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
     NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
     NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->h2d_stream));
+    NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
     return NS3D_OK;
 }
 
@@ -304,8 +244,8 @@ extern "C" int ns3d_free(ns3d_ctx* ctx, double* dptr)
     NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
     NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
-    // nothing may keep the pointer: captured graphs of the fused loop and peer mappings of this block go first
-    ns3d_internal_pt_free_graphs(ctx);
+    // nothing may keep the pointer: peer mappings of this block go first (the fused loop's graphs only hold
+    // context-owned buffers)
     auto pm = ctx->p2p_map.find((const void*)dptr);
     if (pm != ctx->p2p_map.end()) {
         if (pm->second.first) cudaIpcCloseMemHandle(pm->second.first);
@@ -338,6 +278,51 @@ extern "C" int ns3d_d2h(ns3d_ctx* ctx, double* h_dst, const double* dptr, size_t
     return NS3D_OK;
 }
 
+// ---- asynchronous host <-> device copies on their own streams (a driver that overlaps them with time steps) ----
+static cudaStream_t xfer_stream(ns3d_ctx* ctx, int which)
+{
+    return which == NS3D_STREAM_COMPUTE ? ctx->stream : (which == NS3D_STREAM_H2D ? ctx->h2d_stream : (which == NS3D_STREAM_D2H ? ctx->d2h_stream : nullptr));
+}
+
+extern "C" int ns3d_h2d_async(ns3d_ctx* ctx, double* dptr, const double* h_pinned_src, size_t count)
+{
+    NS3D_CHECK_CTX(ctx);
+    if (!dptr || !h_pinned_src) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_h2d_async: NULL pointer");
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    NS3D_CUDA(ctx, cudaMemcpyAsync(dptr, h_pinned_src, count * sizeof(double), cudaMemcpyHostToDevice, ctx->h2d_stream));
+    return NS3D_OK;
+}
+
+extern "C" int ns3d_d2h_async(ns3d_ctx* ctx, double* h_pinned_dst, const double* dptr, size_t count)
+{
+    NS3D_CHECK_CTX(ctx);
+    if (!dptr || !h_pinned_dst) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_d2h_async: NULL pointer");
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    NS3D_CUDA(ctx, cudaMemcpyAsync(h_pinned_dst, dptr, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    return NS3D_OK;
+}
+
+extern "C" int ns3d_stream_wait(ns3d_ctx* ctx, int waiter, int signaller)
+{
+    NS3D_CHECK_CTX(ctx);
+    cudaStream_t w = xfer_stream(ctx, waiter), s = xfer_stream(ctx, signaller);
+    if (!w || !s || w == s) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_stream_wait: bad stream ids %d, %d", waiter, signaller);
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    NS3D_CUDA(ctx, cudaEventRecord(ctx->ev_xfer, s));
+    NS3D_CUDA(ctx, cudaStreamWaitEvent(w, ctx->ev_xfer, 0));
+    return NS3D_OK;
+}
+
+extern "C" int ns3d_stream_sync(ns3d_ctx* ctx, int which)
+{
+    NS3D_CHECK_CTX(ctx);
+    cudaStream_t s = xfer_stream(ctx, which);
+    if (!s) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_stream_sync: bad stream id %d", which);
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    NS3D_CUDA(ctx, cudaStreamSynchronize(s));
+    return NS3D_OK;
+}
+
 extern "C" int ns3d_copy(ns3d_ctx* ctx, double* dst, const double* src, size_t count)
 {
     NS3D_CHECK_CTX(ctx);
@@ -357,6 +342,56 @@ extern "C" int ns3d_fill(ns3d_ctx* ctx, double* dptr, double value, size_t count
     NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned blocks = (unsigned)std::min<size_t>((count + 255) / 256, (size_t)ctx->num_sms * 16);
     fill_kernel<<<blocks ? blocks : 1, 256, 0, ctx->stream>>>(dptr, value, count);
+    NS3D_LAUNCH_CHECK(ctx);
+    return NS3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-side initialisers: the scripts build their initial 3-D arrays on the host
+// with comprehensions (G:86-87, M:370) and upload them; every one of them depends on z alone, so the
+// host computes the nz profile values (the power law of G:86 uses `^(1/6)`, which CUDA's pow does not
+// round like the host's libm -- it stays on the host) and the device broadcasts them.
+// ---------------------------------------------------------------------------------------------
+__global__ void fill_profile_z_kernel(double* __restrict__ a, const double* __restrict__ prof, size_t sxy, size_t n)
+{
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) a[q] = prof[q / sxy];
+}
+
+__global__ void fill_plane_x_kernel(double* __restrict__ a, int sx, int ix, double v, size_t nyz)
+{
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < nyz; q += (size_t)gridDim.x * blockDim.x)
+        a[(size_t)ix + (size_t)sx * q] = v;
+}
+
+extern "C" int ns3d_fill_profile_z(ns3d_ctx* ctx, double* A, int sx, int sy, int sz, const double* h_profile)
+{
+    NS3D_CHECK_CTX(ctx);
+    if (!A || !h_profile || sx <= 0 || sy <= 0 || sz <= 0) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_fill_profile_z: bad argument");
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* d_prof = nullptr;
+    NS3D_CUDA(ctx, cudaMalloc(&d_prof, (size_t)sz * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d_prof, h_profile, (size_t)sz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        const size_t n = (size_t)sx * sy * sz;
+        const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->num_sms * 16);
+        fill_profile_z_kernel<<<blocks, 256, 0, ctx->stream>>>(A, d_prof, (size_t)sx * sy, n);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // h_profile may go away; d_prof is freed below
+    cudaFree(d_prof);
+    if (e != cudaSuccess) return ns3d_fail(ctx, NS3D_ECUDA, "ns3d_fill_profile_z failed: %s", cudaGetErrorString(e));
+    return NS3D_OK;
+}
+
+extern "C" int ns3d_fill_plane_x(ns3d_ctx* ctx, double* A, int sx, int sy, int sz, int ix, double value)
+{
+    NS3D_CHECK_CTX(ctx);
+    if (!A || sx <= 0 || sy <= 0 || sz <= 0 || ix < 0 || ix >= sx) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_fill_plane_x: bad argument");
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nyz = (size_t)sy * sz;
+    const unsigned blocks = (unsigned)std::min<size_t>((nyz + 255) / 256, (size_t)ctx->num_sms * 16);
+    fill_plane_x_kernel<<<blocks, 256, 0, ctx->stream>>>(A, sx, ix, value, nyz);
     NS3D_LAUNCH_CHECK(ctx);
     return NS3D_OK;
 }

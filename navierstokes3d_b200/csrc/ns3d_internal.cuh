@@ -21,22 +21,15 @@ struct ns3d_ctx {
     cudaStream_t stream = nullptr;       // all operators run here
     cudaStream_t comm_stream = nullptr;  // halo exchange, overlapped with interior compute
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
-    // z-band pipelining of the two-iteration launches (option "pt_bands", candidate): one stream per
-    // band, events [launch parity][band], created on first use
-    static const int MAX_BANDS = 8;
-    cudaStream_t band_stream[MAX_BANDS] = {};
-    cudaEvent_t band_ev[2][MAX_BANDS] = {};
-    cudaEvent_t band_fork = nullptr;
-    int bands_ready = 0;
+    // copy engines beside the compute stream: asynchronous uploads / downloads of a driver that pipelines
+    // host <-> device traffic with the time steps (ns3d_h2d_async, ns3d_d2h_async, ns3d_stream_wait)
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_xfer = nullptr;
     long long launches = 0;
     std::string err;
     std::unordered_map<void*, size_t> allocs;
     size_t bytes = 0;
     // scratch owned by the context
-    double* pr_shadow = nullptr;  // ping-pong partner of Pr in the fused PT loop
-    size_t pr_shadow_count = 0;
-    double* dp_shadow = nullptr;  // ping-pong partner of dPrdtau (two-iterations-per-launch path)
-    size_t dp_shadow_count = 0;
     void* out_stage = nullptr;    // device staging of the output path (ns3d_box_d2h)
     size_t out_stage_bytes = 0;
     void* gather_stage = nullptr;  // rank 0: where the ranks' boxes land (ns3d_gather_box)
@@ -54,29 +47,15 @@ struct ns3d_ctx {
     std::unordered_map<const void*, std::pair<void*, void*>> p2p_map;  // local base -> (lower, upper) peer base
     int opt_p2p = 1;
     // tuning knobs (ns3d_set_option)
-    int opt_pt_minb = 0;  // 0 = per-mode default
     int opt_serpentine = -1;  // -1 = by working-set size
-    int opt_tb2 = 1;          // two PT iterations per launch (pt_tb2_kernel); 0 = one-iteration kernel only
-    int opt_tb2_ty = 0;       // tile height of the two-iteration kernels (8, 16 or 32; 0 = by grid size)
-    int opt_tb2_pf = 1;       // pt_tb2s_kernel: planes of software prefetch into L2 ahead of the register prefetch (0..2)
-    int opt_tb2_np = 1;       // pt_tb2s_kernel: in-plane neighbours of the next plane loaded one step ahead
-    int opt_tb2_spec = 1;     // pt_tb2s_kernel: use the compile-time-stride instantiation when the grid has one
-    int opt_pt_bands = 0;     // >= 2: split every two-iteration launch into that many z-bands with band-to-band
-                              // dependencies, so that launch n+1 starts while launch n drains (candidate, single rank)
-    int opt_tb2_slim_faces = 0;  // slab-interface chunks with pt_tb2sp_kernel instead of pt_tb2_kernel<.,16,true> (candidate)
-    int opt_tb2_pb = 0;       // pt_tb2s_kernel: pairwise row barriers instead of __syncthreads (candidate)
-    int opt_tb2_dual = 0;     // pt_tb2d_kernel (two tile rows per thread) for plain launches: 0 off, 2 = CTAs per SM
-    int opt_tb2_slim = 1;     // plain two-iteration launches use pt_tb2s_kernel (0 = pt_tb2_kernel)
     int opt_graphs = 1;       // replay chunks of PT iterations as CUDA graphs
     long long halo_calls = 0; // uncaptured halo exchanges so far (NCCL peers connected)
-    void* pt_graphs = nullptr;  // graph cache owned by ns3d_pt.cu
     // the fused loop's pitched working copies (ns3d_ptv.cu): Pr x2, dPrdtau x2 (ping-pong), divV
     double* ptv_raw[5] = {};    // cudaMalloc blocks
     double* ptv[5] = {};        // element (0,0,0) inside them (front padding skipped)
     int ptv_nx = 0, ptv_ny = 0, ptv_nz = 0;
     bool ptv_peers_mapped = false;
     void* ptv_graphs = nullptr;  // graph cache owned by ns3d_ptv.cu
-    int opt_ptv = 1;          // the fused loop runs ptv_kernel on the pitched copies (0 = the round-1 kernels on the caller's arrays)
     int opt_ptv_k = 0;        // PT iterations per launch (0 = default)
     int opt_ptv_ns = 0;       // staging slots of the TMA ring (0 = default 4; >= 3)
     int opt_ptv_tma = 1;      // stage the z-plane tiles with the TMA unit (0 = plain loads by all threads)
@@ -154,7 +133,6 @@ __device__ __forceinline__ void block_max_to_global(unsigned long long v, unsign
 
 // internal cross-TU entry points
 int ns3d_internal_p2p_map(ns3d_ctx* ctx, const void* local_base, void** peer_lo, void** peer_hi);
-void ns3d_internal_pt_free_graphs(ns3d_ctx* ctx);
 void ns3d_internal_ptv_free(ns3d_ctx* ctx);     // graph cache of ns3d_ptv.cu
 void ns3d_internal_ptv_release(ns3d_ctx* ctx);  // ... and its buffers
 int ns3d_internal_ptv_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const double* divV, const ns3d_pt_params* p, int* h_iters,

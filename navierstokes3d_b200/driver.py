@@ -52,6 +52,19 @@ def initial_host_fields(s: Setup) -> dict:
     return out
 
 
+def initial_profiles(s: Setup) -> dict:
+    """The z-profiles behind ``initial_host_fields`` -- every initial array of the scripts depends on iz alone:
+    ``{"Pr": nz values}`` (M:370) or ``{"Vx": ..., "Pr": ...}`` (G:86-87).  The ``+ 0*yc[iy] + 0*xv[ix]`` terms of
+    the comprehensions are kept (they turn a -0.0 into +0.0)."""
+    nz = s.nz
+    zc = _linrange(-(s.lz - s.dz) / 2, (s.lz - s.dz) / 2, nz)
+    if s.variant == native.VARIANT_M:
+        zg = np.array([s.grid.x_g(iz, s.dz, nz, 2) for iz in range(1, nz + 1)])
+        return {"Pr": (-(zg - s.dz / 2) * s.rho * s.g) + 0.0 + 0 * zc}
+    prof = s.vin * (7.0 / 6.0) * np.power((zc + s.lz / 2) / s.lz, 1.0 / 6.0)      # host pow: the reference's `^`
+    return {"Vx": prof + 0.0 + 0.0, "Pr": (-(zc - s.lz / 2) * s.rho * s.g) + 0.0 + 0.0}
+
+
 class Simulation:
     """Device state of one rank + the time step."""
 
@@ -65,9 +78,15 @@ class Simulation:
         self.ctx = ctx
         self.zchunk = zchunk
         self.f = {name: ctx.zeros(*shape) for name, shape in setup.shapes().items()}   # M:343-360
-        init = initial_host_fields(setup) if host_fields is None else host_fields
-        for name, arr in init.items():
-            self.f[name].set(arr)
+        if host_fields is None:
+            # device-side initialisers: nz profile values cross PCIe, not 3-D arrays (M:369-370 / G:86-87)
+            for name, prof in initial_profiles(setup).items():
+                ctx.fill_profile_z(self.f[name], prof)
+            if setup.variant == native.VARIANT_M:
+                ctx.fill_plane_x(self.f["Vy"], 0, setup.vin)                          # M:369 (sic: Vy)
+        else:
+            for name, arr in host_fields.items():
+                self.f[name].set(arr)
         if host_fields is None:
             if setup.variant == native.VARIANT_M:
                 self.update_halo("Pr")                                                 # M:371
@@ -191,6 +210,53 @@ class Simulation:
         sx, sy, sz = a.shape
         j = -(-self.s.ny // 2)
         return self.ctx.box(a, (1, sx - 1), (j, j + 1), (1, sz - 1), dtype)[:, 0, :]
+
+
+class StreamedSteps:
+    """Time steps fed from and drained to HOST memory every step, with the traffic hidden behind the computation.
+
+    Two sets of device fields on one context: while step n computes on one set, the input state of step n+1 is
+    uploaded into the other (``ns3d_h2d_async``, the context's upload stream) and the result of step n-1 is
+    downloaded from it (``ns3d_d2h_async``, the download stream); ``ns3d_stream_wait`` orders the three streams.
+    Host buffers must be page-locked: ``inputs`` / ``outputs`` map field names to ``(address, count)``.
+    Nothing in the reference corresponds to this (its ``Data.Array(x)`` / ``Array(A)`` are blocking); it is what
+    bench.py's end-to-end leg calls."""
+
+    def __init__(self, setup: Setup, ctx: native.Context, zchunk: int = 0):
+        self.ctx = ctx
+        self.sims = [Simulation(setup, ctx, zchunk=zchunk), Simulation(setup, ctx, zchunk=zchunk)]
+
+    def run(self, steps: int, inputs: dict, outputs: dict):
+        c, N = self.ctx, native
+        results = []
+
+        def upload(sim):
+            for name, (addr, count) in inputs.items():
+                c.h2d_async(sim.f[name].ptr, addr, count)
+
+        def download(sim):
+            for name, (addr, count) in outputs.items():
+                c.d2h_async(addr, sim.f[name].ptr, count)
+
+        c.stream_wait(N.STREAM_H2D, N.STREAM_COMPUTE)      # whatever still computes on set 0 finishes first
+        upload(self.sims[0])
+        for n in range(steps):
+            cur, nxt = self.sims[n % 2], self.sims[(n + 1) % 2]
+            c.stream_wait(N.STREAM_COMPUTE, N.STREAM_H2D)  # the input of this step has arrived
+            if n + 1 < steps:
+                c.stream_wait(N.STREAM_H2D, N.STREAM_D2H)  # the other set's previous result has left
+                upload(nxt)                                # ... and its next input travels while this step computes
+            results.append(cur.step())
+            c.stream_wait(N.STREAM_D2H, N.STREAM_COMPUTE)  # corrector and advection of this step are done
+            download(cur)
+        c.stream_sync(N.STREAM_H2D)
+        c.stream_sync(N.STREAM_D2H)
+        return results
+
+    def close(self):
+        for sim in self.sims:
+            for a in sim.f.values():
+                self.ctx.free(a)
 
 
 def _dist_env():

@@ -14,6 +14,7 @@ import numpy as np
 from . import build as _build
 
 PARITY, FAST, FASTEST = 0, 1, 2
+STREAM_COMPUTE, STREAM_H2D, STREAM_D2H = 0, 1, 2
 VARIANT_M, VARIANT_G = 0, 1
 
 c_double_p = C.POINTER(C.c_double)
@@ -78,6 +79,12 @@ SIGNATURES = {
     "ns3d_h2d": (_I, [_P, _P, _P, _Z]),
     "ns3d_d2h": (_I, [_P, _P, _P, _Z]),
     "ns3d_copy": (_I, [_P, _P, _P, _Z]),
+    "ns3d_fill_profile_z": (_I, [_P, _P, _I, _I, _I, c_double_p]),
+    "ns3d_fill_plane_x": (_I, [_P, _P, _I, _I, _I, _I, _D]),
+    "ns3d_h2d_async": (_I, [_P, _P, _P, _Z]),
+    "ns3d_d2h_async": (_I, [_P, _P, _P, _Z]),
+    "ns3d_stream_wait": (_I, [_P, _I, _I]),
+    "ns3d_stream_sync": (_I, [_P, _I]),
     "ns3d_fill": (_I, [_P, _P, _D, _Z]),
     "ns3d_bytes_allocated": (_Z, [_P]),
     "ns3d_update_tau": (_I, [_P] + [_P] * 9 + [_D] * 4 + [_I] * 3),
@@ -290,11 +297,37 @@ class Context:
                                           int(dtype == np.dtype(np.float32))), "ns3d_gather_box")
         return out
 
+    # -- asynchronous copies on the context's upload / download streams (pinned host memory) -----------
+    def h2d_async(self, dst_ptr: int, host_ptr: int, count: int):
+        self._ck(self.lib.ns3d_h2d_async(self.h, dst_ptr, host_ptr, count), "ns3d_h2d_async")
+
+    def d2h_async(self, host_ptr: int, src_ptr: int, count: int):
+        self._ck(self.lib.ns3d_d2h_async(self.h, host_ptr, src_ptr, count), "ns3d_d2h_async")
+
+    def stream_wait(self, waiter: int, signaller: int):
+        """Everything enqueued on stream ``waiter`` from now on waits for what ``signaller`` holds so far."""
+        self._ck(self.lib.ns3d_stream_wait(self.h, waiter, signaller), "ns3d_stream_wait")
+
+    def stream_sync(self, which: int):
+        self._ck(self.lib.ns3d_stream_sync(self.h, which), "ns3d_stream_sync")
+
     def d2h_raw(self, host_ptr: int, src_ptr: int, count: int):
         self._ck(self.lib.ns3d_d2h(self.h, host_ptr, src_ptr, count), "ns3d_d2h")
 
     def from_host(self, host: np.ndarray) -> DeviceArray:
         return self.zeros(*host.shape).set(host)
+
+    def fill_profile_z(self, a: DeviceArray, profile: np.ndarray):
+        """``A[ix,iy,iz] = profile[iz]``: the scripts' z-dependent initial arrays (G:86-87, M:370), built on the device."""
+        prof = np.ascontiguousarray(profile, dtype=np.float64)
+        if prof.shape != (a.shape[2],):
+            raise NS3DError(f"fill_profile_z: {prof.shape} values for {a.shape[2]} planes")
+        self._ck(self.lib.ns3d_fill_profile_z(self.h, a.ptr, a.shape[0], a.shape[1], a.shape[2],
+                                              prof.ctypes.data_as(c_double_p)), "ns3d_fill_profile_z")
+
+    def fill_plane_x(self, a: DeviceArray, ix: int, value: float):
+        """``A[ix+1,:,:] .= value`` (M:369; ix 0-based)."""
+        self._ck(self.lib.ns3d_fill_plane_x(self.h, a.ptr, a.shape[0], a.shape[1], a.shape[2], ix, value), "ns3d_fill_plane_x")
 
     def copy(self, dst: DeviceArray, src: DeviceArray):
         self.call("ns3d_copy", dst, src, src.size)

@@ -1,160 +1,20 @@
-"""Host emulation of the CUDA kernels of the fused PT loop (test infrastructure).
+"""The CUDA library, executed on the CPU (test infrastructure).
 
-``tests/emu/pt_emu.cpp`` compiles ``navierstokes3d_b200/csrc/ns3d_pt_kernels.cuh`` -- the very
-source nvcc compiles into libns3d.so -- with g++ behind ``cuda_host_shim.h`` (CUDA threads = host
-threads, ``__syncthreads`` = barrier).  It lets the CPU test suite execute the kernels' index
-arithmetic, boundary folding, tiling and ping-pong logic bit for bit against the oracle without
-a GPU.  It is NOT a product path (nothing in navierstokes3d_b200/ can reach it).
+``build_lib.py`` compiles libns3d.so's own translation units -- kernels and host code, the very source nvcc
+compiles -- with g++ behind ``cuda_host_shim.h`` (CUDA threads = host threads, ``__syncthreads`` = barrier) and a
+fake CUDA runtime / NCCL.  It lets the CPU test suite execute the kernels' index arithmetic, boundary folding,
+tiling and ping-pong logic bit for bit against the oracle without a GPU.  It is NOT a product path (nothing in
+navierstokes3d_b200/ can reach it).
 """
 from __future__ import annotations
 
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-LIB = os.path.join(HERE, "_build", "libpt_emu.so")
-DEPS = [os.path.join(HERE, "pt_emu.cpp"), os.path.join(HERE, "cuda_host_shim.h"),
-        os.path.join(ROOT, "navierstokes3d_b200", "csrc", "ns3d_pt_kernels.cuh"),
-        os.path.join(ROOT, "navierstokes3d_b200", "csrc", "ns3d_shared.cuh"),
-        os.path.join(ROOT, "include", "ns3d.h")]
-_lib = None
-
-KERNELS = {"pt_iter": 0, "pt_tb2": 1, "pt_tb2s": 2, "pt_tb2d": 3, "pt_tb2s_pb": 4}
-
-
-def build(force: bool = False) -> str:
-    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in DEPS):
-        return LIB
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    env = dict(os.environ)
-    env.pop("CC", None)
-    # -ffp-contract=off: like nvcc --fmad=false, FMA only where fma() is written
-    cmd = ["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-pthread",
-           os.path.join(HERE, "pt_emu.cpp"), "-o", LIB]
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
-    if res.returncode != 0:
-        raise RuntimeError("g++ failed building the kernel emulation:\n" + res.stderr)
-    return LIB
-
-
-def lib() -> C.CDLL:
-    global _lib
-    if _lib is None:
-        _lib = C.CDLL(build())
-        _lib.emu_pt_iterate.restype = C.c_int
-        _lib.emu_pt_iterate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
-        _lib.emu_pt_tb2_split.restype = C.c_int
-        _lib.emu_pt_tb2_split.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                          C.c_int, C.c_int, C.c_int, C.c_int]
-        _lib.emu_pt_slab_iterate.restype = C.c_int
-        _lib.emu_pt_slab_iterate.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
-                                             C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
-    return _lib
-
-
-class EmuSlab(C.Structure):
-    """``EmuSlab`` of pt_emu.cpp: this rank's buffers and the neighbours' as 16 raw addresses."""
-    _fields_ = [("pr", C.c_void_p * 2), ("dp", C.c_void_p * 2), ("divV", C.c_void_p),
-                ("lo", C.c_void_p * 4), ("hi", C.c_void_p * 4),
-                ("mbox", C.c_void_p), ("lo_mbox", C.c_void_p), ("hi_mbox", C.c_void_p)]
-
-
-class SlabMemory:
-    """The shared-memory image of one rank of an emulated z-slab run: Pr, its shadow, dPrdτ, its
-    shadow, ∇V (each padded by three planes like ns3d_zeros pads) and a 16-word mailbox, in ONE
-    ``multiprocessing.shared_memory`` block that the neighbouring rank processes map as well --
-    the stand-in for the CUDA IPC mappings of the peer-memory halo path."""
-
-    def __init__(self, nx, ny, nz, name=None, create=False):
-        from multiprocessing import shared_memory
-        self.shape, self.dshape = (nx, ny, nz), (nx - 2, ny - 2, nz - 2)
-        n, nd = nx * ny * nz, (nx - 2) * (ny - 2) * (nz - 2)
-        pn, pd = n + 3 * nx * ny + 32, nd + 3 * (nx - 2) * (ny - 2) + 32
-        self.counts = [pn, pn, pd, pd, pn, 16]           # Pr, Pr shadow, dP, dP shadow, divV, mailbox
-        self.offsets = np.concatenate([[0], np.cumsum(self.counts)[:-1]]) * 8
-        size = int(sum(self.counts) * 8)
-        self.shm = shared_memory.SharedMemory(name=name, create=create, size=size)
-        self._anchor = C.c_char.from_buffer(self.shm.buf)
-        self.base = C.addressof(self._anchor)
-        if create:
-            whole = np.frombuffer(self.shm.buf, dtype=np.float64, count=sum(self.counts))
-            whole[:] = np.nan                            # padding and shadows: a value USED from there poisons the result
-            whole[-16:] = 0.0                            # mailbox words start at zero
-            del whole
-
-    def addr(self, which: int) -> int:
-        return self.base + int(self.offsets[which])
-
-    def view(self, which: int) -> np.ndarray:
-        """A copy-free view while alive; callers drop it before close()."""
-        shape = self.dshape if which in (2, 3) else self.shape
-        return np.frombuffer(self.shm.buf, dtype=np.float64, count=int(np.prod(shape)),
-                             offset=int(self.offsets[which])).reshape(shape, order="F")
-
-    def close(self, unlink=False):
-        self._anchor = None
-        try:
-            self.shm.close()
-        except BufferError:      # a view is still alive somewhere: the mapping goes away with the process
-            pass
-        if unlink:
-            self.shm.unlink()
-
-
-def slab_rank_main(rank, nranks, names, grid, kernel, mode, pt_bytes, n_iter, kernel_mid, ty_mid, queue):
-    """Body of one rank process: map own and neighbours' memory, run the launches, report."""
-    try:
-        mem = {r: SlabMemory(*grid, name=names[r]) for r in (rank - 1, rank, rank + 1) if 0 <= r < nranks}
-        me = mem[rank]
-        b = EmuSlab()
-        b.pr[0], b.pr[1], b.dp[0], b.dp[1], b.divV = me.addr(0), me.addr(1), me.addr(2), me.addr(3), me.addr(4)
-        b.mbox = me.addr(5)
-        for side, r in (("lo", rank - 1), ("hi", rank + 1)):
-            if r in mem:
-                arr = getattr(b, side)
-                for q in range(4):
-                    arr[q] = mem[r].addr(q)
-                setattr(b, side + "_mbox", mem[r].addr(5))
-        pt = (C.c_char * len(pt_bytes)).from_buffer_copy(pt_bytes)
-        wp, wd = C.c_int(-1), C.c_int(-1)
-        rc = lib().emu_pt_slab_iterate(KERNELS[kernel], mode, C.addressof(pt), rank, nranks, C.addressof(b), n_iter,
-                                       KERNELS[kernel_mid], ty_mid, C.byref(wp), C.byref(wd))
-        queue.put((rank, rc, wp.value, wd.value))
-        del b
-        for m in mem.values():
-            m.close()
-    except BaseException as exc:  # noqa: BLE001
-        queue.put((rank, -99, repr(exc), 0))
-
-
-def pt_tb2_split(kernel_mid: str, mode: int, pt_params, Pr, dP, divV, n_pairs: int, klo: int, khi: int,
-                 ty_mid: int = 16, zchunk_mid: int = 16) -> None:
-    """n_pairs double iterations, each as three launches over the plane ranges [1,klo), [klo,khi),
-    [khi,nz-1) -- the outer two with pt_tb2_kernel, the middle one with `kernel_mid` (the way slabs
-    split every launch into interface chunks and the rest)."""
-    rc = lib().emu_pt_tb2_split(KERNELS[kernel_mid], mode, ty_mid, C.addressof(pt_params), Pr.ctypes.data,
-                                dP.ctypes.data, divV.ctypes.data, n_pairs, klo, khi, zchunk_mid)
-    if rc != 0:
-        raise RuntimeError(f"emu_pt_tb2_split failed ({rc})")
-
-
-def pt_iterate(kernel: str, mode: int, pt_params, Pr: np.ndarray, dP: np.ndarray, divV: np.ndarray, n: int,
-               ty: int = 16, serpentine: bool = True, zlo_halo: bool = False, zhi_halo: bool = False) -> int:
-    """n fused PT iterations on host arrays (Fortran order, updated in place) through the emulated
-    kernels, driven like one rank's run_direct() in ns3d_pt.cu.  Returns the number of launches."""
-    for a in (Pr, dP, divV):
-        assert a.dtype == np.float64 and a.flags.f_contiguous
-    nl = C.c_longlong(0)
-    rc = lib().emu_pt_iterate(KERNELS[kernel], mode, ty, C.addressof(pt_params), int(zlo_halo), int(zhi_halo),
-                              int(serpentine), Pr.ctypes.data, dP.ctypes.data, divV.ctypes.data, n, C.byref(nl))
-    if rc != 0:
-        raise RuntimeError(f"emu_pt_iterate failed ({rc})")
-    return nl.value
 
 
 # ---- the whole library on the CPU ------------------------------------------------------------------

@@ -30,7 +30,7 @@ def main():
     ctx = ns.Context(local, ns.PARITY)
     attach_communicator(ctx, rank, world)
     pt_random = len(sys.argv) > 6 and sys.argv[6] == "pt_random"
-    ctx.set_option("tb2", 1 if (tb2 or pt_random) else 0)
+    ctx.set_option("ptv_k", 2 if (tb2 or pt_random) else 1)   # "fused": one iteration per launch with peer stores
     sim = ns.Simulation(s, ctx)
     truth = O.VirtualRanks(nx, ny, nz, (1, 1, world), lz=lz)
     names = ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C", "divV")

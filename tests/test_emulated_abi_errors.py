@@ -19,10 +19,11 @@ def _emulated_library():
 def test_unknown_option_and_bad_values(ns, ctx):
     with pytest.raises(ns.NS3DError, match="unknown option"):
         ctx.set_option("no_such_knob", 1)
-    for name, bad in (("tb2_ty", 7), ("tb2_pf", 3), ("tb2_dual", 3), ("pt_minb", 9), ("pt_bands", 1), ("pt_bands", 99)):
-        with pytest.raises(ns.NS3DError, match=name.split("_")[0]):
+    for name, bad in (("ptv_k", 4), ("ptv_ns", 2), ("ptv_lb", 2), ("ptv_lb", 9)):
+        with pytest.raises(ns.NS3DError, match=name):
             ctx.set_option(name, bad)
-    for name, ok in (("tb2_ty", 0), ("tb2_pf", 2), ("tb2_dual", 0), ("pt_minb", 0), ("pt_bands", 4), ("serpentine", -1)):
+    for name, ok in (("ptv_k", 3), ("ptv_ns", 5), ("ptv_lb", 4), ("ptv_tma", 0), ("ptv_pxt", 8), ("ptv_bty", 0), ("p2p_halo", 0),
+                     ("graphs", 0), ("serpentine", -1)):
         ctx.set_option(name, ok)
 
 
@@ -58,11 +59,9 @@ def test_fused_loop_rejects_bad_arguments(ns, ctx):
     pt.nx = 2
     with pytest.raises(ns.NS3DError, match="at least 3"):
         ctx.pt_iterate(Pr, dP, dv, pt, 2)
-    # the hot kernels prefetch into the allocator's padding: foreign device pointers are refused
+    # the loop runs on pitched copies: the caller's arrays are only read and written within their bounds (pack /
+    # unpack), so any device array of the right shape will do; NULL is refused
     pt = s.pt_params()
-    foreign = np.zeros((12, 9, 9), order="F")
-    rc = ctx.lib.ns3d_pt_iterate(ctx.h, foreign.ctypes.data, dP.ptr, dv.ptr, C.byref(pt), 2)
-    assert rc == -1 and b"not allocated by ns3d_zeros" in ctx.lib.ns3d_last_error(ctx.h)
     assert ctx.lib.ns3d_pt_iterate(ctx.h, None, dP.ptr, dv.ptr, C.byref(pt), 2) == -1
 
 

@@ -50,7 +50,7 @@ def test_native_arm_prints_the_contract_line(monkeypatch, capsys):
     assert line["config"]["workload"].startswith("A: cylinder flow 31x19x19") and line["config"]["mode"] == "FAST"
     assert line["gpu_launches"] > 0 and line["value"] > 0 and line["steps"] == 1
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic", "dram_achieved", "dram_frac")) <= set(line["roofline"])
-    assert "pt_tb2s_kernel" in line["roofline"]["kernel"]
+    assert "ptv_kernel" in line["roofline"]["kernel"] and line["roofline"]["pt_iterations_per_launch"] == 2
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0 and line["e2e"]["value"] > 0
     assert line["parity_check"]["pt_iters_identical"] and line["parity_check"]["within_tolerance"]
     assert line["parity_check"]["max_rel_diff"]["Pr"] == 0.0     # FAST equals PARITY in every value seen so far

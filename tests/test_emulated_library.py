@@ -43,16 +43,18 @@ def test_fused_iteration(O, ns, ctx, variant, grid, zchunk):
     S.test_fused_iteration_bit_exact(O, ns, ctx, variant, grid, zchunk)
 
 
-@pytest.mark.parametrize("variant,grid,zchunk,kern", [
-    ("M", (3, 3, 3), 0, "tb2s_auto"), ("G", (4, 3, 6), 2, "tb2s_auto"), ("M", (37, 23, 19), 7, "tb2s_auto"),
-    ("G", (37, 23, 19), 0, "tb2s_16_nopf"), ("M", (20, 19, 11), 1, "tb2s_8_pf2"), ("G", (20, 12, 12), 0, "tb2_first"),
-    ("M", (20, 12, 12), 2, "tb2d"), ("G", (20, 19, 11), 0, "tb2s_pairbar"), ("M", (20, 12, 14), 3, "bands4"),
-    ("G", (20, 12, 9), 2, "bands2_nographs"),
+@pytest.mark.parametrize("variant,grid,zchunk,cfg", [
+    ("M", (3, 3, 3), 0, "auto"), ("G", (4, 3, 6), 2, "auto"), ("M", (37, 23, 19), 7, "auto"), ("G", (5, 4, 3), 0, "k1"),
+    ("G", (20, 19, 11), 0, "k2_lb0"), ("M", (20, 19, 11), 1, "k2_lb4_ns3"), ("G", (20, 12, 12), 0, "k3_lb0"),
+    ("M", (20, 12, 12), 2, "k2_tiles"), ("G", (20, 19, 11), 0, "k3_tiles"), ("M", (16, 9, 8), 3, "k2_coop_nographs"),
+    ("G", (16, 9, 8), 2, "k1_coop_tiles"), ("M", (4, 3, 6), 1, "k3_tiles"), ("G", (3, 3, 3), 0, "k3_lb0"),
 ])
-def test_two_iterations_per_launch(O, ns, ctx, variant, grid, zchunk, kern):
-    """Every kernel variant behind the options, the candidates and the z-band pipeline included, through
-    ns3d_pt_iterate: 2, 1, 5 and 40 iterations (graph capture and replay from 8 iterations up)."""
-    S.test_two_iterations_per_launch_bit_exact(O, ns, ctx, variant, grid, zchunk, kern)
+def test_ptv_kernel(O, ns, ctx, variant, grid, zchunk, cfg):
+    """The fused loop's kernel in every configuration behind the options -- iterations per launch, launch bounds,
+    staging slots, one tile and several tiles with rims -- through ns3d_pt_iterate: 2, 1, 5 and 40 iterations (graph
+    capture and replay from 8 iterations up).  On the CPU the z-plane tiles are staged by plain loads (the TMA unit
+    is the one thing the emulation cannot execute; the GPU suite runs the same cases through it)."""
+    S.test_ptv_kernel_bit_exact(O, ns, ctx, variant, grid, zchunk, cfg)
 
 
 def test_outlet_guard_off(O, ns, ctx):

@@ -51,20 +51,18 @@ def run_ranks(world, grid, nt, lz, how="step", options=None):
 
 @pytest.mark.parametrize("world,grid,nt,lz,how,options", [
     (2, (20, 12, 9), 2, None, "step", {}),                        # thin slabs: unsplit peer launches
-    (2, (16, 10, 26), 2, 50 / 16, "step", {}),                     # split launches: interface chunks + slim interior
-    (3, (16, 10, 8), 2, 20 / 16, "step", {"tb2": 0}),              # one-iteration kernel, peer stores, three ranks
+    (2, (16, 10, 26), 2, 50 / 16, "step", {}),                     # split launches: interface chunks + interior
+    (3, (16, 10, 8), 2, 20 / 16, "step", {"ptv_k": 1}),            # one iteration per launch, peer stores, three ranks
     (2, (16, 10, 9), 2, None, "step", {"p2p_halo": 0}),            # NCCL send/recv halo path instead of peer memory
     (2, (16, 10, 9), 1, None, "level1", {}),                       # the call-by-call level-1 loop over NCCL
     # the fused loop alone on RANDOM fields (the script's flow is z-invariant and would hide a wrong plane offset)
     (2, (16, 10, 26), 12, 50 / 16, "pt_random", {}),               # split launches, graph replay (>= 8 iterations)
     (3, (14, 10, 9), 7, 23 / 14, "pt_random", {}),                 # unsplit peer launches + odd tail, three ranks
-    (2, (14, 10, 9), 5, None, "pt_random", {"tb2": 0}),            # one-iteration kernel with peer stores
+    (2, (14, 10, 9), 5, None, "pt_random", {"ptv_k": 1}),          # one iteration per launch with peer stores
     (2, (14, 10, 9), 5, None, "pt_random", {"p2p_halo": 0}),       # NCCL send/recv halo exchange
-    (4, (12, 9, 23), 6, 86 / 12, "pt_random", {"tb2_dual": 2}),    # four ranks, the dual-row candidate in the interior
-    # candidate: the slim pipeline on the slab interfaces too (pt_tb2sp_kernel)
-    (2, (16, 10, 26), 12, 50 / 16, "pt_random", {"tb2_slim_faces": 1}),   # split launches
-    (3, (14, 10, 9), 7, 23 / 14, "pt_random", {"tb2_slim_faces": 1}),     # unsplit launches, three ranks
-    (2, (16, 10, 26), 2, 50 / 16, "step", {"tb2_slim_faces": 1}),         # whole time steps
+    (4, (12, 9, 23), 6, 86 / 12, "pt_random", {"ptv_pxt": 4, "ptv_bty": 5}),   # four ranks, several tiles per plane
+    (2, (16, 10, 26), 12, 50 / 16, "pt_random", {"ptv_k": 3}),     # K = 3 asked for: slabs fall back to 2
+    (2, (16, 10, 26), 2, 50 / 16, "step", {"graphs": 0}),          # whole time steps without graph replay
 ])
 def test_rank_processes_match_igg_emulation(world, grid, nt, lz, how, options):
     results = run_ranks(world, grid, nt, lz, how, options)

@@ -76,3 +76,20 @@ def test_bench_line_has_the_contract_keys():
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
     assert line["e2e"]["h2d_bytes_per_step"] > 0
     assert line["parity_check"]["pt_iters_identical"] and line["parity_check"]["within_tolerance"]
+
+
+@pytest.mark.parametrize("variant,nx", [("M", 40), ("G", 40), ("G", 63)])
+def test_device_side_initialisers_match_the_scripts_arrays(ns, variant, nx):
+    """M:369-373 / G:86-88 built on the device (ns3d_fill_profile_z, ns3d_fill_plane_x: nz host values cross PCIe)
+    against the same comprehensions evaluated as 3-D host arrays: bit-equal, signs of zeros included."""
+    from navierstokes3d_b200.driver import initial_host_fields
+    s = ns.setup_multi_gpu(nx) if variant == "M" else ns.setup_gpu(nx)
+    dev = ns.Simulation(s, ns.Context(0, ns.PARITY))
+    host = ns.Simulation(s, ns.Context(0, ns.PARITY), host_fields=initial_host_fields(s))
+    if variant == "M":
+        host.set_cylinder()      # host_fields replace only the arrays; the masking call of M:372 follows them
+    for name in ("Pr", "Vx", "Vy", "Vz", "C"):
+        a, b = dev.host(name), host.host(name)
+        assert np.array_equal(a, b) and np.array_equal(np.signbit(a), np.signbit(b)), name
+    dev.ctx.close()
+    host.ctx.close()

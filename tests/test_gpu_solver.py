@@ -109,53 +109,11 @@ def test_ptv_kernel_bit_exact(O, ns, ctx, variant, grid, zchunk, cfg):
             assert len(bad) == 0, f"{name} differs after {done} iterations: {len(bad)} values, first {bad[:3].tolist()}"
 
 
-CANDIDATES = pytest.mark.skipif(not os.environ.get("NS3D_TEST_CANDIDATES"),
-                                reason="round-2 candidate kernels (emulation-verified, not yet run on a device): "
-                                       "set NS3D_TEST_CANDIDATES=1")
-
-
-@pytest.mark.parametrize("variant", ["M", "G"])
-@pytest.mark.parametrize("grid", [(3, 3, 3), (5, 4, 3), (4, 3, 6), (37, 23, 19), (63, 38, 38), (70, 47, 41)])
-@pytest.mark.parametrize("zchunk", [0, 1, 2, 7])
-@pytest.mark.parametrize("kern", ["tb2s_auto", "tb2s_16_nopf", "tb2s_8_pf2", "tb2_first",
-                                  pytest.param("tb2d", marks=CANDIDATES), pytest.param("tb2s_pairbar", marks=CANDIDATES),
-                                  pytest.param("bands4", marks=CANDIDATES), pytest.param("bands2_nographs", marks=CANDIDATES)])
-def test_two_iterations_per_launch_bit_exact(O, ns, ctx, variant, grid, zchunk, kern):
-    """Temporal blocking (option "tb2"): 2 PT iterations per launch, rims recomputed, Pr^(1) kept in
-    shared memory.  Same per-cell arithmetic -> still bit-equal to the oracle; odd counts end with
-    one single-iteration launch, (70,47,41) spans 3x4 tiles and several z-chunks.  Kernels: the
-    default pt_tb2s_kernel (tile height by grid size, neighbour + L2 prefetch), two of its other
-    instantiations, and the first version pt_tb2_kernel (still the one on slab interfaces)."""
-    p, f = pt_problem(O, variant, grid, 15)
-    s = setup_for(ns, variant, grid[0], ny=grid[1], nz=grid[2])
-    ctx.set_option("ptv", 0)
-    ctx.set_option("tb2", 1)
-    for name, val in {"tb2s_auto": {}, "tb2s_16_nopf": {"tb2_ty": 16, "tb2_pf": 0, "tb2_np": 0},
-                      "tb2s_8_pf2": {"tb2_ty": 8, "tb2_pf": 2}, "tb2_first": {"tb2_slim": 0, "tb2_ty": 16},
-                      "tb2d": {"tb2_dual": 2}, "tb2s_pairbar": {"tb2_pairbar": 1}, "bands4": {"pt_bands": 4},
-                      "bands2_nographs": {"pt_bands": 2, "graphs": 0}}[kern].items():
-        ctx.set_option(name, val)
-    d = {k: ctx.from_host(f[k]) for k in ("Pr", "dPrdtau", "divV")}
-    done = 0
-    for n in (2, 1, 5, 40):
-        ctx.pt_iterate(d["Pr"], d["dPrdtau"], d["divV"], s.pt_params(zchunk), n)
-        for _ in range(n):
-            O.update_dPrdtau(p, f)
-            O.update_Pr(p, f)
-            O.set_bc_Pr(p, f)
-        done += n
-        for name in ("Pr", "dPrdtau"):
-            got = d[name].to_host()
-            bad = np.argwhere(got != f[name])
-            assert len(bad) == 0, f"{name} differs after {done} iterations: {len(bad)} values, first {bad[:3].tolist()}"
-
-
 @pytest.mark.parametrize("variant,nx,nt", [("M", 63, 4), ("G", 40, 2)])
 def test_time_steps_with_two_iterations_per_launch(O, ns, variant, nx, nt):
     p = oracle_params(O, variant, nx)
     f, iters_o, errs_o = O.run(p, nt)
     c = ns.Context(0, ns.PARITY)
-    c.set_option("tb2", 1)
     sim = ns.Simulation(setup_for(ns, variant, nx), c)
     for _ in range(nt):
         sim.step()
@@ -306,27 +264,27 @@ def test_large_grid_oracle_spot_check(O, ns):
 
 
 @pytest.mark.parametrize("variant,grid", [("M", (511, 511, 9)), ("G", (1023, 511, 7)), ("G", (255, 153, 20))])
-def test_compile_time_stride_kernels(O, ns, variant, grid):
-    """Grids whose x-y extent has a compile-time-stride instantiation of pt_tb2s_kernel (255x153,
-    511x511, 1023x511: the reference scripts' and BASELINE.json's planes), thin in z so that the
-    oracle finishes in seconds; 5 iterations = two double launches + one single.  Bit-exact, and
-    identical to the generic-stride instantiation."""
+def test_default_tiles_on_the_benchmark_planes(O, ns, variant, grid):
+    """Grids with the x-y extent of the reference scripts' and BASELINE.json's configurations (255x153, 511x511,
+    1023x511), thin in z so that the oracle finishes in seconds: the default launch configuration (compile-time
+    32 x 16-cell tiles, TMA staging) and the general-geometry instantiation; 5 iterations = two double launches +
+    one single.  Bit-exact, and identical to each other."""
     p, f = pt_problem(O, variant, grid, 23)
     s = setup_for(ns, variant, grid[0], ny=grid[1], nz=grid[2])
     ctx = ns.Context(0, ns.PARITY)
     out = {}
-    for spec in (1, 0):
-        ctx.set_option("tb2_spec", spec)
-        if grid[0] != 255:
-            ctx.set_option("tb2_ty", 16)   # thin grids are "small": the 511/1023 instantiations are 32x16 tiles
+    for generic in (0, 1):
+        if generic:
+            ctx.set_option("ptv_pxt", 17)   # no compile-time instantiation for 34-cell-wide tiles
+            ctx.set_option("ptv_bty", 15)
         d = {k: ctx.from_host(f[k]) for k in ("Pr", "dPrdtau", "divV")}
         ctx.pt_iterate(d["Pr"], d["dPrdtau"], d["divV"], s.pt_params(), 5)
-        out[spec] = (d["Pr"].to_host(), d["dPrdtau"].to_host())
+        out[generic] = (d["Pr"].to_host(), d["dPrdtau"].to_host())
     for _ in range(5):
         O.update_dPrdtau(p, f)
         O.update_Pr(p, f)
         O.set_bc_Pr(p, f)
-    assert (out[1][0] == f["Pr"]).all() and (out[1][1] == f["dPrdtau"]).all()
+    assert (out[0][0] == f["Pr"]).all() and (out[0][1] == f["dPrdtau"]).all()
     assert (out[0][0] == out[1][0]).all() and (out[0][1] == out[1][1]).all()
     ctx.close()
 
