@@ -266,7 +266,7 @@ int ptv_launch(ns3d_ctx* ctx, cudaStream_t st, PtV k, const PtvPlan& pl, int K, 
     memset(&maps, 0, sizeof maps);
     bool tma = false;
 #ifndef NS3D_HOST_EMU
-    tma = !p2p && ctx->opt_ptv_tma;
+    tma = ctx->opt_ptv_tma != 0;
     if (tma) {
         const int W = 2 * k.pxt, H = k.bty;
         NS3D_TRY(ptv_make_map(ctx, &maps.m[0], k.P, k.px, k.ny, k.nz, W + 4, H + 2));

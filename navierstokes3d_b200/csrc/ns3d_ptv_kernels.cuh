@@ -38,8 +38,8 @@
 // peer memory (NVLink): the first iteration of the halo plane is recomputed locally from the local
 // halo plane plus one plane of the neighbour's current iterate and its dPrdτ plane (peer loads), the
 // planes a slab sends are stored straight into the neighbour's halo plane, hand-over through the
-// mailbox protocol of ns3d_pt_common.cuh.  Those chunks stage their planes with plain L1-bypassing loads
-// (ptv_coop_stage) instead of TMA: two of their planes live in the neighbour's memory.
+// mailbox protocol of ns3d_pt_common.cuh.  The four slots of such a chunk that need a neighbour's memory (planes -1 / nz
+// of Pr, dPrdτ of the halo planes) are staged with plain L1-bypassing loads (ptv_coop_stage); all others by TMA.
 #pragma once
 
 #include "ns3d_pt_common.cuh"
@@ -645,6 +645,16 @@ __global__ void __launch_bounds__(NT, MINB) ptv_kernel(const PtV p, const __grid
         if (q > last_load) return;
 #if !defined(NS3D_HOST_EMU)
         if (TMA) {
+            // slab interfaces: the planes beyond the halo (-1, nz) and the dPrdτ of the halo planes (0, nz-1) live in a
+            // neighbour's memory -- those few slots are filled by plain loads of all threads, and the elected thread
+            // completes the slot's mbarrier by hand; every other plane goes through the TMA unit
+            const bool remote = P2P && ((lo_face && q <= 0) || (hi_face && q >= nz - 1));
+            if (remote) {
+                ptv_coop_stage<P2P>(p, smem + (slot - sb), q, X0, Y0, lo_face, hi_face);
+                __syncthreads();
+                if (threadIdx.x == 0) ptv_mbar_expect(bar, 0);
+                return;
+            }
             if (threadIdx.x == 0) {
                 ptv_mbar_expect(bar, p.tx_bytes);
                 ptv_tma_3d(slot, &maps.m[0], X0 - 2, Y0 - 1, q, bar);

@@ -24,12 +24,18 @@ int ptv_launch_t(ns3d_ctx* ctx, cudaStream_t st, const PtV& k, const PtvMaps& ma
 template <int MODE, int K, bool P2P, bool TMA, int PXT, int BTY>
 int ptv_launch_lb(ns3d_ctx* ctx, cudaStream_t st, const PtV& k, const PtvMaps& maps, int lb, dim3 grid, size_t smem)
 {
-    if (PXT * BTY == 512 || (PXT == 0 && lb >= 3)) {
+    if constexpr (PXT * BTY == 512) {
         if (lb == 4) return ptv_launch_t<MODE, K, P2P, TMA, PXT, BTY, 512, 2>(ctx, st, k, maps, grid, smem);
         return ptv_launch_t<MODE, K, P2P, TMA, PXT, BTY, 512, 1>(ctx, st, k, maps, grid, smem);
+    } else if constexpr (PXT * BTY == 256) {
+        if (lb == 0) return ptv_launch_t<MODE, K, P2P, TMA, PXT, BTY, 256, 2>(ctx, st, k, maps, grid, smem);
+        return ptv_launch_t<MODE, K, P2P, TMA, PXT, BTY, 256, 3>(ctx, st, k, maps, grid, smem);
+    } else {   // geometry from the kernel parameters
+        if (lb == 4) return ptv_launch_t<MODE, K, P2P, TMA, PXT, BTY, 512, 2>(ctx, st, k, maps, grid, smem);
+        if (lb == 3) return ptv_launch_t<MODE, K, P2P, TMA, PXT, BTY, 512, 1>(ctx, st, k, maps, grid, smem);
+        if (lb == 0) return ptv_launch_t<MODE, K, P2P, TMA, PXT, BTY, 256, 2>(ctx, st, k, maps, grid, smem);
+        return ptv_launch_t<MODE, K, P2P, TMA, PXT, BTY, 256, 3>(ctx, st, k, maps, grid, smem);
     }
-    if (lb == 0) return ptv_launch_t<MODE, K, P2P, TMA, PXT, BTY, 256, 2>(ctx, st, k, maps, grid, smem);
-    return ptv_launch_t<MODE, K, P2P, TMA, PXT, BTY, 256, 3>(ctx, st, k, maps, grid, smem);
 }
 
 // Tile shapes with a compile-time instantiation (every shared-memory stride an immediate); any other shape runs the
@@ -46,23 +52,35 @@ int ptv_launch_shape(ns3d_ctx* ctx, cudaStream_t st, const PtV& k, const PtvMaps
     return ptv_launch_lb<MODE, K, false, true, 0, 0>(ctx, st, k, maps, lb, grid, smem);
 }
 
-// tma: the staging ring is filled by the TMA unit (plain launches on a device); otherwise by plain loads (slab-interface
-// chunks, whose first / last planes live in a neighbour's memory, and the host emulation of the library)
+// ... on a slab interface (P2P): the default tile or the general geometry
+template <int MODE, int K>
+int ptv_launch_shape_p2p(ns3d_ctx* ctx, cudaStream_t st, const PtV& k, const PtvMaps& maps, int lb, dim3 grid, size_t smem)
+{
+    if (k.ns == 4 && k.pxt == 16 && k.bty == 16) return ptv_launch_lb<MODE, K, true, true, 16, 16>(ctx, st, k, maps, lb, grid, smem);
+    return ptv_launch_lb<MODE, K, true, true, 0, 0>(ctx, st, k, maps, lb, grid, smem);
+}
+
+// tma: the staging ring is filled by the TMA unit (launches on a device); otherwise by plain loads of all threads (the
+// host emulation of the library, option ptv_tma = 0)
 template <int MODE>
 int ptv_launch_m(ns3d_ctx* ctx, cudaStream_t st, const PtV& k, const PtvMaps& maps, const PtvPlan& pl, int K, bool p2p, bool tma,
                  dim3 grid, size_t smem)
 {
-    if (p2p) {
-        if (K == 1) return ptv_launch_lb<MODE, 1, true, false, 0, 0>(ctx, st, k, maps, pl.lb, grid, smem);
-        return ptv_launch_lb<MODE, 2, true, false, 0, 0>(ctx, st, k, maps, pl.lb, grid, smem);
-    }
 #ifndef NS3D_HOST_EMU
+    if (tma && p2p) {
+        if (K == 1) return ptv_launch_shape_p2p<MODE, 1>(ctx, st, k, maps, pl.lb, grid, smem);
+        return ptv_launch_shape_p2p<MODE, 2>(ctx, st, k, maps, pl.lb, grid, smem);
+    }
     if (tma) {
         if (K == 1) return ptv_launch_shape<MODE, 1>(ctx, st, k, maps, pl.lb, grid, smem);
         if (K == 2) return ptv_launch_shape<MODE, 2>(ctx, st, k, maps, pl.lb, grid, smem);
         return ptv_launch_shape<MODE, 3>(ctx, st, k, maps, pl.lb, grid, smem);
     }
 #endif
+    if (p2p) {
+        if (K == 1) return ptv_launch_lb<MODE, 1, true, false, 0, 0>(ctx, st, k, maps, pl.lb, grid, smem);
+        return ptv_launch_lb<MODE, 2, true, false, 0, 0>(ctx, st, k, maps, pl.lb, grid, smem);
+    }
     if (K == 1) return ptv_launch_lb<MODE, 1, false, false, 0, 0>(ctx, st, k, maps, pl.lb, grid, smem);
     if (K == 2) return ptv_launch_lb<MODE, 2, false, false, 0, 0>(ctx, st, k, maps, pl.lb, grid, smem);
     return ptv_launch_lb<MODE, 3, false, false, 0, 0>(ctx, st, k, maps, pl.lb, grid, smem);
