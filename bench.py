@@ -430,9 +430,14 @@ def main():
     ctx.pt_iterate(sim.f["Pr"], sim.f["dPrdtau"], sim.f["divV"], pt, n_probe)
     k1.record(stream)
     ctx.sync()
-    t_launch = k0.elapsed_time(k1) / 1e3 / n_probe * per_launch
+    desc = ctx.pt_kernel_name(pt)
+    # ptv_flow_kernel (single rank): the n_probe iterations between the events are ONE launch of n_probe / per_launch
+    # passes over the fields; ptv_kernel (z-slabs): one launch per pass of per_launch iterations
+    persistent = desc.startswith("ptv_flow_kernel")
+    iters_per_launch = n_probe if persistent else per_launch
+    t_launch = k0.elapsed_time(k1) / 1e3 / n_probe * iters_per_launch
     peak, peak_src = hbm_peak()
-    achieved = 40.0 * per_launch * n_cells / t_launch / 1e9
+    achieved = 40.0 * iters_per_launch * n_cells / t_launch / 1e9
     traffic, tkey = None, kernel_key(args.workload, args.mode, args.opt)
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
@@ -534,8 +539,7 @@ def main():
                                     "pt_iters_identical": rig.reduce([float([r[0] for r in o_res] == p_iters)], "min")[0] == 1.0,
                                     "max_rel_diff_vs_parity": o_worst, "within_tolerance": max(o_worst.values()) <= TOL}
 
-    share = (sum(iters) / args.steps) * (t_launch / per_launch) / (t_all / args.steps)
-    desc = ctx.pt_kernel_name(pt)
+    share = (sum(iters) / args.steps) * (t_launch / iters_per_launch) / (t_all / args.steps)
     ctx.close()
 
     # ---- extra legs of the default run (each on a fresh context; the B fields are freed above) ----
@@ -570,12 +574,13 @@ def main():
                          "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_key": tkey, "us_per_launch": t_launch * 1e6,
-                         "pt_iterations_per_launch": per_launch,
+                         "pt_iterations_per_launch": iters_per_launch, "pt_iterations_per_pass": per_launch,
+                         "us_per_pass": t_launch * 1e6 / iters_per_launch * per_launch,
                          # what actually crossed the DRAM interface (ncu) over the same launch time: the
                          # kernel keeps the intermediate iterates on chip, so this is well below `achieved`
                          "dram_achieved": (traffic / t_launch / 1e9) if traffic else None,
                          "dram_frac": (traffic / t_launch / 1e9 / peak) if traffic else None,
-                         "algorithmic_bytes_per_launch": 40.0 * per_launch * n_cells,
+                         "algorithmic_bytes_per_launch": 40.0 * iters_per_launch * n_cells,
                          "share_of_step": share},
         }
         if parity:

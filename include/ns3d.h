@@ -107,6 +107,11 @@ NS3D_API void* ns3d_stream(ns3d_ctx* ctx);
  * (the power law's `^(1/6)` is evaluated on the host, whose libm CUDA's pow does not match to the last bit), and
  * ns3d_fill_plane_x sets A[ix,:,:] = value (ix 0-based).  No 3-D array exists on the host.                        */
 NS3D_API int ns3d_fill_profile_z(ns3d_ctx* ctx, double* A, int sx, int sy, int sz, const double* h_profile);
+/* ... with the comprehension's other terms kept apart: A[ix,iy,iz] = (h_profile[iz] + h_add_y[iy]) + h_add_z[iz].  M:370 is
+ * `-(z_g(iz,dz,C)-dz/2)*ρ*g + 0*yc[iy] + 0*zc[iz]` with g = 0 (M:316): three SIGNED zeros whose sum is -0.0 exactly where all
+ * three are, so the sign of the initial Pr depends on iy as well (sy + 2 sz host values cross PCIe).                   */
+NS3D_API int ns3d_fill_profile_zy(ns3d_ctx* ctx, double* A, int sx, int sy, int sz, const double* h_profile, const double* h_add_y,
+                                  const double* h_add_z);
 NS3D_API int ns3d_fill_plane_x(ns3d_ctx* ctx, double* A, int sx, int sy, int sz, int ix, double value);
 /* Asynchronous host <-> device copies for a driver that overlaps the traffic of one time step with the computation
  * of another (the reference's `Data.Array(x)` / `Array(A)` are blocking; nothing in it corresponds to these).  Uploads

@@ -13,7 +13,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libns3d.so")
-SOURCES = ["ns3d_core.cu", "ns3d_ops.cu", "ns3d_pt.cu", "ns3d_ptv.cu", "ns3d_ptv_mode0.cu", "ns3d_ptv_mode1.cu", "ns3d_ptv_mode2.cu", "ns3d_out.cu"]
+SOURCES = ["ns3d_core.cu", "ns3d_ops.cu", "ns3d_pt.cu", "ns3d_step.cu", "ns3d_ptv.cu", "ns3d_ptv_mode0.cu", "ns3d_ptv_mode1.cu", "ns3d_ptv_mode2.cu", "ns3d_out.cu"]
 HEADERS = ["ns3d_internal.cuh", "ns3d_shared.cuh", "ns3d_pt_common.cuh", "ns3d_ptv_kernels.cuh", "ns3d_ptv_launch.cuh", os.path.join("..", "..", "include", "ns3d.h")]
 
 NVCC_FLAGS = [

@@ -183,6 +183,8 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
         return NS3D_OK;
     }
     if (!strcmp(name, "ptv_tma")) { ctx->opt_ptv_tma = value != 0; return NS3D_OK; }
+    // persistent launch: every chunk of iterations between two residual checks is ONE kernel (single rank)
+    if (!strcmp(name, "ptv_flow")) { ctx->opt_ptv_flow = value != 0; return NS3D_OK; }
     if (!strcmp(name, "ptv_lb")) {
         if (value < -1 || value > 4 || value == 2) return ns3d_fail(ctx, NS3D_EINVAL, "ptv_lb must be -1 (default), 0, 1, 3 or 4");
         ctx->opt_ptv_lb = value;
@@ -357,6 +359,19 @@ __global__ void fill_profile_z_kernel(double* __restrict__ a, const double* __re
     for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) a[q] = prof[q / sxy];
 }
 
+// A[ix,iy,iz] = (prof[iz] + add_y[iy]) + add_z[iz]: the comprehension of M:370, `-(z_g(iz,dz,C)-dz/2)*ρ*g + 0*yc[iy] + 0*zc[iz]`,
+// term by term -- with g = 0 (M:316, Fr = Inf) every term is a SIGNED zero and the sum is -0.0 exactly where all three are
+__global__ void fill_profile_zy_kernel(double* __restrict__ a, const double* __restrict__ prof, const double* __restrict__ add_y,
+                                       const double* __restrict__ add_z, int sx, int sy, size_t n)
+{
+    const size_t sxy = (size_t)sx * sy;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        const size_t k = q / sxy;
+        const int j = (int)((q - k * sxy) / sx);
+        a[q] = (prof[k] + add_y[j]) + add_z[k];
+    }
+}
+
 __global__ void fill_plane_x_kernel(double* __restrict__ a, int sx, int ix, double v, size_t nyz)
 {
     for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < nyz; q += (size_t)gridDim.x * blockDim.x)
@@ -381,6 +396,31 @@ extern "C" int ns3d_fill_profile_z(ns3d_ctx* ctx, double* A, int sx, int sy, int
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // h_profile may go away; d_prof is freed below
     cudaFree(d_prof);
     if (e != cudaSuccess) return ns3d_fail(ctx, NS3D_ECUDA, "ns3d_fill_profile_z failed: %s", cudaGetErrorString(e));
+    return NS3D_OK;
+}
+
+extern "C" int ns3d_fill_profile_zy(ns3d_ctx* ctx, double* A, int sx, int sy, int sz, const double* h_profile, const double* h_add_y,
+                                    const double* h_add_z)
+{
+    NS3D_CHECK_CTX(ctx);
+    if (!A || !h_profile || !h_add_y || !h_add_z || sx <= 0 || sy <= 0 || sz <= 0)
+        return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_fill_profile_zy: bad argument");
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* d = nullptr;   // prof (sz) | add_z (sz) | add_y (sy)
+    NS3D_CUDA(ctx, cudaMalloc(&d, (size_t)(2 * sz + sy) * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d, h_profile, (size_t)sz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + sz, h_add_z, (size_t)sz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + 2 * sz, h_add_y, (size_t)sy * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        const size_t n = (size_t)sx * sy * sz;
+        const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->num_sms * 16);
+        fill_profile_zy_kernel<<<blocks, 256, 0, ctx->stream>>>(A, d, d + 2 * sz, d + sz, sx, sy, n);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // the host arrays may go away; d is freed below
+    cudaFree(d);
+    if (e != cudaSuccess) return ns3d_fail(ctx, NS3D_ECUDA, "ns3d_fill_profile_zy failed: %s", cudaGetErrorString(e));
     return NS3D_OK;
 }
 

@@ -58,6 +58,9 @@ struct ns3d_ctx {
     void* ptv_graphs = nullptr;  // graph cache owned by ns3d_ptv.cu
     int opt_ptv_k = 0;        // PT iterations per launch (0 = default)
     int opt_ptv_ns = 0;       // staging slots of the TMA ring (0 = default 4; >= 3)
+    unsigned* ptv_work = nullptr;  // work queue + completion counters of the persistent launch (ptv_flow_kernel)
+    size_t ptv_work_words = 0;
+    int opt_ptv_flow = 0;     // persistent launch of whole chunks of iterations (single rank; off: see ptv_flow_kernel)
     int opt_ptv_tma = 1;      // stage the z-plane tiles with the TMA unit (0 = plain loads by all threads)
     int opt_ptv_lb = -1;      // launch-bounds variant (threads / CTAs per SM): 0 = 256/2, 1 = 256/3, 2 = 256/4, 3 = 512/1, 4 = 512/2 (-1 = default)
     int opt_ptv_pxt = 0;      // thread columns per tile (0 = balanced automatically)
@@ -139,6 +142,14 @@ int ns3d_internal_ptv_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const do
                             double* h_err_hist, int err_cap, int* h_nchecks);
 int ns3d_internal_ptv_iterate(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const double* divV, const ns3d_pt_params* p, int n_iter);
 int ns3d_internal_ptv_describe(ns3d_ctx* ctx, const ns3d_pt_params* p, char* buf, int cap, int* iters_per_launch);
+// fused once-per-step kernels (ns3d_step.cu, ns3d_ops.cu)
+int ns3d_internal_predict_fused(ns3d_ctx* ctx, double* Vxn, double* Vyn, double* Vzn, double* C, const double* Vx, const double* Vy,
+                                const double* Vz, const ns3d_step_params* sp);
+int ns3d_internal_correct_fused(ns3d_ctx* ctx, double* Vx, double* Vy, double* Vz, double* C, double* C_o, const double* Pr,
+                                const ns3d_step_params* sp);
+int ns3d_internal_advect_all(ns3d_ctx* ctx, double* Vx, const double* Vx_o, double* Vy, const double* Vy_o, double* Vz,
+                             const double* Vz_o, double* C, const double* C_o, double dt, double dx, double dy, double dz, int nx,
+                             int ny, int nz);
 void ns3d_internal_out_free(ns3d_ctx* ctx);
 int ns3d_internal_gather_bytes(ns3d_ctx* ctx, const void* d_send, size_t bytes, void* d_recv, const size_t* bytes_all);
 int ns3d_internal_max_abs_async(ns3d_ctx* ctx, const double* A, size_t count);  // result -> ctx->d_maxbits

@@ -466,8 +466,12 @@ __device__ __forceinline__ double backtrack(const double* __restrict__ Ao, doubl
 // One thread per (ix,iy,iz) of the (nx+1,ny+1,nz+1) launch range, like the reference.  The
 // third branch targets Vy/Vy_o (M:234, sic): Vz is never advected, and where branches 2 and 3
 // both fire the thread's second store to Vy[ix,iy,iz] wins -- here only the winner is stored.
+// ALL (ns3d_step): the kernel writes EVERY entry of Vx, Vy, Vz -- where advect! leaves an array alone
+// (the x-face planes of Vx, the rows of Vy no branch reaches, all of Vz) it copies the `_o` value, so
+// that a step whose corrector worked on the `_o` arrays needs no `A_o .= A` copies (M:475).
+template <bool ALL>
 __global__ void advect_kernel(double* __restrict__ Vx, const double* __restrict__ Vx_o, double* __restrict__ Vy,
-                              const double* __restrict__ Vy_o, const double* __restrict__ Vz_o,
+                              const double* __restrict__ Vy_o, double* __restrict__ Vz, const double* __restrict__ Vz_o,
                               double* __restrict__ C, const double* __restrict__ C_o, double dt, double dx,
                               double dy, double dz, int nx, int ny, int nz)
 {
@@ -480,6 +484,8 @@ __global__ void advect_kernel(double* __restrict__ Vx, const double* __restrict_
         const double vyc = 0.25 * (((VYO(ix - 1, iy, iz) + VYO(ix - 1, iy + 1, iz)) + VYO(ix, iy, iz)) + VYO(ix, iy + 1, iz));
         const double vzc = 0.25 * (((VZO(ix - 1, iy, iz) + VZO(ix - 1, iy, iz + 1)) + VZO(ix, iy, iz)) + VZO(ix, iy, iz + 1));
         Vx[idx3(ix - 1, iy - 1, iz - 1, nx + 1, ny)] = backtrack(Vx_o, vxc, vyc, vzc, dt, dx, dy, dz, ix, iy, iz, nx + 1, ny, nz);
+    } else if (ALL && iy <= ny && iz <= nz) {
+        Vx[idx3(ix - 1, iy - 1, iz - 1, nx + 1, ny)] = VXO(ix, iy, iz);
     }
     const bool b3 = iz > 1 && iz < nz + 1 && ix <= nx && iy <= ny;
     const bool b2 = iy > 1 && iy < ny + 1 && ix <= nx && iz <= nz;
@@ -493,7 +499,10 @@ __global__ void advect_kernel(double* __restrict__ Vx, const double* __restrict_
         const double vyc = VYO(ix, iy, iz);
         const double vzc = 0.25 * (((VZO(ix, iy - 1, iz) + VZO(ix, iy - 1, iz + 1)) + VZO(ix, iy, iz)) + VZO(ix, iy, iz + 1));
         Vy[idx3(ix - 1, iy - 1, iz - 1, nx, ny + 1)] = backtrack(Vy_o, vxc, vyc, vzc, dt, dx, dy, dz, ix, iy, iz, nx, ny + 1, nz);
+    } else if (ALL && ix <= nx && iz <= nz) {
+        Vy[idx3(ix - 1, iy - 1, iz - 1, nx, ny + 1)] = VYO(ix, iy, iz);
     }
+    if (ALL && ix <= nx && iy <= ny) Vz[idx3(ix - 1, iy - 1, iz - 1, nx, ny)] = VZO(ix, iy, iz);
     if (ix <= nx && iy <= ny && iz <= nz) {
         const double vxc = 0.5 * (VXO(ix, iy, iz) + VXO(ix + 1, iy, iz));
         const double vyc = 0.5 * (VYO(ix, iy, iz) + VYO(ix, iy + 1, iz));
@@ -507,10 +516,21 @@ extern "C" int ns3d_advect(ns3d_ctx* ctx, double* Vx, const double* Vx_o, double
                            double dy, double dz, int nx, int ny, int nz)
 {
     NS3D_CHECK_CTX(ctx);
-    (void)Vz;  // never written by the reference (M:234)
     NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
-    advect_kernel<<<grid3(nx + 1, ny + 1, nz + 1), block3(), 0, ctx->stream>>>(Vx, Vx_o, Vy, Vy_o, Vz_o, C, C_o, dt, dx, dy,
-                                                                              dz, nx, ny, nz);
+    // Vz is never written by the reference (M:234)
+    advect_kernel<false><<<grid3(nx + 1, ny + 1, nz + 1), block3(), 0, ctx->stream>>>(Vx, Vx_o, Vy, Vy_o, Vz, Vz_o, C, C_o, dt, dx,
+                                                                                     dy, dz, nx, ny, nz);
+    NS3D_LAUNCH_CHECK(ctx);
+    return NS3D_OK;
+}
+
+// advect! that also carries the untouched entries over from the `_o` arrays (see advect_kernel<ALL>): ns3d_step.
+int ns3d_internal_advect_all(ns3d_ctx* ctx, double* Vx, const double* Vx_o, double* Vy, const double* Vy_o, double* Vz,
+                             const double* Vz_o, double* C, const double* C_o, double dt, double dx, double dy, double dz, int nx,
+                             int ny, int nz)
+{
+    advect_kernel<true><<<grid3(nx + 1, ny + 1, nz + 1), block3(), 0, ctx->stream>>>(Vx, Vx_o, Vy, Vy_o, Vz, Vz_o, C, C_o, dt, dx, dy,
+                                                                                    dz, nx, ny, nz);
     NS3D_LAUNCH_CHECK(ctx);
     return NS3D_OK;
 }

@@ -54,57 +54,58 @@ extern "C" int ns3d_pt_describe(ns3d_ctx* ctx, const ns3d_pt_params* p, char* bu
 }
 
 // ---- level 2: the three once-per-step groups around the PT loop, and the whole step ---------------
+// z-slab halo exchange of the velocity triple / of cell fields (update_halo!, M:453,455,167,477)
 namespace {
-int step_cylinder(ns3d_ctx* ctx, const ns3d_fields* f, const ns3d_step_params* sp)
+int halo_V(ns3d_ctx* ctx, double* Vx, double* Vy, double* Vz, double* C, int nx, int ny, int nz)
+{
+    if (ctx->nranks == 1) return NS3D_OK;
+    double* h[4] = {Vx, Vy, Vz, C};
+    const int sx[4] = {nx + 1, nx, nx, nx}, sy[4] = {ny, ny + 1, ny, ny}, sz[4] = {nz, nz, nz + 1, nz};
+    return ns3d_internal_halo_z(ctx, ctx->stream, h, sx, sy, sz, C ? 4 : 3, nz);
+}
+int halo_cell(ns3d_ctx* ctx, double* A, int nx, int ny, int nz)
+{
+    if (ctx->nranks == 1) return NS3D_OK;
+    double* h[1] = {A};
+    return ns3d_internal_halo_z(ctx, ctx->stream, h, &nx, &ny, &nz, 1, nz);
+}
+int set_bc_vel(ns3d_ctx* ctx, double* Vx, double* Vy, double* Vz, const ns3d_step_params* sp)
 {
     const ns3d_pt_params& p = sp->pt;
-    return p.variant == NS3D_VARIANT_M
-               ? ns3d_set_cylinder_M(ctx, f->C, f->Vx, f->Vy, f->Vz, sp->a2, sp->b2, sp->ox, sp->oy, sp->sinb, sp->cosb,
-                                     sp->xco_g, sp->yco_g, p.dx, p.dy, p.nx, p.ny, p.nz)
-               : ns3d_set_cylinder_G(ctx, f->C, f->Vx, f->Vy, f->Vz, sp->a2, sp->b2, sp->ox, sp->oy, sp->sinb, sp->cosb,
-                                     sp->lx, sp->ly, p.dx, p.dy, p.nx, p.ny, p.nz);
+    if (p.variant == NS3D_VARIANT_M) return ns3d_set_bc_Vel_M(ctx, Vx, Vy, Vz, sp->inlet_guard, sp->vin, p.nx, p.ny, p.nz);  // M:474
+    return ns3d_set_bc_Vel_G(ctx, Vx, Vy, Vz, p.nx, p.ny, p.nz);                                                             // G:140
 }
 }  // namespace
 
-// Chorin predictor, M:449-455 / G:121-124: update_τ!, predict_V!, set_cylinder!, update_∇V! and the
-// halo updates between them (update_halo!(τxx,τyy,τzz) M:450 is redundant: τ is computed on the
-// halo cells too).
+// Chorin predictor, M:449-455 / G:121-124: update_τ!, predict_V!, set_cylinder!, update_∇V! and the halo updates
+// between them (update_halo!(τxx,τyy,τzz) M:450 is redundant: the stresses are computed on the halo cells too).
+// The first three are ONE kernel (predictor_kernel, ns3d_step.cu) that writes the predicted velocity into the
+// `_o` arrays (scratch at this point of a step: M:475 overwrites them before they are read again); as a stand-alone
+// group it is copied back so that Vx, Vy, Vz hold it as after the reference's lines.  The stress arrays are not used.
 extern "C" int ns3d_predictor(ns3d_ctx* ctx, const ns3d_fields* f, const ns3d_step_params* sp)
 {
     NS3D_CHECK_CTX(ctx);
     if (!f || !sp) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_predictor: NULL argument");
     const ns3d_pt_params& p = sp->pt;
     const int nx = p.nx, ny = p.ny, nz = p.nz;
-    NS3D_TRY(ns3d_update_tau(ctx, f->txx, f->tyy, f->tzz, f->txy, f->txz, f->tyz, f->Vx, f->Vy, f->Vz, sp->mu, p.dx, p.dy,
-                             p.dz, nx, ny, nz));                                                       // M:449
-    NS3D_TRY(ns3d_predict_V(ctx, f->Vx, f->Vy, f->Vz, f->txx, f->tyy, f->tzz, f->txy, f->txz, f->tyz, p.rho, p.g, p.dt,
-                            p.dx, p.dy, p.dz, nx, ny, nz));                                            // M:451
-    NS3D_TRY(step_cylinder(ctx, f, sp));                                                               // M:452
-    if (ctx->nranks > 1) {                                                                             // M:453
-        double* h[4] = {f->C, f->Vx, f->Vy, f->Vz};
-        const int sx[4] = {nx, nx + 1, nx, nx}, sy[4] = {ny, ny, ny + 1, ny}, sz[4] = {nz, nz, nz, nz + 1};
-        NS3D_TRY(ns3d_internal_halo_z(ctx, ctx->stream, h, sx, sy, sz, 4, nz));
-    }
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    NS3D_TRY(ns3d_internal_predict_fused(ctx, f->Vx_o, f->Vy_o, f->Vz_o, f->C, f->Vx, f->Vy, f->Vz, sp));  // M:449-452
+    NS3D_TRY(ns3d_copy(ctx, f->Vx, f->Vx_o, (size_t)(nx + 1) * ny * nz));
+    NS3D_TRY(ns3d_copy(ctx, f->Vy, f->Vy_o, (size_t)nx * (ny + 1) * nz));
+    NS3D_TRY(ns3d_copy(ctx, f->Vz, f->Vz_o, (size_t)nx * ny * (nz + 1)));
+    NS3D_TRY(halo_V(ctx, f->Vx, f->Vy, f->Vz, f->C, nx, ny, nz));                                      // M:453
     NS3D_TRY(ns3d_update_divV(ctx, f->divV, f->Vx, f->Vy, f->Vz, p.dx, p.dy, p.dz, nx, ny, nz));      // M:454
-    if (ctx->nranks > 1) {                                                                             // M:455
-        double* h[1] = {f->divV};
-        NS3D_TRY(ns3d_internal_halo_z(ctx, ctx->stream, h, &nx, &ny, &nz, 1, nz));
-    }
-    return NS3D_OK;
+    return halo_cell(ctx, f->divV, nx, ny, nz);                                                        // M:455
 }
 
-// Pressure-gradient correction, M:472-474 / G:138-140: correct_V!, set_cylinder!, set_bc_Vel!.
+// Pressure-gradient correction, M:472-474 / G:138-140: correct_V! + set_cylinder! in one kernel (in place), set_bc_Vel!.
 extern "C" int ns3d_corrector(ns3d_ctx* ctx, const ns3d_fields* f, const ns3d_step_params* sp)
 {
     NS3D_CHECK_CTX(ctx);
     if (!f || !sp) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_corrector: NULL argument");
-    const ns3d_pt_params& p = sp->pt;
-    const int nx = p.nx, ny = p.ny, nz = p.nz;
-    NS3D_TRY(ns3d_correct_V(ctx, f->Vx, f->Vy, f->Vz, f->Pr, p.dt, p.rho, p.dx, p.dy, p.dz, nx, ny, nz));   // M:472
-    NS3D_TRY(step_cylinder(ctx, f, sp));                                                               // M:473
-    if (p.variant == NS3D_VARIANT_M)
-        return ns3d_set_bc_Vel_M(ctx, f->Vx, f->Vy, f->Vz, sp->inlet_guard, sp->vin, nx, ny, nz);      // M:474
-    return ns3d_set_bc_Vel_G(ctx, f->Vx, f->Vy, f->Vz, nx, ny, nz);                                    // G:140
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    NS3D_TRY(ns3d_internal_correct_fused(ctx, f->Vx, f->Vy, f->Vz, f->C, nullptr, f->Pr, sp));   // M:472-473
+    return set_bc_vel(ctx, f->Vx, f->Vy, f->Vz, sp);                                             // M:474
 }
 
 // Advection, M:475-477 / G:141-142: the four snapshots `A_o .= A`, advect! and update_halo!(Vx,Vy,Vz).
@@ -120,22 +121,29 @@ extern "C" int ns3d_advect_swap(ns3d_ctx* ctx, const ns3d_fields* f, const ns3d_
     NS3D_TRY(ns3d_copy(ctx, f->C_o, f->C, (size_t)nx * ny * nz));
     NS3D_TRY(ns3d_advect(ctx, f->Vx, f->Vx_o, f->Vy, f->Vy_o, f->Vz, f->Vz_o, f->C, f->C_o, p.dt, p.dx, p.dy, p.dz, nx,
                          ny, nz));                                                                     // M:476
-    if (ctx->nranks > 1) {                                                                             // M:477
-        double* h[3] = {f->Vx, f->Vy, f->Vz};
-        const int sx[3] = {nx + 1, nx, nx}, sy[3] = {ny, ny + 1, ny}, sz[3] = {nz, nz, nz + 1};
-        NS3D_TRY(ns3d_internal_halo_z(ctx, ctx->stream, h, sx, sy, sz, 3, nz));
-    }
-    return NS3D_OK;
+    return halo_V(ctx, f->Vx, f->Vy, f->Vz, nullptr, nx, ny, nz);                                      // M:477
 }
 
-// One time step, M:449-477 / G:121-142 = predictor, PT loop, corrector, advection.
+// One time step, M:449-477 / G:121-142.  The velocity makes one round trip per step: predictor V -> V_o, corrector and
+// boundary conditions in place on V_o, advection V_o -> V (see ns3d_step.cu) -- 27 field passes around the PT loop
+// instead of the 47 of the call-by-call sequence, no stress arrays (f->t** may be NULL), no `A_o .= A` copies; on return
+// every other array holds what the reference's step leaves in it (V_o, C_o: the pre-advection snapshot of M:475).
 extern "C" int ns3d_step(ns3d_ctx* ctx, const ns3d_fields* f, const ns3d_step_params* sp, int* h_iters,
                          double* h_err_hist, int err_cap, int* h_nchecks)
 {
     NS3D_CHECK_CTX(ctx);
     if (!f || !sp) return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_step: NULL argument");
-    NS3D_TRY(ns3d_predictor(ctx, f, sp));                                                              // M:449-455
+    const ns3d_pt_params& p = sp->pt;
+    const int nx = p.nx, ny = p.ny, nz = p.nz;
+    NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
+    NS3D_TRY(ns3d_internal_predict_fused(ctx, f->Vx_o, f->Vy_o, f->Vz_o, f->C, f->Vx, f->Vy, f->Vz, sp));  // M:449-452
+    NS3D_TRY(halo_V(ctx, f->Vx_o, f->Vy_o, f->Vz_o, f->C, nx, ny, nz));                                     // M:453
+    NS3D_TRY(ns3d_update_divV(ctx, f->divV, f->Vx_o, f->Vy_o, f->Vz_o, p.dx, p.dy, p.dz, nx, ny, nz));     // M:454
+    NS3D_TRY(halo_cell(ctx, f->divV, nx, ny, nz));                                                          // M:455
     NS3D_TRY(ns3d_pt_solve(ctx, f->Pr, f->dPrdtau, f->divV, &sp->pt, h_iters, h_err_hist, err_cap, h_nchecks));  // M:458-471
-    NS3D_TRY(ns3d_corrector(ctx, f, sp));                                                              // M:472-474
-    return ns3d_advect_swap(ctx, f, sp);                                                               // M:475-477
+    NS3D_TRY(ns3d_internal_correct_fused(ctx, f->Vx_o, f->Vy_o, f->Vz_o, f->C, f->C_o, f->Pr, sp));         // M:472-473, C_o .= C
+    NS3D_TRY(set_bc_vel(ctx, f->Vx_o, f->Vy_o, f->Vz_o, sp));                                               // M:474
+    NS3D_TRY(ns3d_internal_advect_all(ctx, f->Vx, f->Vx_o, f->Vy, f->Vy_o, f->Vz, f->Vz_o, f->C, f->C_o, p.dt, p.dx, p.dy, p.dz,
+                                      nx, ny, nz));                                                         // M:475-476
+    return halo_V(ctx, f->Vx, f->Vy, f->Vz, nullptr, nx, ny, nz);                                           // M:477
 }

@@ -33,6 +33,18 @@ __device__ __forceinline__ unsigned long long atom_add_acq_rel_gpu(unsigned long
     return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL);
 }
 __device__ __forceinline__ unsigned long long wall_ns() { return emu::wall_ns(); }
+// work queue / completion counters of the persistent launch (ptv_flow_kernel)
+__device__ __forceinline__ unsigned atom_add_relaxed_gpu(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+__device__ __forceinline__ void atom_add_release_gpu(unsigned* p, unsigned v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+__device__ __forceinline__ void fence_acq_rel_gpu() { __atomic_thread_fence(__ATOMIC_ACQ_REL); }
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void spin_pause() { emu::spin_pause(); }
+__device__ __forceinline__ unsigned ld_min3_relaxed(const unsigned* a, const unsigned* b, const unsigned* c)
+{
+    return min(min(ld_relaxed_gpu(a), ld_relaxed_gpu(b)), ld_relaxed_gpu(c));
+}
 #else
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
 {
@@ -50,6 +62,41 @@ __device__ __forceinline__ unsigned long long atom_add_acq_rel_gpu(unsigned long
     asm volatile("atom.add.acq_rel.gpu.global.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
     return old;
 }
+// work queue / completion counters of the persistent launch (ptv_flow_kernel)
+__device__ __forceinline__ unsigned atom_add_relaxed_gpu(unsigned* p, unsigned v)
+{
+    unsigned old;
+    asm volatile("atom.add.relaxed.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void atom_add_release_gpu(unsigned* p, unsigned v)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Polling without side effects: an acquire load is followed by an invalidation of the SM's whole L1 (CCTL.IVALL), which a
+// spinning thread repeats in every round -- ncu showed the other CTAs of the SM missing L1 on everything they had there.
+// The counters are polled relaxed (served from L2), ONE fence follows the successful poll.
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// min(*a, *b, *c), polled relaxed (served from L2: no invalidation of the SM's L1 like after an acquire load)
+__device__ __forceinline__ unsigned ld_min3_relaxed(const unsigned* a, const unsigned* b, const unsigned* c)
+{
+    return min(min(ld_relaxed_gpu(a), ld_relaxed_gpu(b)), ld_relaxed_gpu(c));
+}
+// what this thread has observed through the generic proxy is visible to the TMA copies (async proxy) it issues next
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void spin_pause() { __nanosleep(64); }
 // nanoseconds of wall-clock time, independent of the SM clock (the spin limit must not depend on it)
 __device__ __forceinline__ unsigned long long wall_ns()
 {
@@ -60,6 +107,7 @@ __device__ __forceinline__ unsigned long long wall_ns()
 #endif
 
 #define NS3D_SPIN_LIMIT_NS 20000000000ULL  // 20 s of wall-clock time
+#define NS3D_FLOW_WAIT_LOOKS 1000000u  // looks at the counters (~2 us each) before a work item of ptv_flow_kernel gives up: ~2 s
 
 // Spins until the neighbour on `side` (0 lower, 1 upper) has finished the face work of every
 // launch this rank has finished: then its stores into our halo plane have landed and it no

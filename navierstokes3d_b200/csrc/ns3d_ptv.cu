@@ -68,12 +68,14 @@ PtvPlan make_plan(const ns3d_ctx* ctx, bool slabs)
 // about one wave some SMs hold 3 CTAs and others 2 until the end), long enough to amortise the 2(K-1) planes every
 // chunk recomputes and its prologue.  Measured at 255x153x153 (profiles/r02_ptv_sweep_B.jsonl): 10-13 planes beat 19
 // and 38; at 511^3 the tiles alone give more than four waves and chunks are a hundred planes long.
-int auto_zchunk(const ns3d_ctx* ctx, const PtV& k, int K, int planes, int lb)
+int auto_zchunk(const ns3d_ctx* ctx, const PtV& k, int K, int planes, int lb, bool flow = false)
 {
     const long long tiles = (long long)k.ntx * k.nty;
     const int ctas = std::max(1, std::min(ptv_lb_ctas(lb), (int)(227u * 1024u / std::max(1u, k.sm_total + 1024u))));
     const long long slots = (long long)ctx->num_sms * ctas;   // CTAs resident at a time: registers, shared memory
-    const long long want = 4 * slots;                         // CTAs for four waves
+    // persistent launch: no waves to fill -- the chunks only have to be numerous enough that the items an item waits for
+    // (the adjacent chunks of the previous launch) were claimed about two sets of resident CTAs earlier
+    const long long want = flow ? 2 * slots + 2 * tiles : 4 * slots;   // CTAs for four waves
     long long nch = (want + tiles - 1) / tiles;
     if (nch < 1) nch = 1;
     int len = (int)((planes + nch - 1) / nch);
@@ -86,7 +88,7 @@ int auto_zchunk(const ns3d_ctx* ctx, const PtV& k, int K, int planes, int lb)
     return len;
 }
 
-int make_ptv(ns3d_ctx* ctx, const ns3d_pt_params* p, const PtvPlan& pl, int K, PtV* k)
+int make_ptv(ns3d_ctx* ctx, const ns3d_pt_params* p, const PtvPlan& pl, int K, PtV* k, bool flow = false)
 {
     memset(k, 0, sizeof *k);
     ptv_fill(p, k);
@@ -108,7 +110,7 @@ int make_ptv(ns3d_ctx* ctx, const ns3d_pt_params* p, const PtvPlan& pl, int K, P
     if (k->bty > PTV_HMAX || ptv_threads(*k) > ptv_lb_threads(pl.lb))
         return ns3d_fail(ctx, NS3D_EINVAL, "pt: tile of %d x %d threads does not fit the kernel (at most %d threads, %d rows)", k->pxt,
                          k->bty, ptv_lb_threads(pl.lb), PTV_HMAX);
-    k->zchunk = p->zchunk > 0 ? p->zchunk : auto_zchunk(ctx, *k, K, p->nz - 2, pl.lb);
+    k->zchunk = p->zchunk > 0 ? p->zchunk : auto_zchunk(ctx, *k, K, p->nz - 2, pl.lb, flow);
     return NS3D_OK;
 }
 
@@ -180,6 +182,25 @@ int ptv_peer_prepare(ns3d_ctx* ctx, int nz, PtvPeers* pp, bool* on)
     return NS3D_OK;
 }
 
+// Work queue and completion counters of the persistent launch, for up to `iters` iterations in one launch
+// (at most one counter per launch and plane).  Allocated outside stream capture; growing it drops the cached graphs,
+// which hold its address.
+int ptv_work_ensure(ns3d_ctx* ctx, int iters, int nz)
+{
+    const size_t words = PTV_WORK_DONE + (size_t)std::max(iters, 1) * (size_t)nz + 32;   // last word: the sticky error flag
+    if (words <= ctx->ptv_work_words) return NS3D_OK;
+    NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ns3d_internal_ptv_free(ctx);
+    if (ctx->ptv_work) cudaFree(ctx->ptv_work);
+    ctx->ptv_work = nullptr;
+    ctx->ptv_work_words = 0;
+    NS3D_CUDA(ctx, cudaMalloc(&ctx->ptv_work, words * sizeof(unsigned)));
+    NS3D_CUDA(ctx, cudaMemsetAsync(ctx->ptv_work, 0, words * sizeof(unsigned), ctx->stream));
+    ctx->ptv_work_words = words;
+    ctx->h_maxbits[5] = 0ULL;
+    return NS3D_OK;
+}
+
 int ptv_pack(ns3d_ctx* ctx, double* dst, const double* src, int nx, int ny, int nz, int inner)
 {
     const int px = ptv_pitch(nx);
@@ -210,6 +231,12 @@ int ns3d_internal_ptv_launch_fast(ns3d_ctx* ctx, cudaStream_t st, const PtV& k, 
                                   bool tma, dim3 grid, size_t smem);
 int ns3d_internal_ptv_launch_fastest(ns3d_ctx* ctx, cudaStream_t st, const PtV& k, const PtvMaps& maps, const PtvPlan& pl, int K, bool p2p,
                                      bool tma, dim3 grid, size_t smem);
+int ns3d_internal_ptv_flow_launch_parity(ns3d_ctx* ctx, cudaStream_t st, const PtV& k, const PtvMaps& maps, const PtvPlan& pl, int K, bool tma,
+                                         size_t smem);
+int ns3d_internal_ptv_flow_launch_fast(ns3d_ctx* ctx, cudaStream_t st, const PtV& k, const PtvMaps& maps, const PtvPlan& pl, int K, bool tma,
+                                       size_t smem);
+int ns3d_internal_ptv_flow_launch_fastest(ns3d_ctx* ctx, cudaStream_t st, const PtV& k, const PtvMaps& maps, const PtvPlan& pl, int K, bool tma,
+                                          size_t smem);
 
 namespace {
 
@@ -256,8 +283,9 @@ int ptv_make_map(ns3d_ctx* ctx, PtvMaps::Map* out, const double* base, int px, i
     return NS3D_OK;
 }
 
-// One launch = K iterations of the planes [k.kbeg, k.kend) (or of the two interface chunks when k.faces).
-int ptv_launch(ns3d_ctx* ctx, cudaStream_t st, PtV k, const PtvPlan& pl, int K, bool p2p)
+// One launch = K iterations of the planes [k.kbeg, k.kend) (or of the two interface chunks when k.faces);
+// nlaunch > 0: the persistent launch, nlaunch x K iterations.
+int ptv_launch(ns3d_ctx* ctx, cudaStream_t st, PtV k, const PtvPlan& pl, int K, bool p2p, int nlaunch = 0)
 {
     if (!k.faces) ptv_balance_chunks(k);
     const dim3 grid((unsigned)(k.ntx * k.nty), k.faces ? 2u : cdiv(k.kend - k.kbeg, k.zchunk), 1);
@@ -272,8 +300,27 @@ int ptv_launch(ns3d_ctx* ctx, cudaStream_t st, PtV k, const PtvPlan& pl, int K, 
         NS3D_TRY(ptv_make_map(ctx, &maps.m[0], k.P, k.px, k.ny, k.nz, W + 4, H + 2));
         NS3D_TRY(ptv_make_map(ctx, &maps.m[1], k.D, k.px, k.ny, k.nz, W, H));
         NS3D_TRY(ptv_make_map(ctx, &maps.m[2], k.V, k.px, k.ny, k.nz, W, H));
+        if (nlaunch > 0) {   // odd launches read what even ones write
+            NS3D_TRY(ptv_make_map(ctx, &maps.m[3], k.PN, k.px, k.ny, k.nz, W + 4, H + 2));
+            NS3D_TRY(ptv_make_map(ctx, &maps.m[4], k.DN, k.px, k.ny, k.nz, W, H));
+        }
     }
 #endif
+    if (nlaunch > 0) {
+        k.nlaunch = nlaunch;
+        k.nbz = (int)grid.y;
+        const size_t words = PTV_WORK_DONE + (size_t)nlaunch * k.nbz;
+        if (words + 32 > ctx->ptv_work_words)   // ptv_work_ensure() sizes it ahead of any stream capture
+            return ns3d_fail(ctx, NS3D_EINVAL, "pt: the work queue holds %zu words, %zu needed", ctx->ptv_work_words, words);
+        k.work = ctx->ptv_work;
+        k.work_err = ctx->ptv_work + ctx->ptv_work_words - 1;
+        NS3D_CUDA(ctx, cudaMemsetAsync(ctx->ptv_work, 0, words * sizeof(unsigned), st));
+        switch (ctx->mode) {
+            case NS3D_PARITY: return ns3d_internal_ptv_flow_launch_parity(ctx, st, k, maps, pl, K, tma, smem);
+            case NS3D_FAST: return ns3d_internal_ptv_flow_launch_fast(ctx, st, k, maps, pl, K, tma, smem);
+            default: return ns3d_internal_ptv_flow_launch_fastest(ctx, st, k, maps, pl, K, tma, smem);
+        }
+    }
     switch (ctx->mode) {
         case NS3D_PARITY: return ns3d_internal_ptv_launch_parity(ctx, st, k, maps, pl, K, p2p, tma, grid, smem);
         case NS3D_FAST: return ns3d_internal_ptv_launch_fast(ctx, st, k, maps, pl, K, p2p, tma, grid, smem);
@@ -309,6 +356,22 @@ int ptv_run_direct(ns3d_ctx* ctx, PtvRun& r, int n, int iter0)
     const ns3d_pt_params* p = r.p;
     if (ctx->nranks > 1) NS3D_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
     int done = 0, launch = 0;
+    // single rank: all full launches of K iterations as ONE persistent launch (ptv_flow_kernel); an odd rest follows below
+    if (ctx->nranks == 1 && ctx->opt_ptv_flow && ptv_lb_threads(r.pl.lb) == 256 && n / r.pl.K >= 2) {
+        const int K = r.pl.K, L = n / K;
+        PtV k;
+        NS3D_TRY(make_ptv(ctx, p, r.pl, K, &k, true));
+        PtV probe = k;
+        ptv_balance_chunks(probe);
+        // an item waits for its own chunk and the two next to it in the previous launch: its planes +- K must lie in them
+        if (probe.zchunk >= K) {
+            ptv_bind(ctx, k, r.cur);
+            NS3D_TRY(ptv_launch(ctx, ctx->stream, k, r.pl, K, false, L));
+            if (L & 1) r.cur = 1 - r.cur;
+            done += L * K;
+            launch += L;
+        }
+    }
     while (done < n) {
         const int K = std::min(r.pl.K, n - done);
         PtV k;
@@ -380,7 +443,8 @@ struct PtvGraphCache {
 void opts_key(const ns3d_ctx* ctx, int (&o)[8])
 {
     o[0] = ctx->opt_ptv_k; o[1] = ctx->opt_ptv_ns; o[2] = ctx->opt_ptv_lb; o[3] = ctx->opt_ptv_pxt;
-    o[4] = ctx->opt_ptv_bty; o[5] = ctx->opt_serpentine; o[6] = ctx->opt_p2p; o[7] = ctx->opt_ptv_tma;
+    o[4] = ctx->opt_ptv_bty; o[5] = ctx->opt_serpentine; o[6] = ctx->opt_p2p;
+    o[7] = ctx->opt_ptv_tma | (ctx->opt_ptv_flow << 1);
 }
 
 int ptv_run(ns3d_ctx* ctx, PtvRun& r, int n, int iter0)
@@ -453,11 +517,12 @@ int ptv_residual(ns3d_ctx* ctx, const PtvRun& r)
 }
 
 // Pack the caller's arrays, agree with the neighbours that the previous solve is over.
-int ptv_begin(ns3d_ctx* ctx, PtvRun& r, const double* Pr, const double* dPrdtau, const double* divV)
+int ptv_begin(ns3d_ctx* ctx, PtvRun& r, const double* Pr, const double* dPrdtau, const double* divV, int max_chunk_iters)
 {
     const ns3d_pt_params* p = r.p;
     NS3D_CUDA(ctx, cudaSetDevice(ctx->device));
     NS3D_TRY(ptv_ensure(ctx, p->nx, p->ny, p->nz));
+    if (ctx->nranks == 1 && ctx->opt_ptv_flow) NS3D_TRY(ptv_work_ensure(ctx, max_chunk_iters, p->nz));
     r.pl = make_plan(ctx, ctx->nranks > 1);
     NS3D_TRY(ptv_peer_prepare(ctx, p->nz, &r.peers, &r.peer_on));
     if (ctx->nranks > 1 && !r.peer_on) r.pl.K = 1;  // NCCL halo exchange after every iteration
@@ -480,8 +545,14 @@ int ptv_end(ns3d_ctx* ctx, PtvRun& r, double* Pr, double* dPrdtau, bool sync)
     NS3D_TRY(ptv_unpack(ctx, dPrdtau, ctx->ptv[2 + r.cur], p->nx, p->ny, p->nz, 1));
     if (r.peer_on)
         NS3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_maxbits + 3, ctx->mbox + NS3D_MB_ERROR, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->ptv_work)
+        NS3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_maxbits + 5, ctx->ptv_work + ctx->ptv_work_words - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (sync || r.peer_on) {
         NS3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->ptv_work && (ctx->h_maxbits[5] & 0xffffffffULL) != 0ULL) {
+            cudaMemsetAsync(ctx->ptv_work + ctx->ptv_work_words - 1, 0, 4, ctx->stream);
+            return ns3d_fail(ctx, NS3D_ECUDA, "persistent PT launch: a work item waited for its predecessors beyond the spin limit");
+        }
         if (r.peer_on && ctx->h_maxbits[3] != 0ULL) {
             const unsigned long long who = ctx->h_maxbits[3];
             cudaMemsetAsync(ctx->mbox + NS3D_MB_ERROR, 0, 8, ctx->stream);  // reported: the next solve starts clean
@@ -508,6 +579,11 @@ void ns3d_internal_ptv_free(ns3d_ctx* ctx)
 void ns3d_internal_ptv_release(ns3d_ctx* ctx)
 {
     ns3d_internal_ptv_free(ctx);
+    if (ctx->ptv_work) {
+        cudaFree(ctx->ptv_work);
+        ctx->ptv_work = nullptr;
+        ctx->ptv_work_words = 0;
+    }
     for (int q = 0; q < 5; ++q) {
         if (!ctx->ptv_raw[q]) continue;
         ptv_unmap(ctx, ctx->ptv_raw[q]);
@@ -521,7 +597,7 @@ int ns3d_internal_ptv_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const do
 {
     PtvRun r;
     r.p = p;
-    NS3D_TRY(ptv_begin(ctx, r, Pr, dPrdtau, divV));
+    NS3D_TRY(ptv_begin(ctx, r, Pr, dPrdtau, divV, std::min(p->nchk, p->niter)));
     int iters = 0, nc = 0;
     while (iters < p->niter) {
         const int chunk = std::min(p->nchk - iters % p->nchk, p->niter - iters);  // up to the next check
@@ -547,7 +623,7 @@ int ns3d_internal_ptv_iterate(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const 
 {
     PtvRun r;
     r.p = p;
-    NS3D_TRY(ptv_begin(ctx, r, Pr, dPrdtau, divV));
+    NS3D_TRY(ptv_begin(ctx, r, Pr, dPrdtau, divV, n_iter));
     NS3D_TRY(ptv_run(ctx, r, n_iter, 0));
     return ptv_end(ctx, r, Pr, dPrdtau, false);
 }
@@ -557,14 +633,20 @@ int ns3d_internal_ptv_describe(ns3d_ctx* ctx, const ns3d_pt_params* p, char* buf
     const bool slabs = ctx->nranks > 1;
     PtvPlan pl = make_plan(ctx, slabs);
     if (slabs && !(ctx->opt_p2p && ctx->p2p_ready && p->nz >= 6)) pl.K = 1;
+    const bool flow = !slabs && ctx->opt_ptv_flow && ptv_lb_threads(pl.lb) == 256;
     PtV k;
-    NS3D_TRY(make_ptv(ctx, p, pl, pl.K, &k));
+    NS3D_TRY(make_ptv(ctx, p, pl, pl.K, &k, flow));
+    ptv_balance_chunks(k);
     const char* mode = ctx->mode == NS3D_PARITY ? "PARITY" : (ctx->mode == NS3D_FAST ? "FAST" : "FASTEST");
     if (buf && cap > 0)
         snprintf(buf, cap,
-                 "ptv_kernel<%s,K=%d> (%d fused PT iterations per launch: %d x (K5+K6+set_bc_Pr!) on the pitched copies, z-plane tiles "
-                 "staged by TMA; tiles of %d x %d cells, %d x %d tiles, %d-plane chunks, %d threads, %u B shared memory%s)",
-                 mode, pl.K, pl.K, pl.K, 2 * k.pxt, k.bty, k.ntx, k.nty, k.zchunk, ptv_threads(k), k.sm_total,
+                 "%s<%s,K=%d> (%s%d fused PT iterations per pass over the fields: %d x (K5+K6+set_bc_Pr!) on the pitched copies, z-plane "
+                 "tiles staged by TMA; tiles of %d x %d cells, %d x %d tiles, %d-plane chunks, %d threads, %u B shared memory%s)",
+                 flow ? "ptv_flow_kernel" : "ptv_kernel", mode, pl.K,
+                 flow ? "persistent: all passes between two residual checks are ONE launch, work items ordered by pass and z-chunk with "
+                        "per-chunk completion counters; "
+                      : "",
+                 pl.K, pl.K, 2 * k.pxt, k.bty, k.ntx, k.nty, k.zchunk, ptv_threads(k), k.sm_total,
                  slabs ? "; slab-interface chunks: the P2P instantiation with update_halo!(Pr) over peer memory" : "");
     if (iters_per_launch) *iters_per_launch = pl.K;
     return NS3D_OK;

@@ -90,7 +90,15 @@ struct PtV {
     const double* peer_hi_cur;         // upper neighbour's Pr plane 2      (= local plane nz)
     const double* peer_lo_dp;          // lower neighbour's dPrdτ plane nz-2 (= local plane 0)
     const double* peer_hi_dp;          // upper neighbour's dPrdτ plane 1    (= local plane nz-1)
+    // persistent launch (ptv_flow_kernel): `nlaunch` launches of K iterations each in ONE kernel.  Work item w is tile
+    // w % (ntx*nty) of z-chunk (w / (ntx*nty)) % nbz of launch w / (ntx*nty*nbz); launch l reads the buffers launch l-1
+    // wrote (P/PN and D/DN swap roles every launch).  work[0] = the queue (next unclaimed item), work[PTV_WORK_DONE + l*nbz + c]
+    // = finished items of chunk c of launch l.
+    unsigned* work;
+    unsigned* work_err;   // sticky: set when a dependency wait ran into the spin limit
+    int nlaunch, nbz;
 };
+enum { PTV_WORK_DONE = 32 };   // the counters start one 128-byte line after the queue
 
 // iterations per launch and launch-bounds variant of ptv_kernel (threads per CTA / CTAs per SM the kernel is
 // compiled for: 0 = 256 / 2 (128 registers), 1 = 256 / 3 (80), 3 = 512 / 1 (128), 4 = 512 / 2 (64))
@@ -104,10 +112,11 @@ inline int ptv_lb_ctas(int lb) { return lb == 0 ? 2 : (lb == 1 ? 3 : (lb == 3 ? 
 
 // The TMA descriptors of one launch: Pr (current iterate), dPrdτ (current), ∇V -- 3-D tensor maps over the pitched
 // arrays (dims px x ny x nz), box = the CTA's tile (with halo for Pr).  128 opaque bytes each (CUtensorMap).
+// m[3], m[4]: Pr and dPrdτ of the OTHER pair of ping-pong buffers (odd launches of a persistent launch).
 struct alignas(64) PtvMaps {
     struct alignas(64) Map {
         unsigned long long opaque[16];
-    } m[3];
+    } m[5];
 };
 // Keeps a per-thread value in a register: without it ptxas re-derives loop invariants from %tid / %ctaid in every
 // iteration to stay under the register cap (measured in SASS).
@@ -220,7 +229,8 @@ __device__ __forceinline__ double ptv_xface(const PtV& p, bool hi, int k, double
 
 // Per-thread constants of a launch.  Everything that concerns a domain face sits behind ONE flag per kind of
 // store (`rs` for the ring of the intermediate iterates, `own == 2` for the final stores), so that warps without
-// such threads -- almost all -- execute a single branch for it.
+// such threads -- almost all -- execute a single branch for it.  (Separate ints on purpose: ptxas keeps the ones the
+// hot loop tests in predicate registers; packed into one word they cost general registers and the kernel spilled.)
 struct PtvThread {
     int own;       // 0: stores nothing; 1: stores the results of its pair, no face nearby; 2: ... with face images
     int rs;        // the pair needs special treatment when it is published in the ring (a face column / row nearby)
@@ -232,16 +242,19 @@ struct PtvThread {
     int peer_ok;   // P2P: both neighbours answered
 };
 
-// CTA-uniform constants of a launch: the steps at which stage m works (plane t - m), copies the upper z-face image,
-// sets the lower one; strides in bytes.
+// CTA-uniform constants of a work item: the steps at which stage m works (plane t - m), copies the upper z-face image,
+// sets the lower one; strides in bytes.  (Kept in registers: read from shared memory in every step -- tried, to relieve the
+// register allocation -- they put five dependent loads in front of each step and cost 7 %.)
 template <int K>
 struct PtvUni {
+    int ts_lo, ts_hi;             // steady steps: every stage works and none of the z-face cases applies
+    int last_load, t_last;        // last plane of iterate 0 the item reads; its last step
     int tlo[K + 1], thi[K + 1];   // stage m computes at steps tlo[m] <= t <= thi[m]
     int timg[K + 1];              // step at which stage m < K takes plane nz-1 as the image of plane nz-2 (-1: never)
     int tz1[K + 1];               // step at which stage m < K also sets plane 0 as the image of plane 1 (-1: never)
     int t_out1, t_outn;           // steps at which stage K puts out plane 1 / plane nz-2
-    int ts_lo, ts_hi;             // steady steps: every stage works and none of the above applies
-    long long planeB, oDN;
+    long long oDN;                // from a cell of the Pr buffer the item writes to the same cell of its dPrdτ buffer
+    char* pn;                     // element (0,0,0) of the Pr buffer the item writes
 };
 
 // ---- shared memory by 32-bit address ------------------------------------------------------------------------------
@@ -350,20 +363,24 @@ __device__ __forceinline__ void ptv_mbar_expect(sa_t bar, unsigned bytes)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded: a copy that never completes (a bad descriptor) traps instead of hanging the GPU.
+__device__ __forceinline__ bool ptv_mbar_try(sa_t bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0u;
+}
 __device__ __forceinline__ void ptv_mbar_wait(sa_t bar, unsigned parity)
 {
     for (unsigned n = 0;; ++n) {
-        unsigned ok;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred P1;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, P1;\n\t"
-            "}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) return;
+        if (ptv_mbar_try(bar, parity)) return;
         if (n > (1u << 24)) __trap();
     }
 }
@@ -472,14 +489,14 @@ __device__ __forceinline__ void ptv_step(const PtV& p, const PtvThread& v, const
                 if (v.own) ptv_st2(o + u.oDN, dn0, dn1);
                 ptv_store_plane(p, v, o, t - K, u0, u1);
                 if (!STEADY && t == u.t_out1) {
-                    if (!p.zlo_halo) ptv_store_plane(p, v, o - u.planeB, 0, u0, u1);  // bc_z! M:129
+                    if (!p.zlo_halo) ptv_store_plane(p, v, o - p.planeB, 0, u0, u1);  // bc_z! M:129
                     else if (P2P && v.peer_ok)  // update_halo!(Pr): our plane 1 is the lower neighbour's halo plane
-                        ptv_store_plane(p, v, (char*)p.peer_lo_plane + (o - ((char*)p.PN + u.planeB)), 1, u0, u1);
+                        ptv_store_plane(p, v, (char*)p.peer_lo_plane + (o - (u.pn + p.planeB)), 1, u0, u1);
                 }
                 if (!STEADY && t == u.t_outn) {
-                    if (!p.zhi_halo) ptv_store_plane(p, v, o + u.planeB, p.nz - 1, u0, u1);  // bc_z! M:130
+                    if (!p.zhi_halo) ptv_store_plane(p, v, o + p.planeB, p.nz - 1, u0, u1);  // bc_z! M:130
                     else if (P2P && v.peer_ok)
-                        ptv_store_plane(p, v, (char*)p.peer_hi_plane + (o - ((char*)p.PN + (long long)(p.nz - 2) * u.planeB)), p.nz - 2, u0, u1);
+                        ptv_store_plane(p, v, (char*)p.peer_hi_plane + (o - (u.pn + (long long)(p.nz - 2) * p.planeB)), p.nz - 2, u0, u1);
                 }
             }
         } else if (!STEADY && m < K && t == u.timg[m]) {
@@ -492,13 +509,14 @@ __device__ __forceinline__ void ptv_step(const PtV& p, const PtvThread& v, const
 // Plain-load staging of one plane (z-slab interface chunks, whose first / last planes live in a neighbour's memory, and
 // the host emulation): every thread copies box elements, zero-filling what lies outside the arrays like the TMA unit.
 template <bool P2P>
-__device__ __forceinline__ void ptv_coop_stage(const PtV& p, char* slot, int q, int X0, int Y0, bool lo_face, bool hi_face)
+__device__ __forceinline__ void ptv_coop_stage(const PtV& p, const double* P, const double* D, char* slot, int q, int X0, int Y0,
+                                               bool lo_face, bool hi_face)
 {
     const int W = 2 * p.pxt, H = p.bty;
     const int nthreads = blockDim.x, tid = threadIdx.x;
     const long long plane = p.planeB / 8;
-    const double* Psrc = p.P + (long long)q * plane;
-    const double* Dsrc = p.D + (long long)q * plane;
+    const double* Psrc = P + (long long)q * plane;
+    const double* Dsrc = D + (long long)q * plane;
     const double* Vsrc = p.V + (long long)q * plane;
     if (P2P) {
         if (q == -1) Psrc = p.peer_lo_cur;          // the lower neighbour's plane nz-3
@@ -534,43 +552,48 @@ __device__ __forceinline__ void ptv_coop_stage(const PtV& p, char* slot, int q, 
     }
 }
 
-template <int MODE, int K, bool P2P, bool TMA, int PXT, int BTY, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) ptv_kernel(const PtV p, const __grid_constant__ PtvMaps maps)
+// One work item: K iterations of the planes of z-chunk `bz` (of `nbz`) in the columns of tile `tile`.  `flip`: the launch
+// reads PN / DN and writes P / D (odd launches of a persistent launch); `init_bars`: the CTA's first item initialises the
+// slots' mbarriers; CARRY (persistent launch): later items of the CTA carry on with slots and mbarrier parities where the
+// last one stopped (s_loads counts the CTA's copies) -- the mbarriers are never initialised twice (an mbarrier.inval +
+// mbarrier.init pair per item, the first version of this, hung a launch-bounds variant of the kernel on hardware: the
+// invalidation is not ordered with the store that initialises) -- and the item's first copies wait for `gate()`.
+template <int MODE, int K, bool P2P, bool TMA, bool CARRY, int PXT, int BTY, class Gate>
+__device__ __forceinline__ void ptv_item(const PtV& p, const PtvMaps& maps, char* smem, const int tile, int bz, const int nbz,
+                                         const bool flip, const bool init_bars, Gate gate)
 {
     typedef PtvGeo<PXT, BTY> G;
-#ifdef NS3D_HOST_EMU
-    char* smem = (char*)emu::dyn_smem();
-#else
-    extern __shared__ __align__(128) char ptv_smem[];
-    char* smem = ptv_smem;
-#endif
     const sa_t sb = sa_base(smem);
     const int nx = p.nx, ny = p.ny, nz = p.nz;
     const int NS = G::CT ? 4 : p.ns;
     const int pxt = G::pxt(p), bty = G::bty(p);
+    const double* const P = flip ? p.PN : p.P;
+    double* const PN = flip ? const_cast<double*>(p.P) : p.PN;
+    const double* const D = flip ? p.DN : p.D;
+    double* const DN = flip ? const_cast<double*>(p.D) : p.DN;
     int ty = (int)threadIdx.x / pxt;
     const int tx = (int)threadIdx.x - ty * pxt;
     const bool dup = ty >= bty;   // surplus threads of the last warp shadow a thread of the last row (same values, no stores)
     if (dup) ty = bty - 1;
-    const int bxi = (int)blockIdx.x / p.nty, byi = (int)blockIdx.x - bxi * p.nty;   // y tiles fastest
-    int bz = blockIdx.y;
-    if (p.reverse && !p.faces) bz = gridDim.y - 1 - bz;
+    const int bxi = tile / p.nty, byi = tile - bxi * p.nty;   // y tiles fastest
+    if (p.reverse && !p.faces) bz = nbz - 1 - bz;
     const int kb = p.faces ? (bz == 0 ? 1 : nz - 1 - p.zchunk) : p.kbeg + bz * p.zchunk;
     const int ke = p.faces ? kb + p.zchunk : min(kb + p.zchunk, p.kend);   // stage-K planes [kb, ke)
     const bool lo_face = P2P && p.zlo_halo && kb == 1;
     const bool hi_face = P2P && p.zhi_halo && ke == nz - 1;
     __shared__ int s_peer_ok;
+    __shared__ unsigned s_loads;   // CARRY: TMA copies the CTA has issued in its earlier items
     PtvThread v;
-    v.peer_ok = 1;
+    bool peer_ok = true;
     const unsigned pboxB = G::pboxB(p), dboxB = G::dboxB(p), slotB = G::slotB(p);
     const sa_t bars = sb + p.sm_bars, stage0 = sb + p.sm_stage;
-    const sa_t stage_end = stage0 + (unsigned)NS * slotB;
 #if !defined(NS3D_HOST_EMU)
-    if (TMA && threadIdx.x == 0) {
+    if (TMA && init_bars && threadIdx.x == 0) {
         for (int q = 0; q < NS; ++q) ptv_mbar_init(bars + 8 * q, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 #endif
+    if (CARRY && init_bars && threadIdx.x == 0) s_loads = 0u;
     if (P2P && (lo_face | hi_face)) {
         if (threadIdx.x == 0) {
             bool ok = true;
@@ -579,13 +602,14 @@ __global__ void __launch_bounds__(NT, MINB) ptv_kernel(const PtV p, const __grid
             s_peer_ok = ok;
         }
         __syncthreads();
-        v.peer_ok = s_peer_ok;
+        peer_ok = s_peer_ok != 0;
     } else {
         __syncthreads();   // the mbarriers are initialised
     }
     const int W = 2 * pxt, H = bty;
     const int X0 = bxi * p.sx, Y0 = byi * p.sy;
     const int i0 = X0 + 2 * tx;
+    v.peer_ok = peer_ok;
     v.j0 = Y0 + ty;
     v.lo_pair = i0 == 0;
     v.hi_in = i0 == nx - 2;
@@ -604,9 +628,10 @@ __global__ void __launch_bounds__(NT, MINB) ptv_kernel(const PtV p, const __grid
     const int a1 = max(kb - (K - 1), lo1);               // first plane stage 1 computes
     const int b1 = min(ke - 1 + (K - 1), hi1);           // last one
     const int q0 = a1 - 1;                               // first plane of iterate 0 the chunk reads
-    const int last_load = b1 + 1;                        // last one
-    const int t0 = a1 + 1, t_last = ke - 1 + K;
+    const int t0 = a1 + 1;
     PtvUni<K> u;
+    u.last_load = b1 + 1;                                // last plane of iterate 0 it reads
+    u.t_last = ke - 1 + K;
 #pragma unroll
     for (int m = 1; m <= K; ++m) {
         const int need_lo = kb - (K - m), need_hi = ke - 1 + (K - m);   // planes stage m has to produce for this chunk
@@ -628,8 +653,8 @@ __global__ void __launch_bounds__(NT, MINB) ptv_kernel(const PtV p, const __grid
     }
     u.ts_lo = max(u.ts_lo, K + 2);            // past the steps that set the lower z-face images (t <= 1 + K)
     u.ts_hi = min(u.ts_hi, nz - 3 + K);       // before the one that stores the upper z-face image / the peer plane
-    u.planeB = p.planeB;
-    u.oDN = (const char*)p.DN - (const char*)p.PN;
+    u.oDN = (const char*)DN - (const char*)PN;
+    u.pn = (char*)PN;
     // the thread's pair inside a box with halo / without
     unsigned ringo = (unsigned)(ty + 1) * G::rwB(p) + (unsigned)(2 * tx + 2) * 8u;
     unsigned cello = (unsigned)(ty * W + 2 * tx) * 8u;
@@ -640,9 +665,15 @@ __global__ void __launch_bounds__(NT, MINB) ptv_kernel(const PtV p, const __grid
         qr[l] = sb + p.sm_qring + (unsigned)(3 * l) * pboxB + ringo;
         NS3D_KEEP(qr[l]);   // ptxas otherwise re-derives these from %tid and the shared-window base at every use (ncu)
     }
-    // ---- staging: plane q0 + j lives in slot j mod NS; its mbarrier completes with parity (j / NS) & 1 ----------------
+    // ---- staging: the item's copy number j (plane q0 + j) is the CTA's copy number g0 + j; copy number g lives in slot
+    // g mod NS and completes the slot's mbarrier with parity (g / NS) & 1.  One-item kernel: g0 = 0.  CARRY (persistent
+    // launch): g0 = what the CTA's earlier items have issued -- an item carries on with slots and parities where the last
+    // one stopped, so the mbarriers are never initialised twice and nothing per step distinguishes it from a first item.
+    const unsigned g0 = CARRY ? s_loads : 0u;
+    const unsigned s0 = CARRY ? g0 % (unsigned)NS : 0u;             // slot of plane q0
+    auto slot_of = [&](unsigned j) { const unsigned c = s0 + j; return c >= (unsigned)NS ? c - (unsigned)NS : c; };   // j < NS
     auto stage_plane = [&](int q, sa_t slot, sa_t bar) {
-        if (q > last_load) return;
+        if (q > u.last_load) return;
 #if !defined(NS3D_HOST_EMU)
         if (TMA) {
             // slab interfaces: the planes beyond the halo (-1, nz) and the dPrdτ of the halo planes (0, nz-1) live in a
@@ -650,49 +681,71 @@ __global__ void __launch_bounds__(NT, MINB) ptv_kernel(const PtV p, const __grid
             // completes the slot's mbarrier by hand; every other plane goes through the TMA unit
             const bool remote = P2P && ((lo_face && q <= 0) || (hi_face && q >= nz - 1));
             if (remote) {
-                ptv_coop_stage<P2P>(p, smem + (slot - sb), q, X0, Y0, lo_face, hi_face);
+                ptv_coop_stage<P2P>(p, P, D, smem + (slot - sb), q, X0, Y0, lo_face, hi_face);
                 __syncthreads();
                 if (threadIdx.x == 0) ptv_mbar_expect(bar, 0);
                 return;
             }
             if (threadIdx.x == 0) {
                 ptv_mbar_expect(bar, p.tx_bytes);
-                ptv_tma_3d(slot, &maps.m[0], X0 - 2, Y0 - 1, q, bar);
-                ptv_tma_3d(slot + pboxB, &maps.m[1], X0, Y0, q, bar);
+                ptv_tma_3d(slot, flip ? &maps.m[3] : &maps.m[0], X0 - 2, Y0 - 1, q, bar);
+                ptv_tma_3d(slot + pboxB, flip ? &maps.m[4] : &maps.m[1], X0, Y0, q, bar);
                 ptv_tma_3d(slot + pboxB + dboxB, &maps.m[2], X0, Y0, q, bar);
             }
             return;
         }
 #endif
         (void)bar;
-        ptv_coop_stage<P2P>(p, smem + (slot - sb), q, X0, Y0, lo_face, hi_face);
+        ptv_coop_stage<P2P>(p, P, D, smem + (slot - sb), q, X0, Y0, lo_face, hi_face);
     };
-    for (int j = 0; j < NS; ++j) stage_plane(q0 + j, stage0 + (unsigned)j * slotB, bars + 8 * j);
+    // CARRY (persistent launch): the item's first copies wait for gate() -- the issuing thread's look at the item's
+    // predecessors.  With TMA staging that wait happens INSIDE the loop in which every thread waits for the first plane
+    // anyway (below): as a loop of its own anywhere in the kernel, it cost the hot loop its spill-free register allocation.
+    bool issued = !(TMA && CARRY);
+    if (!TMA && CARRY) {
+        if (threadIdx.x == 0)
+            while (!gate()) spin_pause();
+        __syncthreads();
+    }
+    if (issued)
+        for (int j = 0; j < NS; ++j) stage_plane(q0 + j, stage0 + slot_of((unsigned)j) * slotB, bars + 8u * slot_of((unsigned)j));
     if (!TMA) __syncthreads();
     PtvRegs<K> s;
     // ---- prologue: the thread's own Pr of planes a1-1 and a1 (register slots 1 and 2) -------------------------------
     {
+        const unsigned c0 = s0, c1 = slot_of(1u);
 #if !defined(NS3D_HOST_EMU)
-        if (TMA) ptv_mbar_wait(bars, 0);
+        if (TMA) {
+            for (unsigned n = 0;; ++n) {
+                if (CARRY && !issued && threadIdx.x == 0 && gate()) {
+                    for (int j = 0; j < NS; ++j)
+                        stage_plane(q0 + j, stage0 + slot_of((unsigned)j) * slotB, bars + 8u * slot_of((unsigned)j));
+                    issued = true;
+                }
+                if (ptv_mbar_try(bars + 8u * c0, (g0 / (unsigned)NS) & 1u)) break;
+                if (n > (1u << 24)) __trap();   // bounded: a copy (or a predecessor) that never arrives traps instead of hanging the GPU
+            }
+        }
 #endif
-        D2 w = sa_ld2(stage0 + ringo);
+        D2 w = sa_ld2(stage0 + c0 * slotB + ringo);
         s.h[0][1][0] = w.x; s.h[0][1][1] = w.y;
 #if !defined(NS3D_HOST_EMU)
-        if (TMA) ptv_mbar_wait(bars + 8, 0);
+        if (TMA) ptv_mbar_wait(bars + 8u * c1, ((g0 + 1u) / (unsigned)NS) & 1u);
 #endif
-        w = sa_ld2(stage0 + slotB + ringo);
+        w = sa_ld2(stage0 + c1 * slotB + ringo);
         s.h[0][2][0] = w.x; s.h[0][2][1] = w.y;
-        __syncthreads();            // every thread has read its pair of plane q0: slot 0 is free
-        stage_plane(q0 + NS, stage0, bars);
+        __syncthreads();            // every thread has read its pair of plane q0 (and s_loads): its slot is free
+        if (CARRY && threadIdx.x == 0) s_loads = g0 + (unsigned)(u.last_load - q0 + 1);   // where the CTA's next item carries on
+        stage_plane(q0 + NS, stage0 + c0 * slotB, bars + 8u * c0);
     }
     // the thread's pair in plane t0 - K of PN
-    char* o = (char*)p.PN + (long long)(t0 - K) * p.planeB + (long long)v.j0 * p.rowB + (long long)i0 * 8;
+    char* o = (char*)PN + (long long)(t0 - K) * p.planeB + (long long)v.j0 * p.rowB + (long long)i0 * 8;
     int t = t0;
-    sa_t cur = stage0 + 2 * slotB;   // staging slot of plane t0 (= q0 + 2; NS >= 3)
-    sa_t prv = stage0 + slotB;       // ... of plane t0 - 1
-    sa_t bar = bars + 16;            // mbarrier of the current slot
-    sa_t pbar = bars + 8;
-    unsigned par = 0;                // parity the current slot's mbarrier completes with
+    sa_t prv = stage0 + slot_of(1u) * slotB;       // staging slot of plane t0 - 1
+    sa_t pbar = bars + 8u * slot_of(1u);
+    sa_t cur = stage0 + slot_of(2u) * slotB;       // ... of plane t0 (= q0 + 2; NS >= 3)
+    sa_t bar = bars + 8u * slot_of(2u);            // mbarrier of the current slot
+    unsigned par = ((g0 + 2u) / (unsigned)NS) & 1u;   // parity it completes with
 #ifdef NS3D_HOST_EMU
 #define PTV_MBAR_WAIT(b, parity) ((void)0)
 #else
@@ -700,7 +753,7 @@ __global__ void __launch_bounds__(NT, MINB) ptv_kernel(const PtV p, const __grid
 #endif
 #define PTV_STEP(PH)                                                                                                       \
     {                                                                                                                      \
-        if (TMA && t <= last_load) PTV_MBAR_WAIT(bar, par);                                                                \
+        if (TMA && t <= u.last_load) PTV_MBAR_WAIT(bar, par);                                                              \
         if (t >= u.ts_lo && t <= u.ts_hi)                                                                                  \
             ptv_step<MODE, K, P2P, PH, G, true>(p, v, u, s, t, o, cur + ringo, prv + ringo, prv + pboxB + cello, qr);      \
         else                                                                                                               \
@@ -711,20 +764,20 @@ __global__ void __launch_bounds__(NT, MINB) ptv_kernel(const PtV p, const __grid
 #define PTV_NEXT()                                                                          \
     {                                                                                       \
         ++t;                                                                                \
-        o += u.planeB;                                                                      \
+        o += p.planeB;                                                                      \
         prv = cur; pbar = bar;                                                              \
         cur += slotB; bar += 8;                                                             \
-        if (cur == stage_end) { cur = stage0; bar = bars; par ^= 1u; }                      \
+        if (cur == stage0 + (unsigned)NS * slotB) { cur = stage0; bar = bars; par ^= 1u; }  \
     }
     while (true) {
         PTV_STEP(0)
-        if (t == t_last) break;
+        if (t == u.t_last) break;
         PTV_NEXT()
         PTV_STEP(1)
-        if (t == t_last) break;
+        if (t == u.t_last) break;
         PTV_NEXT()
         PTV_STEP(2)
-        if (t == t_last) break;
+        if (t == u.t_last) break;
         PTV_NEXT()
     }
 #undef PTV_STEP
@@ -734,9 +787,117 @@ __global__ void __launch_bounds__(NT, MINB) ptv_kernel(const PtV p, const __grid
         __threadfence_system();  // this thread's peer stores are performed before the flag can be seen
         __syncthreads();
         if (threadIdx.x == 0) {
-            const unsigned nface = gridDim.x;
+            const unsigned nface = (unsigned)(p.ntx * p.nty);
             if (lo_face) signal_neighbour(p.mbox, 0, p.peer_lo_flag, nface);
             if (hi_face) signal_neighbour(p.mbox, 1, p.peer_hi_flag, nface);
+        }
+    }
+}
+
+#ifdef NS3D_HOST_EMU
+#define PTV_SMEM(name) char* name = (char*)emu::dyn_smem()
+#else
+#define PTV_SMEM(name)                                   \
+    extern __shared__ __align__(128) char ptv_smem_[];   \
+    char* name = ptv_smem_
+#endif
+
+// One launch = K iterations; one CTA per (tile, z-chunk): grid (ntx*nty, chunks).
+template <int MODE, int K, bool P2P, bool TMA, int PXT, int BTY, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) ptv_kernel(const PtV p, const __grid_constant__ PtvMaps maps)
+{
+    PTV_SMEM(smem);
+    ptv_item<MODE, K, P2P, TMA, false, PXT, BTY>(p, maps, smem, (int)blockIdx.x, (int)blockIdx.y, (int)gridDim.y, false, true, [] { return true; });
+}
+
+// Persistent launch: p.nlaunch launches of K iterations in ONE kernel, without the idle ramp and tail between dependent
+// launches (ncu of ptv_kernel at 255x153x153: the SMs are idle 17 % of a launch) and without their launch gaps.  The
+// CTAs -- as many as are resident at a time -- claim work items from a queue in launch-major, chunk-major order.  An item
+// of launch l reads planes of the iterate that launch l-1 wrote and overwrites planes that launch l-1 read, both within
+// K planes of its chunk: it waits until every tile of the chunks within that range has finished launch l-1 (a counter
+// per launch and chunk; release / acquire at gpu scope, then a proxy fence because the readers are TMA copies).  Items
+// are claimed in order, so everything an item waits for has been claimed by a CTA that is running: no deadlock, whatever
+// the number of resident CTAs.  In steady state the wait is over before it starts -- the chunks an item needs were
+// claimed a whole launch earlier.
+//
+// The predecessors of work item w: launch l-1 must have finished every tile of the chunks whose planes [kb - K, ke - 1 + K]
+// the item reads or overwrites -- the item's own chunk and its two neighbours (chunks are at least K planes long, the host
+// sees to that), clamped at the ends.  dep[0..2]: indices of their counters in p.work; dep[3]: the count they must reach
+// (0: nothing to wait for).
+__device__ __forceinline__ void ptv_flow_deps(const PtV& p, unsigned w, unsigned ntiles, unsigned per_launch, unsigned* dep)
+{
+    const unsigned l = w / per_launch, bz = (w - l * per_launch) / ntiles;
+    const unsigned base = PTV_WORK_DONE + (l > 0 ? l - 1 : 0) * (unsigned)p.nbz;
+    dep[0] = base + (bz > 0 ? bz - 1 : 0);
+    dep[1] = base + bz;
+    dep[2] = base + min(bz + 1, (unsigned)p.nbz - 1);
+    dep[3] = (l > 0 && l < (unsigned)p.nlaunch) ? ntiles : 0u;   // (no such item: the CTA is about to leave)
+}
+// One look at them: three relaxed polls, served from L2, then ONE fence (an acquire load is followed by an invalidation of
+// the SM's whole L1, which a waiting thread would repeat with every look).
+__device__ __forceinline__ bool ptv_flow_ready(const unsigned* work, const unsigned* dep)
+{
+    const bool ok = ld_min3_relaxed(work + dep[0], work + dep[1], work + dep[2]) >= dep[3];
+    if (ok) {
+        fence_acq_rel_gpu();
+        fence_proxy_async();   // ... and what was acquired is visible to the TMA copies this thread issues next
+    }
+    return ok;
+}
+
+// Register allocation of this kernel is fragile: its hot loop (ptv_item) sits at the 80-register limit of three CTAs per SM,
+// and ptxas loses the spill-free allocation (ptxas -v: 0 -> 112 bytes of stack, reloads inside the hot loop that the L1
+// cannot hold next to three CTAs' shared memory: ncu, 45 % of the stall samples) as soon as the kernel contains another loop
+// in which one thread waits, a NANOSLEEP or a non-inlined call -- wherever it stands and however it is written.  Hence the
+// look at an item's predecessors sits inside ptv_item's own wait for the item's first plane (`gate`), reads what it needs
+// from shared memory, and nothing else in this kernel waits.
+template <int MODE, int K, bool TMA, int PXT, int BTY, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) ptv_flow_kernel(const PtV p, const __grid_constant__ PtvMaps maps)
+{
+    PTV_SMEM(smem);
+    __shared__ unsigned s_w;        // the CTA's work item
+    __shared__ unsigned s_dep[4];   // ... and its predecessors (ptv_flow_deps)
+    __shared__ unsigned s_ready;    // ... which were complete at the first look
+    if (threadIdx.x == 0) {
+        const unsigned ntiles = (unsigned)(p.ntx * p.nty), per_launch = ntiles * (unsigned)p.nbz;
+        const unsigned w = atom_add_relaxed_gpu(p.work, 1u);
+        s_w = w;
+        ptv_flow_deps(p, w, ntiles, per_launch, s_dep);
+    }
+    bool first = true;
+    for (;;) {   // (re-)entry: the item's predecessors are waited for
+        if (threadIdx.x == 0) {
+            unsigned looks = 0;
+            while (!ptv_flow_ready(p.work, s_dep)) {
+                if (++looks > NS3D_FLOW_WAIT_LOOKS) {   // bounded: a bug must not hang the GPU; the host reports the error word
+                    *p.work_err = 1u;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        for (;;) {   // items whose predecessors are complete on arrival
+            {
+                const unsigned ntiles = (unsigned)(p.ntx * p.nty), per_launch = ntiles * (unsigned)p.nbz;
+                const unsigned w = s_w;
+                if (w >= per_launch * (unsigned)p.nlaunch) return;
+                const int l = (int)(w / per_launch);
+                const unsigned r = w - (unsigned)l * per_launch;
+                const int bz = (int)(r / ntiles), tile = (int)(r - (unsigned)bz * ntiles);
+                ptv_item<MODE, K, false, TMA, true, PXT, BTY>(p, maps, smem, tile, bz, p.nbz, (l & 1) != 0, first, [] { return true; });
+                first = false;
+            }
+            __syncthreads();   // the item's stores happen before the counter moves (and s_w, s_dep have been read)
+            if (threadIdx.x == 0) {
+                const unsigned ntiles = (unsigned)(p.ntx * p.nty), per_launch = ntiles * (unsigned)p.nbz;
+                atom_add_release_gpu(p.work + s_dep[1] + (s_dep[3] ? (unsigned)p.nbz : 0u), 1u);   // = done[l][bz]
+                const unsigned w = atom_add_relaxed_gpu(p.work, 1u);
+                s_w = w;
+                ptv_flow_deps(p, w, ntiles, per_launch, s_dep);
+                s_ready = (w >= per_launch * (unsigned)p.nlaunch || ptv_flow_ready(p.work, s_dep)) ? 1u : 0u;
+            }
+            __syncthreads();
+            if (!s_ready) break;
         }
     }
 }

@@ -6,3 +6,9 @@ int ns3d_internal_ptv_launch_parity(ns3d_ctx* ctx, cudaStream_t st, const PtV& k
 {
     return ptv_launch_m<NS3D_PARITY>(ctx, st, k, maps, pl, K, p2p, tma, grid, smem);
 }
+
+int ns3d_internal_ptv_flow_launch_parity(ns3d_ctx* ctx, cudaStream_t st, const PtV& k, const PtvMaps& maps, const PtvPlan& pl, int K, bool tma,
+                                        size_t smem)
+{
+    return ptv_flow_launch_m<NS3D_PARITY>(ctx, st, k, maps, pl, K, tma, smem);
+}

@@ -54,13 +54,16 @@ def initial_host_fields(s: Setup) -> dict:
 
 def initial_profiles(s: Setup) -> dict:
     """The z-profiles behind ``initial_host_fields`` -- every initial array of the scripts depends on iz alone:
-    ``{"Pr": nz values}`` (M:370) or ``{"Vx": ..., "Pr": ...}`` (G:86-87).  The ``+ 0*yc[iy] + 0*xv[ix]`` terms of
+    ``{"Pr": (nz values, ny zeros, nz zeros)}`` (M:370) or ``{"Vx": ..., "Pr": ...}`` (G:86-87).  The ``+ 0*yc[iy] + 0*xv[ix]`` terms of
     the comprehensions are kept (they turn a -0.0 into +0.0)."""
     nz = s.nz
     zc = _linrange(-(s.lz - s.dz) / 2, (s.lz - s.dz) / 2, nz)
     if s.variant == native.VARIANT_M:
+        # M:370 `-(z_g(iz,dz,C)-dz/2)*ρ*g + 0*yc[iy] + 0*zc[iz]`: with g = 0 three signed zeros, so the sign of the sum
+        # depends on iy too -- the three terms stay apart (ns3d_fill_profile_zy adds them on the device)
         zg = np.array([s.grid.x_g(iz, s.dz, nz, 2) for iz in range(1, nz + 1)])
-        return {"Pr": (-(zg - s.dz / 2) * s.rho * s.g) + 0.0 + 0 * zc}
+        yc = _linrange(-(s.ly - s.dy) / 2, (s.ly - s.dy) / 2, s.ny)
+        return {"Pr": (-(zg - s.dz / 2) * s.rho * s.g, 0 * yc, 0 * zc)}
     prof = s.vin * (7.0 / 6.0) * np.power((zc + s.lz / 2) / s.lz, 1.0 / 6.0)      # host pow: the reference's `^`
     return {"Vx": prof + 0.0 + 0.0, "Pr": (-(zc - s.lz / 2) * s.rho * s.g) + 0.0 + 0.0}
 
@@ -81,7 +84,10 @@ class Simulation:
         if host_fields is None:
             # device-side initialisers: nz profile values cross PCIe, not 3-D arrays (M:369-370 / G:86-87)
             for name, prof in initial_profiles(setup).items():
-                ctx.fill_profile_z(self.f[name], prof)
+                if isinstance(prof, tuple):
+                    ctx.fill_profile_zy(self.f[name], *prof)
+                else:
+                    ctx.fill_profile_z(self.f[name], prof)
             if setup.variant == native.VARIANT_M:
                 ctx.fill_plane_x(self.f["Vy"], 0, setup.vin)                          # M:369 (sic: Vy)
         else:

@@ -80,6 +80,7 @@ SIGNATURES = {
     "ns3d_d2h": (_I, [_P, _P, _P, _Z]),
     "ns3d_copy": (_I, [_P, _P, _P, _Z]),
     "ns3d_fill_profile_z": (_I, [_P, _P, _I, _I, _I, c_double_p]),
+    "ns3d_fill_profile_zy": (_I, [_P, _P, _I, _I, _I, c_double_p, c_double_p, c_double_p]),
     "ns3d_fill_plane_x": (_I, [_P, _P, _I, _I, _I, _I, _D]),
     "ns3d_h2d_async": (_I, [_P, _P, _P, _Z]),
     "ns3d_d2h_async": (_I, [_P, _P, _P, _Z]),
@@ -324,6 +325,14 @@ class Context:
             raise NS3DError(f"fill_profile_z: {prof.shape} values for {a.shape[2]} planes")
         self._ck(self.lib.ns3d_fill_profile_z(self.h, a.ptr, a.shape[0], a.shape[1], a.shape[2],
                                               prof.ctypes.data_as(c_double_p)), "ns3d_fill_profile_z")
+
+    def fill_profile_zy(self, a: DeviceArray, profile: np.ndarray, add_y: np.ndarray, add_z: np.ndarray):
+        """``A[ix,iy,iz] = (profile[iz] + add_y[iy]) + add_z[iz]`` (M:370 term by term: signed zeros when g = 0)."""
+        prof, ay, az = (np.ascontiguousarray(v, dtype=np.float64) for v in (profile, add_y, add_z))
+        if prof.shape != (a.shape[2],) or az.shape != (a.shape[2],) or ay.shape != (a.shape[1],):
+            raise NS3DError(f"fill_profile_zy: {prof.shape}, {ay.shape}, {az.shape} values for an array of shape {a.shape}")
+        self._ck(self.lib.ns3d_fill_profile_zy(self.h, a.ptr, a.shape[0], a.shape[1], a.shape[2], prof.ctypes.data_as(c_double_p),
+                                               ay.ctypes.data_as(c_double_p), az.ctypes.data_as(c_double_p)), "ns3d_fill_profile_zy")
 
     def fill_plane_x(self, a: DeviceArray, ix: int, value: float):
         """``A[ix+1,:,:] .= value`` (M:369; ix 0-based)."""

@@ -19,9 +19,9 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "navierstokes3d_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libns3d_emu.so")
-SOURCES = ["ns3d_core.cu", "ns3d_ops.cu", "ns3d_pt.cu", "ns3d_ptv.cu", "ns3d_ptv_mode0.cu", "ns3d_ptv_mode1.cu", "ns3d_ptv_mode2.cu", "ns3d_out.cu"]
+SOURCES = ["ns3d_core.cu", "ns3d_ops.cu", "ns3d_pt.cu", "ns3d_step.cu", "ns3d_ptv.cu", "ns3d_ptv_mode0.cu", "ns3d_ptv_mode1.cu", "ns3d_ptv_mode2.cu", "ns3d_out.cu"]
 # kernels that synchronise (__syncthreads, named barriers, warp shuffles): one host thread per CUDA thread
-THREADED = ("ptv_kernel_fn", "ptv_residual_kernel", "pt_tb2_kernel", "pt_tb2s_kernel", "pt_tb2sp_kernel", "pt_tb2d_kernel", "pt_residual_kernel", "max_abs_kernel")
+THREADED = ("ptv_kernel_fn", "ptv_flow_kernel_fn", "predictor_kernel", "ptv_residual_kernel", "pt_tb2_kernel", "pt_tb2s_kernel", "pt_tb2sp_kernel", "pt_tb2d_kernel", "pt_residual_kernel", "max_abs_kernel")
 
 
 def _match_back_template(s: str, end: int) -> int:

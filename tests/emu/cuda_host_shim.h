@@ -51,6 +51,7 @@ using std::min;
 
 inline void __syncthreads();
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline long long clock64()  // 10 ns ticks: the kernels' spin limits (8e9 "cycles") become 80 s, generous for a loaded CI box
 {
     return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() / 10;

@@ -13,6 +13,7 @@ a CPU.  This is test infrastructure: the product has no switch that selects the 
 import numpy as np
 import pytest
 
+import tests.test_gpu_driver as D
 import tests.test_gpu_kernels as K
 import tests.test_gpu_solver as S
 import tests.test_gpu_zz_output as Z
@@ -35,6 +36,10 @@ test_box_matches_numpy_slicing = Z.test_box_matches_numpy_slicing
 test_box_rejects_a_box_outside_the_array = Z.test_box_rejects_a_box_outside_the_array
 
 
+# ---- device-side initialisers (signed zeros of M:370 included) ----------------------------------------
+test_device_side_initialisers = D.test_device_side_initialisers_match_the_scripts_arrays
+
+
 # ---- level 2 on CPU-sized grids ---------------------------------------------------------------------
 @pytest.mark.parametrize("variant", ["M", "G"])
 @pytest.mark.parametrize("grid", [(3, 3, 3), (5, 4, 3), (20, 12, 9)])
@@ -48,6 +53,8 @@ def test_fused_iteration(O, ns, ctx, variant, grid, zchunk):
     ("G", (20, 19, 11), 0, "k2_lb0"), ("M", (20, 19, 11), 1, "k2_lb4_ns3"), ("G", (20, 12, 12), 0, "k3_lb0"),
     ("M", (20, 12, 12), 2, "k2_tiles"), ("G", (20, 19, 11), 0, "k3_tiles"), ("M", (16, 9, 8), 3, "k2_coop_nographs"),
     ("G", (16, 9, 8), 2, "k1_coop_tiles"), ("M", (4, 3, 6), 1, "k3_tiles"), ("G", (3, 3, 3), 0, "k3_lb0"),
+    ("M", (20, 12, 12), 2, "k2_flow"), ("G", (20, 19, 11), 3, "k3_flow_tiles"), ("M", (16, 9, 8), 0, "k1_flow"),
+    ("G", (37, 23, 19), 7, "k2_flow_lb0"),
 ])
 def test_ptv_kernel(O, ns, ctx, variant, grid, zchunk, cfg):
     """The fused loop's kernel in every configuration behind the options -- iterations per launch, launch bounds,
@@ -95,7 +102,9 @@ def test_whole_time_steps(O, ns, variant, nx, nt, how):
         {"step": sim.step, "groups": sim.step_groups, "level1": sim.step_level1}[how]()
     assert sim.iters == iters_o
     assert np.array_equal(np.concatenate(sim.err_hist), np.concatenate(errs_o), equal_nan=True)
-    for name in ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C", "divV"):
+    # the snapshots of M:475 too: the fused step works ON the `_o` arrays (predictor V -> V_o, corrector in place,
+    # advection V_o -> V) and must leave in them what `A_o .= A` leaves there
+    for name in ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C", "divV", "Vx_o", "Vy_o", "Vz_o", "C_o"):
         got = sim.host(name)
         assert ((got == f[name]) | (np.isnan(got) & np.isnan(f[name]))).all(), name
     sim.ctx.close()

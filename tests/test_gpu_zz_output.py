@@ -87,6 +87,15 @@ def test_step_groups_equal_the_fused_step(O, ns, variant):
     for _ in range(nt):
         sim.step_groups()
     assert sim.iters == iters_o and sim.err_hist == errs_o
-    for name in ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C", "divV"):
+    for name in ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C", "divV", "Vx_o", "Vy_o", "Vz_o", "C_o"):
+        assert np.array_equal(sim.host(name), f[name]), name
+    sim.ctx.close()
+    # ns3d_step: one round trip of the velocity through the `_o` arrays (fused predictor / corrector / advection,
+    # ns3d_step.cu), no stress arrays -- the same state, snapshots included
+    sim = ns.Simulation(ns.setup_multi_gpu(nx) if variant == "M" else ns.setup_gpu(nx), ns.Context(0, ns.PARITY))
+    for _ in range(nt):
+        sim.step()
+    assert sim.iters == iters_o and sim.err_hist == errs_o
+    for name in ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C", "divV", "Vx_o", "Vy_o", "Vz_o", "C_o"):
         assert np.array_equal(sim.host(name), f[name]), name
     sim.ctx.close()

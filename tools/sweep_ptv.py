@@ -1,4 +1,4 @@
-"""Times ptv_kernel (the fused PT loop on the pitched copies) over iterations per launch, rows per thread,
+"""Times the fused PT loop (ptv_flow_kernel / ptv_kernel on the pitched copies) over iterations per launch, rows per thread,
 launch bounds, tile shapes and chunk lengths (tuning aid; results go to profiles/*.jsonl).
 
     python tools/sweep_ptv.py --grids 255x153x153 --modes FAST,FASTEST [--quick]
@@ -15,7 +15,6 @@ ap.add_argument("--modes", default="FAST,FASTEST")
 ap.add_argument("--iters", type=int, default=120)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--sets", default="", help="';'-separated sets of ','-separated name=value options; zchunk=N is the chunk length")
-ap.add_argument("--old", action="store_true", help="also time the round-1 kernel (ptv=0)")
 args = ap.parse_args()
 
 
@@ -41,13 +40,13 @@ for g in args.grids.split(","):
         Pr = ctx.from_host(host_pr)
         dP = ctx.zeros(nx - 2, ny - 2, nz - 2)
         dv = ctx.from_host(host_dv)
-        todo = ([{"ptv": 0}] if args.old else []) + sets
-        for opts in todo:
+        for opts in sets:
             for name in ("ptv_k", "ptv_ns", "ptv_pxt", "ptv_bty"):
                 ctx.set_option(name, 0)
             ctx.set_option("ptv_lb", -1)
             ctx.set_option("ptv_tma", 1)
-            ctx.set_option("ptv", 1)
+            ctx.set_option("ptv_flow", 0)
+            ctx.set_option("serpentine", -1)
             zc = 0
             for k, v in opts.items():
                 if k == "zchunk":
