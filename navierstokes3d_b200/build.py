@@ -42,8 +42,22 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Builds the library unless it is up to date.  Several ranks of one job may get here at once (torchrun on a
+    box whose snapshot has sources newer than the library): one of them builds, the others wait on a file lock."""
     if not force and not needs_build():
         return LIB
+    import fcntl
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB   # another process built it while this one waited
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     from concurrent.futures import ThreadPoolExecutor
     nvcc = _nvcc()
     env = dict(os.environ)

@@ -46,6 +46,7 @@ struct ns3d_ctx {
     bool p2p_ready = false;
     std::unordered_map<const void*, std::pair<void*, void*>> p2p_map;  // local base -> (lower, upper) peer base
     int opt_p2p = 1;
+    int opt_p2p_split = 1;    // z-slabs: the interface chunks of a pass as a launch of their own on the high-priority stream (0: one launch per pass)
     // tuning knobs (ns3d_set_option)
     int opt_serpentine = -1;  // -1 = by working-set size
     int opt_graphs = 1;       // replay chunks of PT iterations as CUDA graphs

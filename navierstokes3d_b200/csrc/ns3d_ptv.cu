@@ -384,7 +384,7 @@ int ptv_run_direct(ns3d_ctx* ctx, PtvRun& r, int n, int iter0)
         if (r.peer_on) {
             ptv_set_peers(k, r.peers, 1 - r.cur, 2 + r.cur);
             const int zf = r.pl.zf;
-            const bool split = (p->nz - 2) >= 2 * zf + 4;
+            const bool split = ctx->opt_p2p_split && (p->nz - 2) >= 2 * zf + 4;
             if (split) {
                 PtV f = k, in = k;
                 f.faces = 1;
@@ -444,7 +444,7 @@ void opts_key(const ns3d_ctx* ctx, int (&o)[8])
 {
     o[0] = ctx->opt_ptv_k; o[1] = ctx->opt_ptv_ns; o[2] = ctx->opt_ptv_lb; o[3] = ctx->opt_ptv_pxt;
     o[4] = ctx->opt_ptv_bty; o[5] = ctx->opt_serpentine; o[6] = ctx->opt_p2p;
-    o[7] = ctx->opt_ptv_tma | (ctx->opt_ptv_flow << 1);
+    o[7] = ctx->opt_ptv_tma | (ctx->opt_ptv_flow << 1) | (ctx->opt_p2p_split << 2);
 }
 
 int ptv_run(ns3d_ctx* ctx, PtvRun& r, int n, int iter0)

@@ -63,6 +63,8 @@ def run_ranks(world, grid, nt, lz, how="step", options=None):
     (4, (12, 9, 23), 6, 86 / 12, "pt_random", {"ptv_pxt": 4, "ptv_bty": 5}),   # four ranks, several tiles per plane
     (2, (16, 10, 26), 12, 50 / 16, "pt_random", {"ptv_k": 3}),     # K = 3 asked for: slabs fall back to 2
     (2, (16, 10, 26), 2, 50 / 16, "step", {"graphs": 0}),          # whole time steps without graph replay
+    (2, (16, 10, 26), 12, 50 / 16, "pt_random", {"p2p_split": 0}), # thick slabs, ONE launch per pass (interface chunks inside it)
+    (3, (16, 10, 26), 2, 76 / 16, "step", {"p2p_split": 0}),
 ])
 def test_rank_processes_match_igg_emulation(world, grid, nt, lz, how, options):
     results = run_ranks(world, grid, nt, lz, how, options)
