@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import re
 import os
 import subprocess
 import sys
@@ -435,6 +436,10 @@ def main():
     # passes over the fields; ptv_kernel (z-slabs): one launch per pass of per_launch iterations
     persistent = desc.startswith("ptv_flow_kernel")
     iters_per_launch = n_probe if persistent else per_launch
+    # z-bands: a pass over the fields is several launches on as many streams that overlap with the next pass's; what the
+    # events measure -- and what `us_per_launch` then holds -- is the time per PASS
+    m_bands = re.search(r"a pass = (\d+) launches", desc)
+    launches_per_pass = int(m_bands.group(1)) if m_bands else 1
     t_launch = k0.elapsed_time(k1) / 1e3 / n_probe * iters_per_launch
     peak, peak_src = hbm_peak()
     achieved = 40.0 * iters_per_launch * n_cells / t_launch / 1e9
@@ -575,6 +580,7 @@ def main():
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_key": tkey, "us_per_launch": t_launch * 1e6,
                          "pt_iterations_per_launch": iters_per_launch, "pt_iterations_per_pass": per_launch,
+                         "launches_per_pass": launches_per_pass,
                          "us_per_pass": t_launch * 1e6 / iters_per_launch * per_launch,
                          # what actually crossed the DRAM interface (ncu) over the same launch time: the
                          # kernel keeps the intermediate iterates on chip, so this is well below `achieved`

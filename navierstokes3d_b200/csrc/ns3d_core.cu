@@ -186,6 +186,11 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
     // persistent launch: every chunk of iterations between two residual checks is ONE kernel (single rank)
     if (!strcmp(name, "ptv_flow")) { ctx->opt_ptv_flow = value != 0; return NS3D_OK; }
     if (!strcmp(name, "p2p_split")) { ctx->opt_p2p_split = value != 0; return NS3D_OK; }
+    if (!strcmp(name, "ptv_bands")) {
+        if (value < -1 || value > 16) return ns3d_fail(ctx, NS3D_EINVAL, "ptv_bands must be -1 (default) .. 16");
+        ctx->opt_ptv_bands = value;
+        return NS3D_OK;
+    }
     if (!strcmp(name, "ptv_lb")) {
         if (value < -1 || value > 4 || value == 2) return ns3d_fail(ctx, NS3D_EINVAL, "ptv_lb must be -1 (default), 0, 1, 3 or 4");
         ctx->opt_ptv_lb = value;

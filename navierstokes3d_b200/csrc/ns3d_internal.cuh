@@ -62,6 +62,12 @@ struct ns3d_ctx {
     unsigned* ptv_work = nullptr;  // work queue + completion counters of the persistent launch (ptv_flow_kernel)
     size_t ptv_work_words = 0;
     int opt_ptv_flow = 0;     // persistent launch of whole chunks of iterations (single rank; off: see ptv_flow_kernel)
+    // z-bands (single rank): every pass as `bands` launches on as many streams; band b of pass n+1 waits for bands b-1, b, b+1
+    // of pass n only, so consecutive passes overlap like a wavefront instead of idling in every launch's ramp and tail
+    int opt_ptv_bands = -1;   // -1 = by grid size, 0 / 1 = off
+    cudaStream_t band_stream[16] = {};
+    cudaEvent_t band_ev[2][16] = {};
+    cudaEvent_t band_fork = nullptr;
     int opt_ptv_tma = 1;      // stage the z-plane tiles with the TMA unit (0 = plain loads by all threads)
     int opt_ptv_lb = -1;      // launch-bounds variant (threads / CTAs per SM): 0 = 256/2, 1 = 256/3, 2 = 256/4, 3 = 512/1, 4 = 512/2 (-1 = default)
     int opt_ptv_pxt = 0;      // thread columns per tile (0 = balanced automatically)

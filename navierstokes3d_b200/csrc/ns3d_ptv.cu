@@ -345,6 +345,104 @@ void ptv_bind(const ns3d_ctx* ctx, PtV& k, int cur)
     k.V = ctx->ptv[4];
 }
 
+// ---- z-bands (single rank) -------------------------------------------------------------------------------------------
+// ncu of ptv_kernel at 255x153x153: the SMs are idle 17 % of a launch (ramp, tail, 3.1 waves of CTAs), and a pass cannot
+// start before the last CTA of the previous one has finished.  Here a pass is `nb` launches, one per band of z-chunks, on
+// `nb` streams; band b of pass n+1 depends on bands b-1, b, b+1 of pass n only -- its reads reach K planes into the
+// adjacent bands, and those launches are also the last readers of what it overwrites -- so the first bands of the next
+// pass run while the last bands of this one drain.  The dependencies are events (graph edges inside a captured chunk);
+// no device-side waiting (cf. ptv_flow_kernel).
+int ptv_bands_ensure(ns3d_ctx* ctx, int nb)
+{
+    if (!ctx->band_fork) NS3D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->band_fork, cudaEventDisableTiming));
+    for (int b = 0; b < nb; ++b) {
+        if (!ctx->band_stream[b]) NS3D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->band_stream[b], cudaStreamNonBlocking));
+        for (int q = 0; q < 2; ++q)
+            if (!ctx->band_ev[q][b]) NS3D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->band_ev[q][b], cudaEventDisableTiming));
+    }
+    return NS3D_OK;
+}
+
+// Bands for L passes of K iterations: how many (0 = do not band); may lengthen k.zchunk (chunks need not fill waves any more).
+// Measured at 255x153x153 (profiles/r02_bands_sweep_B.jsonl): 8 bands of one 16-19-plane chunk each, 25.5 us per iteration
+// against 32.0 for one launch per pass; 511^3 (25 waves of CTAs per launch) loses 4-6 % with bands.
+int ptv_bands_plan(const ns3d_ctx* ctx, PtV& k, const PtvPlan& pl, int K, int L, bool zchunk_given)
+{
+    int nb = ctx->opt_ptv_bands;
+    const int planes = k.kend - k.kbeg;
+    if (nb == 0 || nb == 1 || L < 2) return 0;
+    if (nb < 0) {
+        // by default only where a launch is a few waves of CTAs: there its ramp and tail are a good part of it
+        const long long tiles = (long long)k.ntx * k.nty;
+        const int ctas = std::max(1, std::min(ptv_lb_ctas(pl.lb), (int)(227u * 1024u / std::max(1u, k.sm_total + 1024u))));
+        const long long nch = (planes + k.zchunk - 1) / k.zchunk;
+        if (tiles * nch >= 6LL * ctx->num_sms * ctas) return 0;
+        nb = 8;
+    }
+    if (nb > 16) nb = 16;
+    if (!zchunk_given) {   // one chunk per band, at most 32 planes long (see auto_zchunk)
+        int len = (planes + nb - 1) / nb;
+        len = std::max(len, 4 * K + 2);
+        len = std::min(std::min(len, 32), planes);
+        k.zchunk = len;
+        ptv_balance_chunks(k);
+    }
+    const int nch = (planes + k.zchunk - 1) / k.zchunk;
+    if (nb > nch) nb = nch;
+    if (nb < 3 || k.zchunk < K) return 0;   // fewer than three bands overlap nothing
+    return nb;
+}
+
+// k: the planes the bands cover.  Slabs (faces != NULL): those are the planes between the interface chunks, and the two
+// interface chunks -- one launch of the P2P instantiation on the high-priority stream, as without bands -- are one more
+// "band" F next to band 0 and band nb-1: F(n+1) waits for F(n), band 0 (n) and band nb-1 (n); bands 0 and nb-1 wait for F.
+int ptv_run_banded(ns3d_ctx* ctx, PtvRun& r, PtV k, int K, int L, int nb, const PtV* faces)
+{
+    NS3D_TRY(ptv_bands_ensure(ctx, nb));
+    const int planes = k.kend - k.kbeg, zc = k.zchunk;
+    const int nch = (planes + zc - 1) / zc;
+    int first[17];   // band b = chunks [first[b], first[b+1])
+    for (int b = 0; b <= nb; ++b) first[b] = (int)((long long)nch * b / nb);
+    NS3D_CUDA(ctx, cudaEventRecord(ctx->band_fork, ctx->stream));
+    for (int b = 0; b < nb; ++b) NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->band_stream[b], ctx->band_fork, 0));
+    if (faces) NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->band_fork, 0));
+    cudaEvent_t evF[2] = {ctx->ev_a, ctx->ev_b};   // the interface launches of even / odd passes
+    const int kbeg0 = k.kbeg, kend0 = k.kend;
+    for (int l = 0; l < L; ++l) {
+        ptv_bind(ctx, k, r.cur);
+        if (faces) {
+            PtV f = *faces;
+            ptv_bind(ctx, f, r.cur);
+            ptv_set_peers(f, r.peers, 1 - r.cur, 2 + r.cur);
+            if (l > 0) {
+                NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->band_ev[(l - 1) & 1][0], 0));
+                NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->band_ev[(l - 1) & 1][nb - 1], 0));
+            }
+            NS3D_TRY(ptv_launch(ctx, ctx->comm_stream, f, r.pl, K, true, 0));
+            NS3D_CUDA(ctx, cudaEventRecord(evF[l & 1], ctx->comm_stream));
+        }
+        for (int b = 0; b < nb; ++b) {
+            if (l > 0) {
+                for (int q = std::max(b - 1, 0); q <= std::min(b + 1, nb - 1); ++q)
+                    if (q != b) NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->band_stream[b], ctx->band_ev[(l - 1) & 1][q], 0));
+                if (faces && (b == 0 || b == nb - 1)) NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->band_stream[b], evF[(l - 1) & 1], 0));
+            }
+            PtV kb = k;
+            kb.kbeg = kbeg0 + first[b] * zc;
+            kb.kend = std::min(kbeg0 + first[b + 1] * zc, kend0);
+            kb.zchunk = zc;
+            kb.reverse = 0;
+            kb.mbox = nullptr;
+            NS3D_TRY(ptv_launch(ctx, ctx->band_stream[b], kb, r.pl, K, false, 0));
+            NS3D_CUDA(ctx, cudaEventRecord(ctx->band_ev[l & 1][b], ctx->band_stream[b]));
+        }
+        r.cur = 1 - r.cur;
+    }
+    for (int b = 0; b < nb; ++b) NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->band_ev[(L - 1) & 1][b], 0));
+    if (faces) NS3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, evF[(L - 1) & 1], 0));
+    return NS3D_OK;
+}
+
 // n iterations as launches of K (then of fewer) iterations; on z-slabs the two chunks next to the interfaces
 // (peer loads / stores, mailbox flags) run on the high-priority stream beside the launch that updates the
 // other planes.  Event protocol (ev_a = "main stream finished reading the iterate that is about to be
@@ -370,6 +468,40 @@ int ptv_run_direct(ns3d_ctx* ctx, PtvRun& r, int n, int iter0)
             if (L & 1) r.cur = 1 - r.cur;
             done += L * K;
             launch += L;
+        }
+    }
+    // single rank: the full passes as bands of launches that overlap consecutive passes
+    if (ctx->nranks == 1 && done == 0 && n / r.pl.K >= 2) {
+        const int K = r.pl.K, L = n / K;
+        PtV k;
+        NS3D_TRY(make_ptv(ctx, p, r.pl, K, &k));
+        ptv_balance_chunks(k);
+        const int nb = ptv_bands_plan(ctx, k, r.pl, K, L, p->zchunk > 0);
+        if (nb > 0) {
+            NS3D_TRY(ptv_run_banded(ctx, r, k, K, L, nb, nullptr));
+            done += L * K;
+            launch += L;
+        }
+    }
+    // z-slabs over peer memory, split launches: the planes between the interface chunks in bands, the interface chunks as
+    // one more band on the high-priority stream
+    if (r.peer_on && ctx->opt_p2p_split && done == 0 && n / r.pl.K >= 2 && (p->nz - 2) >= 2 * r.pl.zf + 4) {
+        const int K = r.pl.K, L = n / K, zf = r.pl.zf;
+        PtV k;
+        NS3D_TRY(make_ptv(ctx, p, r.pl, K, &k));
+        PtV f = k, in = k;
+        f.faces = 1;
+        f.zchunk = zf;
+        in.kbeg = 1 + zf;
+        in.kend = p->nz - 1 - zf;
+        if (p->zchunk <= 0) in.zchunk = auto_zchunk(ctx, in, K, in.kend - in.kbeg, r.pl.lb);
+        ptv_balance_chunks(in);
+        const int nb = ptv_bands_plan(ctx, in, r.pl, K, L, p->zchunk > 0);
+        if (nb > 0) {
+            NS3D_TRY(ptv_run_banded(ctx, r, in, K, L, nb, &f));
+            done += L * K;
+            launch += L;
+            NS3D_CUDA(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));   // the protocol of the loop below starts from here
         }
     }
     while (done < n) {
@@ -444,7 +576,7 @@ void opts_key(const ns3d_ctx* ctx, int (&o)[8])
 {
     o[0] = ctx->opt_ptv_k; o[1] = ctx->opt_ptv_ns; o[2] = ctx->opt_ptv_lb; o[3] = ctx->opt_ptv_pxt;
     o[4] = ctx->opt_ptv_bty; o[5] = ctx->opt_serpentine; o[6] = ctx->opt_p2p;
-    o[7] = ctx->opt_ptv_tma | (ctx->opt_ptv_flow << 1) | (ctx->opt_p2p_split << 2);
+    o[7] = ctx->opt_ptv_tma | (ctx->opt_ptv_flow << 1) | (ctx->opt_p2p_split << 2) | ((ctx->opt_ptv_bands + 1) << 3);
 }
 
 int ptv_run(ns3d_ctx* ctx, PtvRun& r, int n, int iter0)
@@ -579,6 +711,16 @@ void ns3d_internal_ptv_free(ns3d_ctx* ctx)
 void ns3d_internal_ptv_release(ns3d_ctx* ctx)
 {
     ns3d_internal_ptv_free(ctx);
+    for (int b = 0; b < 16; ++b) {
+        if (ctx->band_stream[b]) cudaStreamDestroy(ctx->band_stream[b]);
+        ctx->band_stream[b] = nullptr;
+        for (int q = 0; q < 2; ++q) {
+            if (ctx->band_ev[q][b]) cudaEventDestroy(ctx->band_ev[q][b]);
+            ctx->band_ev[q][b] = nullptr;
+        }
+    }
+    if (ctx->band_fork) cudaEventDestroy(ctx->band_fork);
+    ctx->band_fork = nullptr;
     if (ctx->ptv_work) {
         cudaFree(ctx->ptv_work);
         ctx->ptv_work = nullptr;
@@ -632,21 +774,40 @@ int ns3d_internal_ptv_describe(ns3d_ctx* ctx, const ns3d_pt_params* p, char* buf
 {
     const bool slabs = ctx->nranks > 1;
     PtvPlan pl = make_plan(ctx, slabs);
-    if (slabs && !(ctx->opt_p2p && ctx->p2p_ready && p->nz >= 6)) pl.K = 1;
+    const bool peer = slabs && ctx->opt_p2p && ctx->p2p_ready && p->nz >= 6;
+    if (slabs && !peer) pl.K = 1;
     const bool flow = !slabs && ctx->opt_ptv_flow && ptv_lb_threads(pl.lb) == 256;
     PtV k;
     NS3D_TRY(make_ptv(ctx, p, pl, pl.K, &k, flow));
     ptv_balance_chunks(k);
+    // the band plan of a chunk of iterations (ptv_run_direct)
+    int nb = 0;
+    const bool split = peer && ctx->opt_p2p_split && (p->nz - 2) >= 2 * pl.zf + 4;
+    if (!flow && !slabs) {
+        nb = ptv_bands_plan(ctx, k, pl, pl.K, 2, p->zchunk > 0);
+    } else if (split) {
+        PtV in = k;
+        in.kbeg = 1 + pl.zf;
+        in.kend = p->nz - 1 - pl.zf;
+        if (p->zchunk <= 0) in.zchunk = auto_zchunk(ctx, in, pl.K, in.kend - in.kbeg, pl.lb);
+        ptv_balance_chunks(in);
+        nb = ptv_bands_plan(ctx, in, pl, pl.K, 2, p->zchunk > 0);
+        k.zchunk = in.zchunk;
+    }
     const char* mode = ctx->mode == NS3D_PARITY ? "PARITY" : (ctx->mode == NS3D_FAST ? "FAST" : "FASTEST");
+    char bands[160] = "";
+    if (nb > 0)
+        snprintf(bands, sizeof bands, "; a pass = %d launches (z-bands on %d streams, band b waits for bands b-1, b, b+1 of the previous pass)",
+                 nb + (split ? 1 : 0), nb + (split ? 1 : 0));
     if (buf && cap > 0)
         snprintf(buf, cap,
                  "%s<%s,K=%d> (%s%d fused PT iterations per pass over the fields: %d x (K5+K6+set_bc_Pr!) on the pitched copies, z-plane "
-                 "tiles staged by TMA; tiles of %d x %d cells, %d x %d tiles, %d-plane chunks, %d threads, %u B shared memory%s)",
+                 "tiles staged by TMA; tiles of %d x %d cells, %d x %d tiles, %d-plane chunks, %d threads, %u B shared memory%s%s)",
                  flow ? "ptv_flow_kernel" : "ptv_kernel", mode, pl.K,
                  flow ? "persistent: all passes between two residual checks are ONE launch, work items ordered by pass and z-chunk with "
                         "per-chunk completion counters; "
                       : "",
-                 pl.K, pl.K, 2 * k.pxt, k.bty, k.ntx, k.nty, k.zchunk, ptv_threads(k), k.sm_total,
+                 pl.K, pl.K, 2 * k.pxt, k.bty, k.ntx, k.nty, k.zchunk, ptv_threads(k), k.sm_total, bands,
                  slabs ? "; slab-interface chunks: the P2P instantiation with update_halo!(Pr) over peer memory" : "");
     if (iters_per_launch) *iters_per_launch = pl.K;
     return NS3D_OK;

@@ -65,6 +65,11 @@ def run_ranks(world, grid, nt, lz, how="step", options=None):
     (2, (16, 10, 26), 2, 50 / 16, "step", {"graphs": 0}),          # whole time steps without graph replay
     (2, (16, 10, 26), 12, 50 / 16, "pt_random", {"p2p_split": 0}), # thick slabs, ONE launch per pass (interface chunks inside it)
     (3, (16, 10, 26), 2, 76 / 16, "step", {"p2p_split": 0}),
+    # tall slabs: the planes between the interface chunks run as z-BANDS of launches on their own streams (band b of a pass
+    # waits for bands b-1, b, b+1 of the previous one), the interface chunks as one more band on the high-priority stream
+    (2, (12, 9, 50), 12, 98 / 12, "pt_random", {}),
+    (2, (12, 9, 50), 13, 98 / 12, "pt_random", {"ptv_bands": 3, "graphs": 0}),
+    (2, (12, 9, 50), 2, 98 / 12, "step", {}),
 ])
 def test_rank_processes_match_igg_emulation(world, grid, nt, lz, how, options):
     results = run_ranks(world, grid, nt, lz, how, options)

@@ -46,6 +46,7 @@ for g in args.grids.split(","):
             ctx.set_option("ptv_lb", -1)
             ctx.set_option("ptv_tma", 1)
             ctx.set_option("ptv_flow", 0)
+            ctx.set_option("ptv_bands", -1)
             ctx.set_option("serpentine", -1)
             zc = 0
             for k, v in opts.items():

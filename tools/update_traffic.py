@@ -2,7 +2,9 @@
 looks up (workload : mode : options : hash of the kernel sources), so that `roofline.traffic` is only ever reported
 for the kernel source it was measured on.
 
-    python tools/update_traffic.py gpurun_out/r2ncu/ptv_x_1.ncu-rep B FAST [name=value ...]
+    python tools/update_traffic.py gpurun_out/r2ncu/ptv_x_1.ncu-rep B FAST [--passes=N] [name=value ...]
+
+--passes=N: the capture holds EVERY ptv_kernel launch of N passes over the fields (z-bands: several launches per pass).
 """
 import csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,7 +12,8 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 rep, workload, mode = sys.argv[1:4]
-opts = sys.argv[4:]
+opts = [a for a in sys.argv[4:] if not a.startswith("--passes=")]
+passes = next((int(a.split("=")[1]) for a in sys.argv[4:] if a.startswith("--passes=")), 0)   # z-bands: launches per pass vary
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
@@ -24,7 +27,7 @@ for r in data:
         v, u = float(r[ix[k]]), units[ix[k]].lower()
         tot += v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
     vals.append(tot)
-traffic = sum(vals) / len(vals)
+traffic = sum(vals) / (passes if passes else len(vals))   # per pass over the fields (= per launch without z-bands)
 path = os.path.join(ROOT, "profiles", "traffic.json")
 d = json.load(open(path))
 key = bench.kernel_key(workload, mode, opts)
