@@ -14,19 +14,31 @@ import bench  # noqa: E402
 rep, workload, mode = sys.argv[1:4]
 opts = [a for a in sys.argv[4:] if not a.startswith("--passes=")]
 passes = next((int(a.split("=")[1]) for a in sys.argv[4:] if a.startswith("--passes=")), 0)   # z-bands: launches per pass vary
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, data = rows[0], rows[1], rows[2:]
-ix = {h: i for i, h in enumerate(hdr)}
+SCALE = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}
 vals = []
-for r in data:
-    if "ptv_kernel" not in r[ix["Kernel Name"]]:
-        continue
-    tot = 0.0
-    for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-        v, u = float(r[ix[k]]), units[ix[k]].lower()
-        tot += v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
-    vals.append(tot)
+if rep.endswith(".csv"):
+    # `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --csv --log-file X.csv`: one row per launch and metric
+    rows = list(csv.reader(l for l in open(rep, newline="") if l.startswith('"')))
+    ix = {h: i for i, h in enumerate(rows[0])}
+    per_launch = {}
+    for r in rows[1:]:
+        if "ptv_kernel" not in r[ix["Kernel Name"]] or not r[ix["Metric Name"]].startswith("dram__bytes"):
+            continue
+        v = float(r[ix["Metric Value"]].replace(",", "")) * SCALE[r[ix["Metric Unit"]].lower()]
+        per_launch[r[ix["ID"]]] = per_launch.get(r[ix["ID"]], 0.0) + v
+    vals = list(per_launch.values())
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    for r in data:
+        if "ptv_kernel" not in r[ix["Kernel Name"]]:
+            continue
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(r[ix[k]]) * SCALE[units[ix[k]].lower()]
+        vals.append(tot)
 traffic = sum(vals) / (passes if passes else len(vals))   # per pass over the fields (= per launch without z-bands)
 path = os.path.join(ROOT, "profiles", "traffic.json")
 d = json.load(open(path))
