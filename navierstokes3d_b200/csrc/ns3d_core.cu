@@ -199,6 +199,7 @@ extern "C" int ns3d_set_option(ns3d_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "ptv_pxt")) { ctx->opt_ptv_pxt = value < 0 ? 0 : value; return NS3D_OK; }
     if (!strcmp(name, "ptv_bty")) { ctx->opt_ptv_bty = value < 0 ? 0 : value; return NS3D_OK; }
     if (!strcmp(name, "graphs")) { ctx->opt_graphs = value != 0; return NS3D_OK; }
+    if (!strcmp(name, "graph_pieces")) { ctx->opt_graph_pieces = value < 0 ? -1 : value; return NS3D_OK; }
     if (!strcmp(name, "serpentine")) { ctx->opt_serpentine = value < 0 ? -1 : (value != 0); return NS3D_OK; }
     return ns3d_fail(ctx, NS3D_EINVAL, "ns3d_set_option: unknown option '%s'", name);
 }

@@ -50,6 +50,7 @@ struct ns3d_ctx {
     // tuning knobs (ns3d_set_option)
     int opt_serpentine = -1;  // -1 = by working-set size
     int opt_graphs = 1;       // replay chunks of PT iterations as CUDA graphs
+    int opt_graph_pieces = -1; // ... each chunk as this many graphs launched back to back (-1 = default 1; see ptv_run_pieces)
     long long halo_calls = 0; // uncaptured halo exchanges so far (NCCL peers connected)
     // the fused loop's pitched working copies (ns3d_ptv.cu): Pr x2, dPrdtau x2 (ping-pong), divV
     double* ptv_raw[5] = {};    // cudaMalloc blocks

@@ -631,6 +631,29 @@ int ptv_run(ns3d_ctx* ctx, PtvRun& r, int n, int iter0)
     return NS3D_OK;
 }
 
+// A chunk of iterations as several graphs launched back to back (option graph_pieces; off by default).  The chunk between
+// two residual checks is one graph of hundreds of kernel nodes (255x153x153 with z-bands: 76 passes x 8 launches), launched
+// after a host synchronisation; in pieces only the first piece's launch would be exposed.  Measured
+// (profiles/r02_graph_pieces_bench.log): 8 428 GB/s in one piece, 8 334 in two, 8 197 in four, 8 010 in eight -- the launch
+// is not what the step waits for, and every piece boundary drains the bands.  Pieces hold an even number of passes (the
+// ping-pong buffers end where they started: one cached graph serves them all).
+int ptv_run_pieces(ns3d_ctx* ctx, PtvRun& r, int n, int iter0)
+{
+    const int K = r.pl.K;
+    int pieces = ctx->opt_graph_pieces;
+    if (pieces < 0) pieces = 1;
+    if (!ctx->opt_graphs || pieces <= 1 || n / K < 8 * pieces) return ptv_run(ctx, r, n, iter0);
+    int per = (n / K + pieces - 1) / pieces;   // passes per piece ...
+    per += per & 1;                            // ... an even number
+    int done = 0;
+    while (done < n) {
+        const int m = std::min(per * K, n - done);
+        NS3D_TRY(ptv_run(ctx, r, m, iter0 + done));
+        done += m;
+    }
+    return NS3D_OK;
+}
+
 int ptv_residual(ns3d_ctx* ctx, const PtvRun& r)
 {
     PtV k;
@@ -743,7 +766,7 @@ int ns3d_internal_ptv_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const do
     int iters = 0, nc = 0;
     while (iters < p->niter) {
         const int chunk = std::min(p->nchk - iters % p->nchk, p->niter - iters);  // up to the next check
-        NS3D_TRY(ptv_run(ctx, r, chunk, iters));
+        NS3D_TRY(ptv_run_pieces(ctx, r, chunk, iters));
         iters += chunk;
         if (iters % p->nchk == 0) {
             NS3D_TRY(ptv_residual(ctx, r));
@@ -766,7 +789,7 @@ int ns3d_internal_ptv_iterate(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const 
     PtvRun r;
     r.p = p;
     NS3D_TRY(ptv_begin(ctx, r, Pr, dPrdtau, divV, n_iter));
-    NS3D_TRY(ptv_run(ctx, r, n_iter, 0));
+    NS3D_TRY(ptv_run_pieces(ctx, r, n_iter, 0));
     return ptv_end(ctx, r, Pr, dPrdtau, false);
 }
 
