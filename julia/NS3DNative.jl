@@ -17,7 +17,7 @@
 # call for call.  Every `ccall` below passes its arguments one by one (`ccall` takes no splats).
 module NS3DNative
 
-export Ctx, DevArray, zeros3, to_host, set!, set_mode!, PARITY, FAST, FASTEST, VARIANT_M, VARIANT_G,
+export Ctx, DevArray, zeros3, to_host, set!, set_mode!, fill_profile_z!, fill_profile_zy!, fill_plane_x!, PARITY, FAST, FASTEST, VARIANT_M, VARIANT_G,
        update_τ!, predict_V!, update_∇V!, update_dPrdτ!, update_Pr!, compute_res!, max_g_abs, correct_V!,
        bc_x!, bc_y!, bc_z!, bc_x_Vx!, bc_x_Pr!, bc_zV!, bc_xhydstatic!, set_bc_Vel_M!, set_bc_Vel_G!,
        set_bc_Pr_M!, set_bc_Pr_G!, advect!, set_cylinder_M!, set_cylinder_G!, update_halo!,
@@ -83,6 +83,29 @@ function Base.copy!(c::Ctx, dst::DevArray, src::DevArray)
     dst.dims == src.dims || error("shape mismatch")
     check(c, ccall((:ns3d_copy, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Csize_t), c.h, dst.p, src.p, length(src)))
     return dst
+end
+
+# ---- device-side initialisers: the comprehensions of G:86-87 / M:369-370 without a 3-D host array ----
+"`A[ix,iy,iz] = profile[iz]` (G:86-87): nz host values cross PCIe"
+function fill_profile_z!(c::Ctx, a::DevArray, profile::Vector{Float64})
+    length(profile) == a.dims[3] || error("fill_profile_z!: one value per z-plane")
+    sx, sy, sz = a.dims
+    check(c, ccall((:ns3d_fill_profile_z, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Cint, Ptr{Float64}), c.h, a.p, sx, sy, sz, profile))
+    return a
+end
+"`A[ix,iy,iz] = (profile[iz] + add_y[iy]) + add_z[iz]` (M:370 term by term: with g = 0 the terms are signed zeros)"
+function fill_profile_zy!(c::Ctx, a::DevArray, profile::Vector{Float64}, add_y::Vector{Float64}, add_z::Vector{Float64})
+    (length(profile) == a.dims[3] && length(add_z) == a.dims[3] && length(add_y) == a.dims[2]) || error("fill_profile_zy!: shape mismatch")
+    sx, sy, sz = a.dims
+    check(c, ccall((:ns3d_fill_profile_zy, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   c.h, a.p, sx, sy, sz, profile, add_y, add_z))
+    return a
+end
+"`A[ix,:,:] .= value` (M:369); ix 1-based"
+function fill_plane_x!(c::Ctx, a::DevArray, ix::Integer, value::Real)
+    sx, sy, sz = a.dims
+    check(c, ccall((:ns3d_fill_plane_x, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Cint, Cint, Cdouble), c.h, a.p, sx, sy, sz, ix - 1, value))
+    return a
 end
 
 # ---- output path: only the requested box leaves the device (ns3d_box_d2h) ---------------------
