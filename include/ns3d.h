@@ -240,9 +240,10 @@ typedef struct ns3d_pt_params {
     int reserved;
 } ns3d_pt_params;
 
-/* The whole pseudo-transient loop M:458-471 / G:126-137 in fused kernels:
- * K5+K6+set_bc_Pr! are one launch per iteration (Pr ping-pongs with a context-owned
- * shadow buffer), compute_res!+abs+maximum(+allreduce) one launch per check.
+/* The whole pseudo-transient loop M:458-471 / G:126-137 in fused kernels, on pitched copies of
+ * the three arrays owned by the context (packed on entry, unpacked on exit): K x (K5+K6+set_bc_Pr!
+ * (+update_halo!(Pr) over peer memory on z-slabs)) per launch, K = 2 by default;
+ * compute_res!+abs+maximum(+allreduce) one launch per check.
  * h_err_hist (capacity err_cap) receives err at every check (M:467).  On return Pr
  * and dPrdtau hold exactly the reference's iterates after *h_iters iterations. */
 NS3D_API int ns3d_pt_solve(ns3d_ctx* ctx, double* Pr, double* dPrdtau, const double* divV,
@@ -272,19 +273,24 @@ typedef struct ns3d_step_params {
     int reserved;
 } ns3d_step_params;
 
-/* The three once-per-step groups around the PT loop, each the level-1 sequence of its lines:
- *   predictor   M:449-455 / G:121-124  update_τ!, predict_V!, set_cylinder!, update_halo!(C,V),
- *                                      update_∇V!, update_halo!(∇V)
- *   corrector   M:472-474 / G:138-140  correct_V!, set_cylinder!, set_bc_Vel! (halo inside)
+/* The three once-per-step groups around the PT loop, each with the effect of the level-1 sequence of its lines:
+ *   predictor   M:449-455 / G:121-124  update_τ!, predict_V!, set_cylinder! (ONE kernel, the stresses never reach memory:
+ *                                      the six stress arrays are not touched and may be NULL; Vx_o, Vy_o, Vz_o are used as
+ *                                      scratch -- the reference overwrites them at M:475 before it reads them again),
+ *                                      update_halo!(C,V), update_∇V!, update_halo!(∇V)
+ *   corrector   M:472-474 / G:138-140  correct_V! + set_cylinder! (one kernel), set_bc_Vel! (halo inside)
  *   advect_swap M:475-477 / G:141-142  `A_o .= A` x4, advect!, update_halo!(Vx,Vy,Vz)
  * Asynchronous on the context's stream.                                                  */
 NS3D_API int ns3d_predictor(ns3d_ctx* ctx, const ns3d_fields* f, const ns3d_step_params* p);
 NS3D_API int ns3d_corrector(ns3d_ctx* ctx, const ns3d_fields* f, const ns3d_step_params* p);
 NS3D_API int ns3d_advect_swap(ns3d_ctx* ctx, const ns3d_fields* f, const ns3d_step_params* p);
 
-/* One whole time step M:449-477 / G:121-142 (everything between the `for it` line
- * and the visualisation block) = predictor, ns3d_pt_solve, corrector, advect_swap.
- * Same iterates as the level-1 sequence.                                         */
+/* One whole time step M:449-477 / G:121-142 (everything between the `for it` line and the visualisation block) in
+ * fused kernels: the velocity makes one round trip through the `_o` arrays (predictor V -> V_o, corrector and boundary
+ * conditions in place on V_o, advection V_o -> V writing every entry), so the four copies of M:475 never happen as
+ * copies.  On return EVERY array holds what the reference's step leaves in it -- the snapshots Vx_o, Vy_o, Vz_o, C_o
+ * included, same PT iteration count and err history -- except the six stress arrays, which are not touched (NULL
+ * allowed).                                                                                                          */
 NS3D_API int ns3d_step(ns3d_ctx* ctx, const ns3d_fields* f, const ns3d_step_params* p, int* h_iters,
               double* h_err_hist, int err_cap, int* h_nchecks);
 
