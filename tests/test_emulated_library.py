@@ -55,6 +55,8 @@ def test_fused_iteration(O, ns, ctx, variant, grid, zchunk):
     ("G", (16, 9, 8), 2, "k1_coop_tiles"), ("M", (4, 3, 6), 1, "k3_tiles"), ("G", (3, 3, 3), 0, "k3_lb0"),
     ("M", (20, 12, 12), 2, "k2_flow"), ("G", (20, 19, 11), 3, "k3_flow_tiles"), ("M", (16, 9, 8), 0, "k1_flow"),
     ("G", (37, 23, 19), 7, "k2_flow_lb0"),
+    ("M", (20, 12, 19), 2, "k2_bands3"), ("G", (20, 19, 23), 3, "k3_bands5_tiles"), ("M", (16, 9, 38), 2, "k2_bands16_nographs"),
+    ("G", (20, 12, 19), 2, "k2_nobands"),
 ])
 def test_ptv_kernel(O, ns, ctx, variant, grid, zchunk, cfg):
     """The fused loop's kernel in every configuration behind the options -- iterations per launch, launch bounds,

@@ -83,6 +83,12 @@ PTV_CONFIGS = {
     "k2_flow_lb0": {"ptv_k": 2, "ptv_lb": 0, "ptv_flow": 1},
     "k3_flow_tiles": {"ptv_k": 3, "ptv_lb": 0, "ptv_pxt": 6, "ptv_bty": 7, "ptv_flow": 1},
     "k1_flow": {"ptv_k": 1, "ptv_flow": 1},
+    # z-bands (ptv_run_banded: a pass as several launches on as many streams, band b waiting for bands b-1, b, b+1 of the
+    # previous pass; on by default for grids of this size -- here with explicit band counts, and switched off)
+    "k2_bands3": {"ptv_k": 2, "ptv_bands": 3},
+    "k3_bands5_tiles": {"ptv_k": 3, "ptv_lb": 0, "ptv_pxt": 6, "ptv_bty": 7, "ptv_bands": 5},
+    "k2_bands16_nographs": {"ptv_k": 2, "ptv_bands": 16, "graphs": 0},
+    "k2_nobands": {"ptv_k": 2, "ptv_bands": 0},
 }
 
 
