@@ -78,7 +78,7 @@ PTV_CONFIGS = {
     "k2_coop_nographs": {"ptv_k": 2, "ptv_tma": 0, "graphs": 0, "serpentine": 1},
     "k1_coop_tiles": {"ptv_k": 1, "ptv_tma": 0, "ptv_pxt": 4, "ptv_bty": 3},
     # the PERSISTENT launch (ptv_flow_kernel, option ptv_flow: all full passes of a call are ONE kernel, work queue +
-    # per-chunk completion counters between dependent passes); off by default -- measured slower, DESIGN.md section 3.3
+    # per-chunk completion counters between dependent passes); off by default -- measured slower, DESIGN.md section 3.4
     "k2_flow": {"ptv_k": 2, "ptv_flow": 1},
     "k2_flow_lb0": {"ptv_k": 2, "ptv_lb": 0, "ptv_flow": 1},
     "k3_flow_tiles": {"ptv_k": 3, "ptv_lb": 0, "ptv_pxt": 6, "ptv_bty": 7, "ptv_flow": 1},
