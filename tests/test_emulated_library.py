@@ -40,6 +40,13 @@ test_box_rejects_a_box_outside_the_array = Z.test_box_rejects_a_box_outside_the_
 test_device_side_initialisers = D.test_device_side_initialisers_match_the_scripts_arrays
 
 
+# ---- whole runs against what the reference's own source text computes (jl_reference_fixtures.npz) ----
+@pytest.mark.parametrize("rid,path", [("M31", "fused"), ("M31", "level1"), ("M31", "groups"), ("G20", "fused"), ("G20", "level1"),
+                                      ("M40rot", "fused")])
+def test_library_runs_equal_the_reference_text(ns, rid, path):
+    D.test_library_runs_equal_the_reference_text(ns, rid, path)
+
+
 # ---- level 2 on CPU-sized grids ---------------------------------------------------------------------
 @pytest.mark.parametrize("variant", ["M", "G"])
 @pytest.mark.parametrize("grid", [(3, 3, 3), (5, 4, 3), (20, 12, 9)])

@@ -93,3 +93,36 @@ def test_device_side_initialisers_match_the_scripts_arrays(ns, variant, nx):
         assert np.array_equal(a, b) and np.array_equal(np.signbit(a), np.signbit(b)), name
     dev.ctx.close()
     host.ctx.close()
+
+
+# ---- the library against the reference's own source text (tests/golden/jl_reference_fixtures.npz) ----------
+def _text_fixtures():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "jl_reference_fixtures.npz"))
+    return z, json.loads(str(z["meta"]))
+
+
+@pytest.mark.parametrize("rid,path", [("M31", "fused"), ("M31", "level1"), ("M31", "groups"), ("G20", "fused"), ("G20", "level1"),
+                                      ("M40rot", "fused"), ("G40", "fused"), ("M63", "fused")])
+def test_library_runs_equal_the_reference_text(ns, rid, path):
+    """Whole runs of the two scripts through the C ABI (PARITY arithmetic) against what the scripts' own TEXT
+    computes when oracle/jl_interp.py executes it (tests/golden/make_jl_fixtures.py; nothing of the C oracle is
+    involved in the expected values): identical PT iteration counts, every residual of every check, and the
+    final Pr, Vx, Vy, Vz, C bit for bit -- through ns3d_step, through the level-2 groups and call site by call
+    site through level 1."""
+    from tests import jl_cases as J
+    z, meta = _text_fixtures()
+    _, variant, nx, nt, _, lit = next(rc for rc in J.RUN_CASES if rc[0] == rid)
+    ph = ns.Physics(**lit) if lit else None
+    s = ns.setup_multi_gpu(nx, physics=ph) if variant == "M" else ns.setup_gpu(nx, physics=ph)
+    sim = ns.Simulation(s, mode=ns.PARITY, device=0)
+    for _ in range(nt):
+        {"fused": sim.step, "level1": sim.step_level1, "groups": sim.step_groups}[path]()
+    m = meta["run"][rid]
+    assert sim.iters == m["iters"]
+    assert sim.err_hist == m["errs"]
+    for name in J.RUN_FIELDS:
+        got = sim.host(name)
+        assert J.digest(got) == m["digest"][name], f"{rid}/{path}: {name} differs from the reference text's result"
+        if rid in J.FULL_ARRAYS:
+            assert np.array_equal(got, z[f"run/{rid}/{name}"])
+    sim.ctx.close()

@@ -1,0 +1,294 @@
+"""The oracle pinned to the reference's own SOURCE TEXT.
+
+Julia is not in the image, so the reference cannot run; its one golden vector is stale.  What can be
+done instead: oracle/jl_interp.py tokenises and parses the two reference scripts as they lie under
+/root/reference and evaluates their kernels, boundary-condition functions, parameter blocks, initial
+conditions and time loops with numpy -- only the meaning of the package names (ParallelStencil's
+FiniteDifferences3D macros and launch ranges, ImplicitGlobalGrid on one rank, Base Julia arithmetic) is
+restated there.  tests/golden/make_jl_fixtures.py stored what that execution produces.
+
+* always (the fixtures travel, /root/reference does not): the C oracle against the fixtures, BIT-EXACT --
+  78 single launches on seeded random fields and 5 whole runs incl. PT iteration counts and err histories;
+* when /root/reference is present: the fixtures re-derived from the text (they cannot drift from it), and
+  the line ranges the runs execute checked against the cited ones;
+* the interpreter itself on Julia snippets whose value is known (precedence, `2μ`, `^`, `%`, short-circuit,
+  divergent `if`, bounds checks).
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import jl_run
+from oracle.jl_interp import JlError, JuliaScript, L, lin_range
+from tests import jl_cases as J
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+live = pytest.mark.skipif(not jl_run.reference_available(), reason="/root/reference is not on this machine")
+
+
+@pytest.fixture(scope="module")
+def fx():
+    z = np.load(os.path.join(GOLD, "jl_reference_fixtures.npz"))
+    return z, json.loads(str(z["meta"]))
+
+
+def same_bits(a, b):
+    return a.shape == b.shape and np.array_equal(np.asfortranarray(a).view(np.uint64), np.asfortranarray(b).view(np.uint64))
+
+
+# ---- the C oracle against what the reference's text computes ----------------------------------------
+@pytest.mark.parametrize("case", J.KERNEL_CASES, ids=J.case_id)
+def test_oracle_kernel_equals_reference_text(O, fx, case):
+    z, meta = fx
+    p, f = J.inputs_of(O, case)
+    before = {n: a.copy(order="F") for n, a in f.items()}
+    J.run_oracle(O, case, p, f)
+    cid = J.case_id(case)
+    for n in J.OUTPUTS[case[0]]:
+        assert J.digest(f[n]) == meta["kernel"][cid][n], f"{cid}: {n} differs from the reference text's result"
+        key = f"kernel/{cid}/{n}"
+        if key in z.files:
+            assert same_bits(f[n], z[key]), key
+    for n in f:                                   # and nothing but the outputs is touched
+        if n not in J.OUTPUTS[case[0]] and n != "absRp":
+            assert same_bits(f[n], before[n]), f"{cid}: {n} modified"
+
+
+@pytest.mark.parametrize("rc", J.RUN_CASES, ids=lambda rc: rc[0])
+def test_oracle_run_equals_reference_text(O, fx, rc):
+    z, meta = fx
+    fields, iters, errs, p = J.run_case_oracle(O, rc)
+    m = meta["run"][rc[0]]
+    assert iters == m["iters"]
+    assert errs == m["errs"]                       # every residual of every check, to the last bit
+    for n in J.RUN_FIELDS:
+        assert J.digest(fields[n]) == m["digest"][n], f"{rc[0]}: {n}"
+        if rc[0] in J.FULL_ARRAYS:
+            assert same_bits(fields[n], z[f"run/{rc[0]}/{n}"])
+    # the parameter block (M:290-341 / G:15-61) as the text derives it
+    for jl, attr in (("dx", "dx"), ("dy", "dy"), ("dz", "dz"), ("dt", "dt"), ("dτ", "dtau"), ("damp", "damp"),
+                     ("niter", "niter"), ("nchk", "nchk"), ("a2", "a2"), ("b2", "b2"), ("g", "g")):
+        assert getattr(p, attr) == m["params"][jl], jl
+
+
+def test_test3D_samples_of_the_text_run(O, fx):
+    """test/test3D.jl's own sampling `Pr[inds_x,inds_y,inds_z]` on the M63 run of the text (three steps: the
+    first is degenerate): the oracle reproduces the 64 samples bit for bit, and they are NOT the stale literals."""
+    z, meta = fx
+    with open(os.path.join(GOLD, "test3D_pr_ref.json")) as fh:
+        t3 = json.load(fh)
+    fields, _, _, _ = J.run_case_oracle(O, next(rc for rc in J.RUN_CASES if rc[0] == "M63"))
+    ix, iy, iz = (np.array(t3[k]) - 1 for k in ("inds_x", "inds_y", "inds_z"))
+    got = O.interior(fields["Pr"])[np.ix_(ix, iy, iz)]
+    assert same_bits(got, z["run/M63/Pr_samples"])
+    assert np.abs(got).max() > 0
+    assert not np.allclose(got, np.array(t3["Pr_ref"]).transpose(2, 1, 0), rtol=t3["rtol"], atol=0.0)
+
+
+# ---- the fixtures re-derived from the text (build container only) -------------------------------------
+@pytest.fixture(scope="module")
+def scripts():
+    return {"M": JuliaScript.from_file(jl_run.M_PATH), "G": JuliaScript.from_file(jl_run.G_PATH)}
+
+
+@live
+def test_fixtures_are_what_the_text_computes_kernels(O, fx, scripts):
+    z, meta = fx
+    for case in J.KERNEL_CASES:
+        p, f = J.inputs_of(O, case)
+        J.run_interp(scripts[case[1]], case, p, f)
+        for n in J.OUTPUTS[case[0]]:
+            assert J.digest(f[n]) == meta["kernel"][J.case_id(case)][n], (J.case_id(case), n)
+
+
+@live
+@pytest.mark.parametrize("rid", ["M31", "G20", "M40rot"])
+def test_fixtures_are_what_the_text_computes_runs(fx, rid):
+    z, meta = fx
+    rc = next(rc for rc in J.RUN_CASES if rc[0] == rid)
+    fields, iters, errs, env, info = J.run_case_interp(jl_run, rc)
+    assert iters == meta["run"][rid]["iters"] and errs == meta["run"][rid]["errs"]
+    for n in J.RUN_FIELDS:
+        assert J.digest(fields[n]) == meta["run"][rid]["digest"][n]
+
+
+@live
+def test_the_runs_execute_the_cited_lines(scripts):
+    """M:288-373 + M:446-477, G:13-88 + G:119-142 (what DESIGN.md and the oracle cite)."""
+    _, _, _, info = jl_run.run_M(9, 1)
+    assert info["prefix"] == (288, 374) and info["loop"] == (446, 477)
+    _, _, _, info = jl_run.run_G(20, 1)
+    assert info["prefix"] == (13, 88) and info["loop"] == (119, 142)
+    kinds = {n: d.kind for n, d in scripts["M"].defs.items()}
+    assert kinds["update_dPrdτ!"] == "ps_kernel" and kinds["advect!"] == "pi_kernel" and kinds["backtrack!"] == "function"
+    assert scripts["M"].defs["update_τ!"].lines == (36, 44) and scripts["G"].defs["set_cylinder!"].lines == (336, 368)
+    assert set(scripts["M"].macros) == {"∇V"} == set(scripts["G"].macros)
+
+
+@live
+def test_launch_sequence_of_one_time_step():
+    """The order of kernel launches in one step of M, as the text issues them (M:449-476): what ns3d_step fuses."""
+    env, iters, _, info = jl_run.run_M(9, 1)
+    names = [n for n, _ in info["script"].launches]
+    assert names[0] == "set_cylinder!"                                  # M:372
+    step = names[1:]
+    assert step[:4] == ["update_τ!", "predict_V!", "set_cylinder!", "update_∇V!"]
+    per_iter = ["update_dPrdτ!", "update_Pr!", "bc_x!", "bc_y!", "bc_z!", "bc_x_Pr!"]
+    assert step[4:4 + len(per_iter)] == per_iter
+    tail = ["correct_V!", "set_cylinder!", "bc_x!", "bc_y!", "bc_z!", "bc_x!", "bc_z!", "bc_x!", "bc_y!", "bc_x_Vx!", "advect!"]
+    assert step[-len(tail):] == tail
+    assert step.count("compute_res!") == len(range(env["nchk"], iters[0] + 1, env["nchk"]))
+
+
+@live
+def test_a_diverged_run_raises_like_julia(scripts):
+    """`floor(Int, x)` of a non-finite value is an InexactError in Julia; the interpreter does not paper over it."""
+    S = scripts["M"]
+    n = (5, 4, 3)
+    A, A_o = np.zeros(n, order="F"), np.zeros(n, order="F")
+    ix = L(np.array([2])); one = L(np.array([1]))
+    with pytest.raises(JlError, match="InexactError"):
+        S.call_def(S.defs["backtrack!"], [A, A_o, L(np.array([np.inf])), 0.0, 0.0, 1.0, 1.0, 1.0, 1.0, ix, one, one])
+
+
+# ---- the interpreter on snippets with known values -------------------------------------------------------
+def run_snippet(src, env=None, **frozen):
+    s = JuliaScript(src)
+    s.frozen = frozen
+    env = {} if env is None else env
+    s.run_lines(1, src.count("\n") + 1, env)
+    return env, s
+
+
+def test_precedence_and_literal_coefficients():
+    env, _ = run_snippet("μ = 3.0\na = 2μ*5.0\nb = 1/2μ\nc = -2.0^2\nd = 2.0^3^2\ne = 7 % 3\nf = -7.5 % 2\n"
+                         "g = 1.0/3.0/3.0\nh = 1.0 - 2.0 - 3.0\ni = 2μ^2\nj = (1 + 2)*3\nk = 10/4\nl = 1:3\nm = 2 < 3 && 3 < 2 || true\n"
+                         "n = 1/Inf^2*5.0\no = ceil(Int, 63*0.6)\np = !(1 > 2)")
+    assert env["a"] == 30.0 and env["b"] == 1 / 6.0 and env["c"] == -4.0 and env["d"] == 512.0
+    assert env["e"] == 1 and env["f"] == -1.5                        # rem: sign of the dividend, like C fmod
+    assert env["g"] == (1.0 / 3.0) / 3.0 and env["h"] == -4.0 and env["i"] == 18.0 and env["j"] == 9 and env["k"] == 2.5
+    assert env["l"] == ("range", 1, 3) and env["m"] is True and env["n"] == 0.0 and env["o"] == 38 and env["p"] is True
+
+
+def test_tuple_assignment_blocks_and_loops():
+    env, _ = run_snippet("a, b = 1.5, 2.5\ns, c = sincos(0*π/6)\nacc = 0\nfor i = 1:10\n  if i % 2 == 0 acc += i end\n"
+                         "  if i == 7 break end\nend\nxs = Float64[]; push!(xs, acc/4)\nf(x,y) = (t = x*y; t + 1)\nv = f(2, 3)")
+    assert (env["a"], env["b"], env["s"], env["c"]) == (1.5, 2.5, 0.0, 1.0)
+    assert env["acc"] == 12 and env["i"] == 7 and env["xs"] == [3.0] and env["v"] == 7
+
+
+def test_frozen_literals():
+    env, _ = run_snippet("nx = 255\nny = ceil(Int, nx*0.6)", nx=20)
+    assert env["nx"] == 20 and env["ny"] == 12
+
+
+def test_linrange_is_lerpi():
+    r = lin_range(-0.5, 0.5, 4)
+    assert r[0] == -0.5 and r[3] == 0.5 and r[1] == (1 - 1 / 3) * -0.5 + (1 / 3) * 0.5
+
+
+SRC_KERNELS = '''
+@parallel function lap!(B, A, dx)
+    @inn(B) = @d2_xi(A)/dx/dx + @d2_yi(A)/dx/dx + @d2_zi(A)/dx/dx
+    @all(B) = @all(B) + 1.0
+    return
+end
+@parallel_indices (ix,iy,iz) function pick!(A, B)
+    if ix > 1 && ix <= size(B,1) && B[ix-1,iy,iz] > 0.0
+        t = B[ix-1,iy,iz]
+        if t > 0.5
+            A[ix,iy,iz] = t
+        else
+            A[ix,iy,iz] = -t
+        end
+    end
+    return
+end
+@parallel_indices (iy,iz) function oob!(A)
+    A[end+1, iy, iz] = 0.0
+    return
+end
+function go!(A, B, dx)
+    @parallel lap!(B, A, dx)
+    @parallel (1:size(A,2),1:size(A,3)) oob!(A)
+    return
+end
+'''
+
+
+def test_parallel_function_statement_boxes():
+    s = JuliaScript(SRC_KERNELS)
+    rng = np.random.default_rng(3)
+    A = np.asfortranarray(rng.uniform(-1, 1, (6, 5, 4)))
+    B = np.zeros((6, 5, 4), order="F")
+    s.launch(s.defs["lap!"], [B, A, 0.5])
+    want = np.ones_like(B)
+    for i in range(1, 5):
+        for j in range(1, 4):
+            for k in range(1, 3):
+                d2 = lambda a, b, c: (a - b) - (b - c)   # noqa: E731
+                want[i, j, k] = ((d2(A[i + 1, j, k], A[i, j, k], A[i - 1, j, k]) / 0.5 / 0.5
+                                  + d2(A[i, j + 1, k], A[i, j, k], A[i, j - 1, k]) / 0.5 / 0.5)
+                                 + d2(A[i, j, k + 1], A[i, j, k], A[i, j, k - 1]) / 0.5 / 0.5) + 1.0
+    assert same_bits(B, want)
+
+
+def test_divergent_if_short_circuit_and_bounds():
+    s = JuliaScript(SRC_KERNELS)
+    rng = np.random.default_rng(4)
+    B = np.asfortranarray(rng.uniform(-1, 1, (5, 4, 3)))
+    A = np.full((6, 4, 3), 9.0, order="F")            # the launch box is A's: ix reaches 6 > size(B,1)
+    s.launch(s.defs["pick!"], [A, B])
+    want = np.full_like(A, 9.0)
+    for i in range(1, 5):                             # 0-based ix-1 in 1..4  <->  Julia ix in 2..5
+        for j in range(4):
+            for k in range(3):
+                t = B[i - 1, j, k]
+                if t > 0.0:
+                    want[i, j, k] = t if t > 0.5 else -t
+    assert same_bits(A, want)                         # and B[ix-1] was never read where ix == 1 or ix == 6
+    with pytest.raises(JlError, match="out of bounds"):
+        s.call_def(s.defs["go!"], [A, np.zeros_like(A), 1.0])
+
+
+def test_unknown_names_fail_loudly():
+    with pytest.raises(JlError, match="unknown name"):
+        run_snippet("a = no_such_function(1)")
+    assert math.isnan(run_snippet("a = 0.0/0.0")[0]["a"])
+
+
+# ---- sensitivity: an edited text gives other bits -------------------------------------------------------------
+MUTATIONS = [
+    # (kernel case whose result must change, text before, text after)
+    (("update_dPrdτ!", "M", (13, 9, 8), None), "@d2_xi(Pr)/dx/dx", "@d2_xi(Pr)/(dx*dx)"),          # association of the divisions
+    (("update_dPrdτ!", "M", (13, 9, 8), None), "- ρ/dt*@inn(∇V))", "- ρ*@inn(∇V)/dt)"),            # (ρ/dt)*x vs (ρ*x)/dt
+    (("update_τ!", "M", (13, 9, 8), None), "@∇V()/3.0)", "@∇V()*(1.0/3.0))"),                       # division vs reciprocal
+    (("predict_V!", "G", (13, 9, 8), None), "@d_ya(τyz)/dy - ρ*g)", "@d_ya(τyz)/dy) - dt*g"),      # gravity outside the dt/ρ factor
+    (("correct_V!", "M", (13, 9, 8), None), "dt/ρ*@d_xi(Pr)/dx", "dt*@d_xi(Pr)/(ρ*dx)"),
+    (("advect!", "M", (13, 9, 8), 3.0), "lerp(a,b,t) = b*t + a*(1-t)", "lerp(a,b,t) = a + (b-a)*t"),
+    (("advect!", "M", (13, 9, 8), 3.0), "backtrack!(Vy,Vy_o,vxc,vyc,vzc,dt,dx,dy,dz,ix,iy,iz)\n    end\n    if checkbounds",
+     "backtrack!(Vz,Vz_o,vxc,vyc,vzc,dt,dx,dy,dz,ix,iy,iz)\n    end\n    if checkbounds"),      # "fixing" quirk 1 (M:234)
+    (("advect!", "M", (13, 9, 8), 0.0), "δx = (δx>0) - (δx%1)", "δx = (δx>=0) - (δx%1)"),          # weight at zero displacement
+    (("set_cylinder!", "G", (31, 19, 4), "script"), "xc,yc,zc = xv+dx/2, yv+dx/2, zv+dz/2", "xc,yc,zc = xv+dx/2, yv+dy/2, zv+dz/2"),   # "fixing" G:338
+    (("set_cylinder!", "M", (40, 24, 3), "rotated"), "< 1.05", "<= 1.0"),
+]
+
+
+@live
+@pytest.mark.parametrize("mut", MUTATIONS, ids=lambda m: f"{m[0][0]}:{m[1][:18]}")
+def test_an_edited_text_changes_the_bits(O, fx, mut):
+    """The fixtures are sensitive to exactly the things a re-typed restatement gets wrong -- association order,
+    division vs reciprocal, the scripts' quirks: each one-line edit of the text changes the stored digest."""
+    case, old, new = mut
+    z, meta = fx
+    with open(jl_run.M_PATH if case[1] == "M" else jl_run.G_PATH, encoding="utf-8") as fh:
+        text = fh.read()
+    assert old in text
+    s = JuliaScript(text.replace(old, new))
+    p, f = J.inputs_of(O, case)
+    J.run_interp(s, case, p, f)
+    changed = [n for n in J.OUTPUTS[case[0]] if J.digest(f[n]) != meta["kernel"][J.case_id(case)][n]]
+    assert changed, "the edit went unnoticed"
