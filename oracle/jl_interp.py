@@ -36,6 +36,7 @@ from __future__ import annotations
 
 import math
 import re
+import threading
 
 import numpy as np
 
@@ -506,6 +507,32 @@ def lin_range(start, stop, n):
 
 
 # ------------------------------------------------------------------------------------------------
+# ImplicitGlobalGrid on several ranks: one thread per rank, the collectives are rendezvous points
+# ------------------------------------------------------------------------------------------------
+class Comm:
+    """A Cartesian process grid `dims` (MPI order: the last dimension varies fastest).  Every rank is a thread
+    interpreting its own copy of the script; `update_halo!`, `MPI.Allreduce` and `gather!` meet here."""
+
+    def __init__(self, dims):
+        self.dims = tuple(int(d) for d in dims)
+        self.coords = [(cx, cy, cz) for cx in range(self.dims[0]) for cy in range(self.dims[1]) for cz in range(self.dims[2])]
+        self.size = len(self.coords)
+        self.barrier = threading.Barrier(self.size)
+        self.slots = [None] * self.size
+
+    def rank_of(self, c):
+        return self.coords.index(tuple(c))
+
+    def exchange(self, rank, payload):
+        """All-gather of one Python object per rank."""
+        self.slots[rank] = payload
+        self.barrier.wait(timeout=120)
+        got = list(self.slots)
+        self.barrier.wait(timeout=120)
+        return got
+
+
+# ------------------------------------------------------------------------------------------------
 # the script: definitions + evaluator
 # ------------------------------------------------------------------------------------------------
 class JuliaScript:
@@ -519,6 +546,7 @@ class JuliaScript:
         self.grid = None            # (nx, ny, nz) after init_global_grid (single rank)
         self.launches = []          # (kernel name, ranges) in launch order, for inspection by tests
         self.frozen: dict = {}      # host names whose assignments in the text are ignored (nx = 255 -> test size)
+        self.comm, self.rank = None, 0   # set by run_ranks: several ranks of an ImplicitGlobalGrid
         self._builtins = self._make_builtins()
         self._scan_definitions()
 
@@ -626,14 +654,77 @@ class JuliaScript:
         raise JlError(f"no line matches {pattern!r} after line {after}")
 
     # -- builtins ----------------------------------------------------------------------------------
+    @property
+    def dims(self):
+        return self.comm.dims if self.comm else (1, 1, 1)
+
+    @property
+    def coords(self):
+        return self.comm.coords[self.rank] if self.comm else (0, 0, 0)
+
     def _n_g(self, d):
-        return 1 * (self.grid[d] - 2) + 2            # dims = 1: n_g = dims*(n-overlap)+overlap, overlap 2
+        return self.dims[d] * (self.grid[d] - 2) + 2            # nx_g() = dims*(nx-overlap)+overlap, overlap 2
 
     def _x_g(self, d, i, dx, A):
         n = self.grid[d]
         x0 = 0.5 * (n - A.shape[d]) * dx
-        res = (0 * (n - 2) + _raw(i) - 1) * dx + x0   # coords = 0 on the single rank
+        res = (self.coords[d] * (n - 2) + _raw(i) - 1) * dx + x0
         return _wrap(res, i)
+
+    def _update_halo(self, *fields):
+        """update_halo!(A...): dimension by dimension; plane ol / s-ol+1 (1-based, ol = overlap + size(A,d) - n)
+        goes to the lower / upper neighbour's last / first plane.  Nothing to do on a single rank."""
+        if self.comm is None:
+            return None
+        c = self.coords
+        for d in range(3):
+            if self.dims[d] == 1:
+                continue
+            sends = []
+            for A in fields:
+                sz = A.shape[d]
+                ol = 2 + (sz - self.grid[d])
+                if ol < 2:
+                    raise JlError(f"update_halo!: a field of size {A.shape} has no halo in dimension {d + 1}")
+                sends.append((np.take(A, ol - 1, axis=d).copy(), np.take(A, sz - ol, axis=d).copy()))
+            got = self.comm.exchange(self.rank, sends)
+            for k, A in enumerate(fields):
+                idx = [slice(None)] * 3
+                if c[d] > 0:
+                    lo = list(c)
+                    lo[d] -= 1
+                    idx[d] = 0
+                    A[tuple(idx)] = got[self.comm.rank_of(lo)][k][1]
+                if c[d] < self.dims[d] - 1:
+                    hi = list(c)
+                    hi[d] += 1
+                    idx[d] = A.shape[d] - 1
+                    A[tuple(idx)] = got[self.comm.rank_of(hi)][k][0]
+        return None
+
+    def _allreduce(self, x, op, comm):
+        if self.comm is None:
+            return x
+        vals = self.comm.exchange(self.rank, x)
+        if op != "max":
+            raise JlError(f"MPI.Allreduce with {op}")
+        return math.nan if any(math.isnan(v) for v in vals) else max(vals)
+
+    def _gather(self, A, A_global, **kw):
+        """gather!(A, A_global): block (cx,cy,cz) of the root's A_global is rank (cx,cy,cz)'s A."""
+        if self.comm is None:
+            if A_global.shape != A.shape:
+                raise JlError(f"gather!: size(A_global) {A_global.shape} != dims .* size(A) {A.shape}")
+            A_global[...] = A
+            return None
+        got = self.comm.exchange(self.rank, A.copy())
+        if self.rank == 0:
+            want = tuple(self.dims[d] * A.shape[d] for d in range(3))
+            if A_global.shape != want:
+                raise JlError(f"gather!: size(A_global) {A_global.shape} != dims .* size(A) {want}")
+            for r, c in enumerate(self.comm.coords):
+                A_global[tuple(slice(c[d] * A.shape[d], (c[d] + 1) * A.shape[d]) for d in range(3))] = got[r]
+        return None
 
     def builtin(self, name):
         if name not in self._builtins:
@@ -653,7 +744,8 @@ class JuliaScript:
             "isfinite": lambda x: math.isfinite(x),
             "push!": lambda lst, v: lst.append(v),
             "println": lambda *a: None, "print": lambda *a: None,
-            "update_halo!": lambda *a: None,
+            "update_halo!": self._update_halo,
+            "gather!": self._gather,
             "checkbounds": self._checkbounds,
             "init_global_grid": self._init_global_grid,
             "finalize_global_grid": lambda: None,
@@ -664,10 +756,10 @@ class JuliaScript:
             "LinRange": lambda a, b, n: lin_range(a, b, n),
             "Array": lambda x: np.array(x, order="F"),
             "zeros": lambda *s: np.zeros(s, dtype=np.float64, order="F"),
-            "Int": JlType("Int"), "Bool": JlType("Bool"), "Float64": JlType("Float64"),
+            "Int": JlType("Int"), "Bool": JlType("Bool"), "Float64": JlType("Float64"), "Float32": JlType("Float32"),
             "Inf": math.inf, "π": math.pi, "pi": math.pi,
             "Data": {"Array": lambda x: np.array(x, dtype=np.float64, order="F"), "Number": JlType("Float64")},
-            "MPI": {"Allreduce": lambda x, op, comm: x, "MAX": "max", "COMM_WORLD": "world"},
+            "MPI": {"Allreduce": self._allreduce, "MAX": "max", "COMM_WORLD": "world"},
             "nothing": None,
         }
 
@@ -697,7 +789,7 @@ class JuliaScript:
 
     def _init_global_grid(self, nx, ny, nz, **kw):
         self.grid = (nx, ny, nz)
-        return (0, (1, 1, 1))
+        return (self.rank, self.dims)
 
     # -- evaluation -----------------------------------------------------------------------------
     def lookup(self, name, env):
@@ -955,6 +1047,8 @@ class JuliaScript:
         base = self.ev(e[1], env, ps)
         if isinstance(base, JlType):
             return []                                  # Float64[]
+        if isinstance(base, (tuple, list)):
+            return base[self.ev(e[2][0], env, ps) - 1]
         idx, lanes = self._np_index(base, e[2], env, ps)
         val = base[idx]
         return L(val) if lanes else (float(val) if np.ndim(val) == 0 else val)

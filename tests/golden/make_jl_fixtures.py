@@ -11,7 +11,9 @@ Nothing of the C oracle or of the CUDA library takes part in producing these num
 Stored: for every kernel case of tests/jl_cases.py the SHA-256 of each output array (bit-exactness is the
 bar) and, for the small grids, the arrays themselves; for the whole runs the PT iteration counts, the err
 history, digests of the final Pr,Vx,Vy,Vz,C, the full arrays of the small runs, and -- for the M63 run, the
-size of test/test3D.jl -- the 64 samples `Pr[inds_x,inds_y,inds_z]` in that test's own layout.
+size of test/test3D.jl -- the 64 samples `Pr[inds_x,inds_y,inds_z]` in that test's own layout; for the
+multi-rank cases (one interpreter thread per ImplicitGlobalGrid rank, `update_halo!` at the text's call sites)
+the digests of all 17 local arrays of every rank.
 """
 import json
 import os
@@ -32,7 +34,7 @@ SMALL = 7 * 6 * 5 + 1
 
 def main():
     scripts = {"M": JuliaScript.from_file(jl_run.M_PATH), "G": JuliaScript.from_file(jl_run.G_PATH)}
-    out, meta = {}, {"kernel": {}, "run": {}, "lines": {}}
+    out, meta = {}, {"kernel": {}, "run": {}, "lines": {}, "ranks": {}}
     for case in J.KERNEL_CASES:
         p, f = J.inputs_of(O, case)                         # O only supplies shapes and the parameter block
         J.run_interp(scripts[case[1]], case, p, f)
@@ -57,6 +59,11 @@ def main():
             pr_v = fields["Pr"][1:-1, 1:-1, 1:-1]
             out["run/M63/Pr_samples"] = pr_v[np.ix_(ix, iy, iz)]
         print(rid, iters)
+    for case in J.RANK_CASES:
+        res = J.run_ranks_interp(jl_run, case)
+        meta["ranks"][case[0]] = [{"iters": iters, "errs": errs, "digest": {n: J.digest(f[n]) for n in J.RANK_FIELDS}}
+                                  for f, iters, errs in res]
+        print(case[0], case[4], res[0][1])
     out["meta"] = np.array(json.dumps(meta, ensure_ascii=False))
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes;", len(J.KERNEL_CASES), "kernel cases,", len(J.RUN_CASES), "runs")

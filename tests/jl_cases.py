@@ -48,6 +48,18 @@ RUN_CASES = [
     ("M40rot", "M", 40, 3, {"β": 0.3, "a_lx": 0.1, "ox_lx": -0.2}, {"beta": 0.3, "a_lx": 0.1, "ox_lx": -0.2}),
 ]
 RUN_FIELDS = ("Pr", "Vx", "Vy", "Vz", "C")
+
+# Several ranks of ImplicitGlobalGrid: (id, local nx, ny, nz, dims, nt, literals of the text, kwargs
+# of oracle.VirtualRanks).  The script's own rule keeps lz fixed while nz_g grows, which makes the grid anisotropic and
+# the PT loop (dτ from max(dx,dy,dz)) diverge: the domain lengths are edited so that dx = dy = dz, as for the weak-scaling runs.
+RANK_CASES = [
+    ("z2", 24, 15, 15, (1, 1, 2), 2, {"nz": 15, "lz_lx": 28 / 24}, {"lz": 28 / 24}),
+    ("z3", 24, 15, 15, (1, 1, 3), 2, {"nz": 15, "lz_lx": 41 / 24}, {"lz": 41 / 24}),
+    ("x2", 24, 15, 15, (2, 1, 1), 1, {}, {}),
+    ("y2z2", 24, 15, 15, (1, 2, 2), 1, {"ny": 15, "nz": 15, "ly_lx": 28 / 24, "lz_lx": 28 / 24}, {"ly": 28 / 24, "lz": 28 / 24}),
+]
+RANK_FIELDS = ("Pr", "dPrdtau", "C", "C_o", "Vx", "Vy", "Vz", "Vx_o", "Vy_o", "Vz_o", "divV", "txx", "tyy", "tzz", "txy", "txz", "tyz")
+JL_NAME = {"dPrdtau": "dPrdτ", "divV": "∇V", "txx": "τxx", "tyy": "τyy", "tzz": "τzz", "txy": "τxy", "txz": "τxz", "tyz": "τyz"}
 FULL_ARRAYS = {"M31", "G20"}      # the other runs are stored as digests + the test3D.jl samples
 
 
@@ -151,3 +163,17 @@ def run_case_oracle(O, rc):
     p = O.params_M(nx, **lit) if variant == "M" else O.params_G(nx, **lit)
     f, iters, errs = O.run(p, nt)
     return {n: f[n] for n in RUN_FIELDS}, iters, errs, p
+
+
+def run_ranks_interp(jl_run, case):
+    rid, nx, ny, nz, dims, nt, text_lit, _ = case
+    res = jl_run.run_M_ranks(nx, nt, dims, literals=text_lit)
+    return [({n: env[JL_NAME.get(n, n)] for n in RANK_FIELDS}, iters, errs) for env, iters, errs in res]
+
+
+def run_ranks_oracle(O, case):
+    rid, nx, ny, nz, dims, nt, _, kw = case
+    V = O.VirtualRanks(nx, ny, nz, dims, **kw)
+    for _ in range(nt):
+        V.step()
+    return [({n: f[n] for n in RANK_FIELDS}, V.iters, V.errs) for f in V.f]

@@ -88,7 +88,50 @@ def test_test3D_samples_of_the_text_run(O, fx):
     assert not np.allclose(got, np.array(t3["Pr_ref"]).transpose(2, 1, 0), rtol=t3["rtol"], atol=0.0)
 
 
+@pytest.mark.parametrize("case", J.RANK_CASES, ids=lambda c: c[0])
+def test_igg_emulation_equals_the_text_on_several_ranks(O, fx, case):
+    """the oracle's ImplicitGlobalGrid emulation (VirtualRanks -- the truth of every multi-GPU
+    test) against the script's text interpreted by one thread per rank, `update_halo!` exchanging planes at the
+    text's ten call sites and `max_g` reducing over the ranks: all 17 local arrays of every rank bit for bit, for
+    z-slabs (the product's decomposition) and for x / y-z splits (halo order x -> y -> z, corners)."""
+    z, meta = fx
+    got = run = J.run_ranks_oracle(O, case)
+    want = meta["ranks"][case[0]]
+    assert len(got) == len(want) == int(np.prod(case[4]))
+    for r, ((f, iters, errs), w) in enumerate(zip(run, want)):
+        assert iters == w["iters"] and errs == w["errs"]
+        for n in J.RANK_FIELDS:
+            assert J.digest(f[n]) == w["digest"][n], f"{case[0]} rank {r}: {n}"
+
+
 # ---- the fixtures re-derived from the text (build container only) -------------------------------------
+@live
+@pytest.mark.parametrize("case", J.RANK_CASES, ids=lambda c: c[0])
+def test_fixtures_are_what_the_text_computes_ranks(fx, case):
+    z, meta = fx
+    for (f, iters, errs), w in zip(J.run_ranks_interp(jl_run, case), meta["ranks"][case[0]]):
+        assert iters == w["iters"] and errs == w["errs"]
+        assert {n: J.digest(f[n]) for n in J.RANK_FIELDS} == w["digest"]
+
+
+@live
+def test_the_shipped_multi_rank_geometry_diverges_in_the_text_too():
+    """With its own rule (lz fixed, nz_g growing with the ranks: dz != dx) the script's PT loop diverges on two
+    ranks at this size and `floor(Int, .)` in backtrack! throws -- in the text as in Julia.  Recorded, not a gate."""
+    with pytest.raises(RuntimeError, match="InexactError"):
+        jl_run.run_M_ranks(24, 2, (1, 1, 2))
+
+
+@live
+def test_return_value_of_run_navierstokes3D():
+    """M:375-403 + M:528-535 executed as well: the five returned arrays are the interiors (what test3D.jl:6 receives)."""
+    env, iters, errs, info = jl_run.run_M(31, 2, returns=True)
+    assert info["out_alloc"] == (375, 403) and info["ret"] == (528, 532)
+    for n in ("C", "Pr", "Vx", "Vy", "Vz"):
+        assert np.array_equal(env[n + "_v"], env[n][1:-1, 1:-1, 1:-1])
+    assert env["Vx_v"].shape == (30, 17, 17) and env["Pr_v"].shape == (29, 17, 17)
+
+
 @pytest.fixture(scope="module")
 def scripts():
     return {"M": JuliaScript.from_file(jl_run.M_PATH), "G": JuliaScript.from_file(jl_run.G_PATH)}
