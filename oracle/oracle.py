@@ -2,9 +2,11 @@
 
 TEST INFRASTRUCTURE ONLY.  Imported by tests/, by ``__graft_entry__.smoke()`` and by the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` -- never by the product package
-``navierstokes3d_b200``.  PARITY UNPINNED by the reference's own tests (see the header of
-ns3d_oracle.c): the reference is Julia + un-vendored ParallelStencil/ImplicitGlobalGrid and
-cannot run in the build container.
+``navierstokes3d_b200``.  PARITY UNPINNED by a run of the reference (Julia + un-vendored
+ParallelStencil/ImplicitGlobalGrid cannot run in the build container; see the header of
+ns3d_oracle.c) and pinned to the reference's SOURCE TEXT instead: ``jl_interp.py`` /
+``jl_run.py`` execute the scripts' own text, and this oracle agrees with that bit for bit
+(tests/test_jl_reference.py).
 
 Everything host-side that the reference scripts do around the kernels is restated here
 literally as well, so that oracle runs need nothing from the product package:
