@@ -58,6 +58,8 @@ function Ctx(device::Integer=0; mode=FAST)
     finalizer(x -> ccall((:ns3d_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), c)
     return c
 end
+"Positional form: what `@init_ns3d(device, mode)` expands to."
+Ctx(device::Integer, mode::Integer) = Ctx(device; mode=mode)
 set_mode!(c::Ctx, m) = check(c, ccall((:ns3d_set_mode, LIB), Cint, (Ptr{Cvoid}, Cint), c.h, m))
 
 "`@zeros(nx,ny,nz)` (M:343-360)"

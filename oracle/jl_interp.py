@@ -44,7 +44,7 @@ import numpy as np
 # tokenizer
 # ------------------------------------------------------------------------------------------------
 _OPS3 = ["...", "===", "!=="]
-_OPS2 = [".=", ".*", "./", ".+", ".-", "==", "!=", "<=", ">=", "&&", "||", "+=", "-=", "*=", "/=", "=>", "::", "->"]
+_OPS2 = ["<:", ".=", ".*", "./", ".+", ".-", "==", "!=", "<=", ">=", "&&", "||", "+=", "-=", "*=", "/=", "=>", "::", "->"]
 _BLOCK_OPEN = {"function", "macro", "if", "for", "while", "begin", "let", "struct", "try", "quote", "module", "do"}
 
 
@@ -90,12 +90,13 @@ def _skip_string(s: str, i: int) -> int:
             j += 1
 
 
-def tokenize(s: str) -> list:
+def tokenize(s: str, cont_ops=()) -> list:
+    """`cont_ops`: operators after which a line break does not end the statement (`a =\n b`, `f(x),\n g(y)`)."""
     toks, i, line, depth, n = [], 0, 1, 0, len(s)
     while i < n:
         c = s[i]
         if c == "\n":
-            if depth == 0:
+            if depth == 0 and not (toks and toks[-1].kind == "op" and toks[-1].val in cont_ops):
                 toks.append(Tok("nl", "\n", i, i + 1, line))
             line += 1
             i += 1
@@ -537,10 +538,12 @@ class Comm:
 # ------------------------------------------------------------------------------------------------
 class JuliaScript:
     """One reference script: its definitions parsed from the text, host statements runnable by line range."""
+    parser_cls = Parser
+    cont_ops = ()
 
     def __init__(self, text: str, name: str = "script"):
         self.text, self.name = text, name
-        self.toks = tokenize(text)
+        self.toks = tokenize(text, self.cont_ops)
         self.defs: dict[str, Def] = {}
         self.macros: dict[str, tuple] = {}
         self.grid = None            # (nx, ny, nz) after init_global_grid (single rank)
@@ -578,7 +581,7 @@ class JuliaScript:
             ts = self.toks[a:b]
             vals = [t.val for t in ts]
             if ts[0].kind == "id" and ts[0].val == "macro":
-                p = Parser(ts[1:] + [Tok("eof", None, 0, 0, ts[-1].line)])
+                p = self.parser_cls(ts[1:] + [Tok("eof", None, 0, 0, ts[-1].line)])
                 name = p.cur.val
                 p.i += 1
                 p.call_args()
@@ -599,7 +602,7 @@ class JuliaScript:
                     kind = "ps_kernel"
                 elif deco and deco[0].kind == "macro" and deco[0].val == "parallel_indices":
                     kind, indices = "pi_kernel", [t.val for t in deco[1:] if t.kind == "id"]
-                p = Parser(ts[f + 1:] + [Tok("eof", None, 0, 0, ts[-1].line)])
+                p = self.parser_cls(ts[f + 1:] + [Tok("eof", None, 0, 0, ts[-1].line)])
                 name = p.cur.val
                 p.i += 1
                 if any(t.kind == "op" and t.val == ";" for t in ts[f + 2:f + 4]):
@@ -615,7 +618,7 @@ class JuliaScript:
             # short form  [@inline] name(args) = expr
             k = 1 if ts[0].kind == "macro" and ts[0].val == "inline" else 0
             if len(ts) > k + 3 and ts[k].kind == "id" and ts[k + 1].val == "(" and ts[k + 1].start == ts[k].end:
-                p = Parser(ts[k:] + [Tok("eof", None, 0, 0, ts[-1].line)])
+                p = self.parser_cls(ts[k:] + [Tok("eof", None, 0, 0, ts[-1].line)])
                 name = p.cur.val
                 p.i += 1
                 try:
@@ -635,7 +638,7 @@ class JuliaScript:
         for _ in range(close_blocks):
             ts += [Tok("nl", "\n", 0, 0, line), Tok("id", "end", 0, 0, line)]
         ts += [Tok("nl", "\n", 0, 0, line), Tok("eof", None, 0, 0, line)]
-        p = Parser(ts)
+        p = self.parser_cls(ts)
         body = p.block()
         if p.cur.kind != "eof":
             raise ParseError(f"unbalanced block in lines {first}-{last}: {p.cur!r}")
