@@ -43,6 +43,7 @@ class ShimParser(Parser):
                 self.i += 1
                 continue
             p = {"name": None, "type": None, "default": None, "vararg": False, "kw": kw}
+            at = self.i
             if self.cur.kind == "id":
                 p["name"] = self.cur.val
                 self.i += 1
@@ -58,6 +59,8 @@ class ShimParser(Parser):
             params.append(p)
             if self.is_op(","):
                 self.i += 1
+            if self.i == at:
+                raise ParseError(f"not a parameter list (line {self.cur.line})")
         self.eat(")")
         self.in_index = save
         if self.is_kw("where"):
@@ -997,3 +1000,69 @@ def run_gpu_b200(lib, shim_path, script_path, nx, nt, use_fused=True, mode=0):
                   for k, j in (("Pr", "Pr"), ("Vx", "Vx"), ("Vy", "Vy"), ("Vz", "Vz"), ("C", "C"))}
     _finalize(shim, scr)
     return fields, iters, errs, (shim, scr)
+
+
+class SingleRankMPI:
+    """Stand-in for the MPI.jl module on one rank (`import MPI` of scripts/NavierStokes3D_b200.jl)."""
+    COMM_WORLD = "COMM_WORLD"
+
+    def __init__(self):
+        self.calls = []
+
+    def Initialized(self):
+        return True
+
+    def Init(self):
+        self.calls.append("Init")
+
+    def Comm_rank(self, comm):
+        return 0
+
+    def Comm_size(self, comm):
+        return 1
+
+    def Bcast_b(self, buf, root, comm):
+        self.calls.append("Bcast!")
+        return buf
+
+    def Finalize(self):
+        self.calls.append("Finalize")
+
+
+def run_multi_b200(lib, shim_path, script_path, nx, nt, use_fused=True, mode=0):
+    """scripts/NavierStokes3D_b200.jl on one rank: the body of `run_navierstokes3D` from its first line to the end of the
+    time loop (the `do_save` branch is not executed) and the return statement; `Ctx(...; mode=FAST)` is followed by
+    `set_mode!(ctx, mode)`.  Returns (the five returned interiors C, Pr, Vx, Vy, Vz; local fields; iterations; scripts)."""
+    shim = load_shim(shim_path, lib)
+    scr = load_script(script_path, shim)
+    scr.frozen = {"USE_FUSED_PT": use_fused}
+    mpi = SingleRankMPI()
+    scr.globals["MPI"] = mpi
+    with np.errstate(all="ignore"):
+        for n, ln in enumerate(scr.text.split("\n"), 1):
+            if ln.startswith("const "):
+                scr.run_lines(n, n, scr.globals)
+        head = scr.find_line(r"function run_navierstokes3D\(")
+        first = scr.find_line(r"^\s*for it = 1:nt", head)
+        last = scr.find_line(r"^\s*if do_save && it % 10 == 0", first) - 1
+        ret_first = scr.find_line(r"^\s*np_c = fill", last)
+        ret_last = scr.find_line(r"^end", ret_first) - 1
+        env = {"do_vis": False, "do_save": False, "do_print": False, "nx": nx, "nt": nt}
+        n_ctx = scr.find_line(r"^\s*ctx = Ctx\(", head)
+        scr.run_lines(head + 1, n_ctx, env)
+        scr.apply(shim.lookup("set_mode!", {}), [env["ctx"], mode], {})
+        scr.run_lines(n_ctx + 1, first - 1, env)
+        body = scr.parse_lines(first, last, close_blocks=1)
+        iters = []
+        for it in range(1, nt + 1):
+            env["it"] = it
+            scr.exec_block(body[0][3], env, host=True)
+            iters.append(int(env["iters"] if use_fused else env["iter"]))
+        local = {k: scr.apply(shim.lookup("to_host", {}), [env["ctx"], env[k]], {}) for k in ("Pr", "Vx", "Vy", "Vz", "C")}
+        try:
+            scr.run_lines(ret_first, ret_last, env)
+            returned = None
+        except _Return as r:
+            returned = r.val
+    _finalize(shim, scr)
+    return returned, local, iters, (shim, scr, mpi)
