@@ -12,8 +12,12 @@
 #     `max_g(abs, A)`, `finalize_global_grid()` -- see scripts/NavierStokes3D_b200.jl and
 #     scripts/NavierStokes3D_gpu_b200.jl.
 #
-# NOT EXECUTED in the build container (Julia is not installed there); the same C ABI is exercised
-# end to end by the Python ctypes binding navierstokes3d_b200/native.py, which mirrors this file
+# NOT EXECUTED BY JULIA in the build container (Julia is not installed there).  What runs there instead:
+# oracle/jl_shim.py interprets this file's text -- structs, typed methods, `Ref`/`Ptr`, every `ccall` converted by
+# its declared Julia types and sent into libns3d.so -- together with the two run scripts; every ccall site below
+# is reached and the scripts reproduce the reference's results bit for bit (tests/test_julia_shim_exec.py, CPU
+# emulation and B200), and tests/test_julia_shim_static.py checks every ccall against include/ns3d.h.  The same
+# C ABI is also exercised by the Python ctypes binding navierstokes3d_b200/native.py, which mirrors this file
 # call for call.  Every `ccall` below passes its arguments one by one (`ccall` takes no splats).
 module NS3DNative
 

@@ -5,7 +5,9 @@
 #
 #   mpirun -np N julia -O3 scripts/NavierStokes3D_b200.jl        (one rank per GPU, z-slabs)
 #
-# NOT EXECUTED in the build container (no Julia there).  The executable twin of this file is
+# NOT EXECUTED BY JULIA in the build container (no Julia there); its text is executed there by the interpreter of
+# oracle/jl_shim.py through julia/NS3DNative.jl into libns3d.so (tests/test_julia_shim_exec.py: bit-equal to the
+# reference script's own text, fused and level-1 loop, returned interiors).  The Python twin of this file is
 # navierstokes3d_b200/driver.py (`run_navierstokes3D`), which makes exactly these calls through
 # the same C ABI and is what the parity tests drive.
 include(joinpath(@__DIR__, "..", "julia", "NS3DNative.jl"))

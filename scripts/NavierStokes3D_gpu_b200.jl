@@ -12,7 +12,9 @@
 #
 #   julia -O3 scripts/NavierStokes3D_gpu_b200.jl
 #
-# NOT EXECUTED in the build container (no Julia there).  The executable twin of this file is
+# NOT EXECUTED BY JULIA in the build container (no Julia there); its text is executed there by the interpreter of
+# oracle/jl_shim.py through julia/NS3DNative.jl into libns3d.so (tests/test_julia_shim_exec.py: bit-equal to the
+# reference script's own text with USE_FUSED = true and false).  The Python twin of this file is
 # navierstokes3d_b200/driver.py (`runme`), which makes exactly these calls through the same C ABI and is what the
 # parity tests drive (tests/test_gpu_solver.py::test_config_B_whole_time_steps_vs_oracle runs this configuration
 # for two time steps, bit-exact against the CPU oracle).
