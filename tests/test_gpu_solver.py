@@ -332,3 +332,28 @@ def test_config_B_whole_time_steps_vs_oracle(O, ns):
                 scale = vscale if name[0] == "V" else None
                 assert rel_inf(sim.host(name), f[name], scale) <= TOL_FASTEST, (mode, name)
         c.close()
+
+
+def test_config_B_whole_time_steps_vs_the_shipped_scripts_text(ns):
+    """The benchmark configuration against the reference's own TEXT: `runme()` of scripts/NavierStokes3D_gpu.jl as
+    shipped, executed line by line by oracle/jl_interp.py (tests/golden/make_jl_config_B.py; record under
+    tests/golden/jl_reference_config_B.json -- no oracle, no library involved).  PARITY and FAST (the bench default):
+    identical PT iteration counts, every residual of every check and the five fields bit for bit after each recorded
+    time step."""
+    import hashlib
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jl_reference_config_B.json")) as fh:
+        rec = json.load(fh)
+    assert rec["grid"] == [255, 153, 153] and rec["steps"]
+    for mode in ("PARITY", "FAST"):
+        c = ns.Context(0, getattr(ns, mode))
+        sim = ns.Simulation(ns.setup_gpu(255), c)
+        for s in rec["steps"]:
+            it, hist = sim.step()
+            assert it == s["iters"], (mode, s["it"], it)
+            assert hist == s["errs"], (mode, s["it"])
+            for name in ("Pr", "Vx", "Vy", "Vz", "C"):
+                got = hashlib.sha256(np.asfortranarray(sim.host(name)).tobytes(order="F")).hexdigest()
+                assert got == s["digest"][name], f"{mode}: step {s['it']}: {name} differs from the script's text"
+        c.close()
+

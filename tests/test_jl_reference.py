@@ -335,3 +335,27 @@ def test_an_edited_text_changes_the_bits(O, fx, mut):
     J.run_interp(s, case, p, f)
     changed = [n for n in J.OUTPUTS[case[0]] if J.digest(f[n]) != meta["kernel"][J.case_id(case)][n]]
     assert changed, "the edit went unnoticed"
+
+
+# ---- the benchmark configuration itself (BASELINE configs[1]) ---------------------------------------------------
+def config_B_record():
+    with open(os.path.join(GOLD, "jl_reference_config_B.json")) as fh:
+        return json.load(fh)
+
+
+def test_oracle_equals_the_shipped_script_at_config_B(O):
+    """`runme()` of scripts/NavierStokes3D_gpu.jl exactly as shipped (255x153x153; only `nt` replaced), first time step,
+    executed from its text by tests/golden/make_jl_config_B.py (half an hour of numpy): 3 952 PT iterations, 26 residual
+    checks.  The C oracle reproduces the count, every residual and all five fields bit for bit (about half a minute)."""
+    rec = config_B_record()
+    assert rec["grid"] == [255, 153, 153]
+    O.lib().ns3d_oracle_set_num_threads(len(os.sched_getaffinity(0)))
+    p = O.params_G(255)
+    for jl, attr in (("dx", "dx"), ("dt", "dt"), ("dτ", "dtau"), ("damp", "damp"), ("niter", "niter"), ("nchk", "nchk"), ("g", "g"), ("ox", "ox")):
+        assert getattr(p, attr) == rec["params"][jl], jl
+    f = O.initial_fields(p)
+    it, hist = O.step(p, f)
+    s = rec["steps"][0]
+    assert it == s["iters"] and hist == s["errs"]
+    for n in J.RUN_FIELDS:
+        assert J.digest(f[n]) == s["digest"][n], n
