@@ -2,7 +2,10 @@
 EXACTLY AS SHIPPED (nx = 255 -> 255x153x153, g = 9.81, eps = 1e-3, nchk = 152, G:15-61) executed by
 oracle/jl_interp.py for the first NT time steps (only the literal `nt = 10000`, G:51, is replaced).
 
-    python tests/golden/make_jl_config_B.py [NT]     (needs /root/reference; about half an hour per time step)
+    python tests/golden/make_jl_config_B.py [NT] [G|M]   (needs /root/reference; about half an hour per time step of G)
+
+With `M`: `run_navierstokes3D(; nx=255, nt=NT)` of scripts/NavierStokes3D_multi_gpu.jl on one rank (the same grid; the
+variant the weak-scaling runs use), written to tests/golden/jl_reference_config_B_M.json.
 
 Writes tests/golden/jl_reference_config_B.json after every step: PT iteration count, every residual of every
 check, SHA-256 of Pr, Vx, Vy, Vz, C (full local arrays, column-major bytes) and a few sample values.
@@ -26,7 +29,13 @@ SAMPLES = [(127, 76, 76), (51, 76, 76), (60, 70, 10), (200, 100, 140), (1, 1, 1)
 
 def main():
     nt = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-    rec = {"script": "scripts/NavierStokes3D_gpu.jl", "what": "runme() as shipped, first time steps", "steps": []}
+    variant = sys.argv[2] if len(sys.argv) > 2 else "G"
+    global OUT
+    if variant == "M":
+        OUT = OUT.replace("config_B.json", "config_B_M.json")
+    rec = {"script": "scripts/NavierStokes3D_gpu.jl" if variant == "G" else "scripts/NavierStokes3D_multi_gpu.jl",
+           "what": "runme() as shipped, first time steps" if variant == "G" else "run_navierstokes3D(nx=255) on one rank, first time steps",
+           "steps": []}
     t0 = time.time()
 
     def on_step(it, env):
@@ -42,6 +51,9 @@ def main():
             json.dump(rec, fh, indent=1, ensure_ascii=False)
         print("step", it, "iterations", int(env["iter"]), "after", round(time.time() - t0), "s", flush=True)
 
+    if variant == "M":
+        jl_run.run_M(255, nt, on_step=on_step)
+        return
     # nx stays the script's literal 255 (G:44): freeze only nt
     from oracle.jl_interp import JuliaScript
     s = JuliaScript.from_file(jl_run.G_PATH)

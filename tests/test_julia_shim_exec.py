@@ -221,9 +221,16 @@ def test_swapped_ccall_argument_is_caught(fx):
     check_swapped_argument_is_caught(emu_lib(), fx)
 
 
-def test_zz_every_ccall_site_was_reached():
-    """Runs last in this file: the union of the C symbols reached above is the set the shim's text binds."""
+def test_zz_every_ccall_site_was_reached(fx, O):
+    """The union of the C symbols reached by the checks above is the set the shim's text binds (when this test runs
+    alone the checks are executed here first)."""
     bound = {c[1] for c in ccalls(SHIM)}
+    if bound - REACHED:
+        lib = emu_lib()
+        check_gpu_script(lib, fx, False)
+        check_multi_script(lib, fx, True)
+        check_level2(lib, fx)
+        check_surface(lib, O)
     assert bound - REACHED == set(), f"ccall sites never executed: {sorted(bound - REACHED)}"
 
 
