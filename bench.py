@@ -28,6 +28,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+TEXT_RECORD = os.path.join(ROOT, "tests", "golden", "jl_reference_config_B.json")   # see the warm-up loop of main()
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
@@ -407,8 +408,34 @@ def main():
         return pt_only(args, ns, ctx, s, stream, rank, world, barrier)
 
     # ---- device-resident timing: W warm-up steps, then exactly K steps -------------------------
-    for _ in range(args.warmup):
-        sim.step()
+    # The warm-up steps double as a check against the REFERENCE'S OWN TEXT: tests/golden/jl_reference_config_B.json holds
+    # what `runme()` of scripts/NavierStokes3D_gpu.jl as shipped yields for its first time steps when oracle/jl_interp.py
+    # executes the script line by line (iteration counts, every residual, SHA-256 of the fields).  Untimed.
+    text_rec, text_check = None, None
+    if world == 1 and args.workload == "B" and variant == "G" and not args.fixed_iters and not args.no_parity_check:
+        try:
+            with open(TEXT_RECORD) as fh:
+                text_rec = json.load(fh)
+            if text_rec.get("grid") != [s.nx, s.ny, s.nz]:
+                text_rec = None
+        except OSError:
+            text_rec = None
+    for w in range(args.warmup):
+        it_w, hist_w = sim.step()
+        if text_rec is not None and w < len(text_rec["steps"]):
+            ref_w = text_rec["steps"][w]
+            if text_check is None:
+                text_check = {"against": "scripts/NavierStokes3D_gpu.jl as shipped, executed from its text (tests/golden/make_jl_config_B.py)",
+                              "steps_checked": 0, "pt_iters_identical": True, "residuals_identical": True, "fields_bit_identical": None}
+            text_check["steps_checked"] = w + 1
+            text_check["pt_iters_identical"] &= (it_w == ref_w["iters"])
+            if args.mode != "FASTEST":
+                text_check["residuals_identical"] &= (list(hist_w) == ref_w["errs"])
+                if w + 1 == min(args.warmup, len(text_rec["steps"])):
+                    import hashlib
+                    text_check["fields_bit_identical"] = all(
+                        hashlib.sha256(np.asfortranarray(sim.host(k)).tobytes(order="F")).hexdigest() == ref_w["digest"][k]
+                        for k in ("Pr", "Vx", "Vy", "Vz", "C"))
     snapshot = {k: sim.host(k) for k in STATE}   # for the e2e and parity legs: the same K steps again
     sampler = ClockSampler(local)
     sampler.start()
@@ -591,6 +618,8 @@ def main():
         }
         if parity:
             line["parity_check"] = parity
+            if text_check is not None:
+                parity["reference_text"] = text_check
         if e2e:
             line["e2e"] = e2e
         line.update(extras)
@@ -600,6 +629,9 @@ def main():
         print(json.dumps(line))
     if world > 1:
         rig.dist.destroy_process_group()
+    if text_check is not None and not (text_check["pt_iters_identical"] and text_check["residuals_identical"]
+                                       and text_check["fields_bit_identical"] in (True, None)):
+        parity_ok = False
     if not parity_ok:
         sys.stderr.write("bench.py: PARITY CHECK FAILED (iteration counts differ or a field is outside the tolerance)\n")
         sys.exit(3)

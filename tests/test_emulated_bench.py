@@ -55,3 +55,43 @@ def test_native_arm_prints_the_contract_line(monkeypatch, capsys):
     assert line["parity_check"]["pt_iters_identical"] and line["parity_check"]["within_tolerance"]
     assert line["parity_check"]["max_rel_diff"]["Pr"] == 0.0     # FAST equals PARITY in every value seen so far
     assert len(line["pt_iters_per_step"]) == 1 and line["pt_iters_per_step"][0] > 18
+
+
+def test_warm_up_steps_are_checked_against_the_reference_text(monkeypatch, capsys, tmp_path):
+    """Workload B's warm-up steps are compared with the record of the shipped script's text
+    (tests/golden/jl_reference_config_B.json).  Here: a CPU-sized stand-in for B (script G at nx = 20) and the
+    record built from the G20 run of tests/golden/jl_reference_fixtures.npz; then a falsified record must fail the run."""
+    import os
+
+    import numpy as np
+    import torch
+
+    import bench
+    z = np.load(os.path.join(bench.ROOT, "tests", "golden", "jl_reference_fixtures.npz"))
+    m = json.loads(str(z["meta"]))["run"]["G20"]
+    # the fixture keeps the final state only: a one-step record would need step 1's digest -> check counts and residuals
+    # of both steps and the digest after the second (= the fixture's final state)
+    rec = {"grid": [20, 12, 12], "steps": [{"it": 1, "iters": m["iters"][0], "errs": m["errs"][0], "digest": {}},
+                                           {"it": 2, "iters": m["iters"][1], "errs": m["errs"][1], "digest": m["digest"]}]}
+    path = tmp_path / "record.json"
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.cuda, "ExternalStream", _Stream)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self.clone())
+    monkeypatch.setitem(bench.WORKLOADS, "B", ("G", 20, None, None))
+    monkeypatch.setattr(bench, "TEXT_RECORD", str(path))
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "1", "--warmup", "2", "--no-cpu-baseline", "--no-extras"])
+    path.write_text(json.dumps(rec))
+    with emu.use_emulated_library():
+        bench.main()
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    t = line["parity_check"]["reference_text"]
+    assert t == {"against": t["against"], "steps_checked": 2, "pt_iters_identical": True, "residuals_identical": True,
+                 "fields_bit_identical": True}
+    rec["steps"][1]["errs"][-1] *= 1.0000000001
+    path.write_text(json.dumps(rec))
+    with emu.use_emulated_library():
+        with pytest.raises(SystemExit) as e:
+            bench.main()
+    assert e.value.code == 3
