@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out/r2c24 && cd "$(dirname "$0")/../.." || exit 1
+O=gpurun_out/r2c24
+run() { timeout 200 python bench.py --steps 4 --warmup 3 --no-e2e --no-extras --no-cpu-baseline --no-parity-check "$@" 2>/dev/null | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(sys.argv[1:], 'T_eff', round(d['value'],1), 'ms/step', round(d['ms_per_step'],2), 'us/pass', round(d['roofline']['us_per_launch'],2), 'share', round(d['roofline']['share_of_step'],3))" "$@"; }
+{
+run --opt ptv_bands=8
+run --opt ptv_bands=6
+run --opt ptv_bands=4
+run --opt ptv_bands=3
+run --opt ptv_bands=0
+run --opt ptv_bands=8 --opt graphs=0
+} 2>&1 | tee $O/bands_bench.log
+echo "elapsed ${SECONDS}s"
