@@ -19,10 +19,10 @@ import ctypes as C
 
 import numpy as np
 
-from .jl_interp import Def, JlError, JlType, JuliaScript, ParseError, Parser, Tok, _Break, _Return, _raw
+from .jl_interp import Def, JlError, JlType, JuliaScript, ParseError, Parser, Tok, _Break, _Return
 
 CONT_OPS = ("=", ",", "&&", "||", "+", "-", "*", "/", "?", "->", "==", ".=", "+=", "-=")
-_SKIP_STATEMENTS = ("export", "using", "import", "include")
+_SKIP_STATEMENTS = ("export", "using", "import", "include")    # top-level statements that define nothing
 
 
 # ------------------------------------------------------------------------------------------------
@@ -268,6 +268,9 @@ class ShimParser(Parser):
         if c.kind == "id" and c.val == "break":
             self.i += 1
             return ("breakexpr",)
+        if self.is_op("(") and self.peek().kind == "op" and self.peek().val == ")":
+            self.i += 2
+            return ("tuple", [])
         if self.is_op("["):
             # untyped comprehension with `in` generators, or a vector literal
             save_i = self.i
@@ -955,11 +958,6 @@ def load_script(path: str, shim: ShimScript) -> ShimScript:
 # ------------------------------------------------------------------------------------------------
 # the two re-pointed run scripts
 # ------------------------------------------------------------------------------------------------
-def _host(script: ShimScript, shim: ShimScript, arr):
-    """`Array(A)` of the look-alike surface / `to_host(ctx, A)`."""
-    return script.apply(shim.lookup("to_host", {}), [arr.ctx if hasattr(arr, "ctx") else script._ctx, arr], {})
-
-
 def _finalize(*scripts):
     for s in scripts:
         for f, obj in s.finalizers:

@@ -260,3 +260,61 @@ def test_level2_and_surface_through_the_shim_on_the_device(fx, O):
         if "NCCL" in str(e) or "nccl" in str(e):
             pytest.skip(f"no NCCL in this process: {e}")
         raise
+
+
+# ---- the interpreter's additional language features on snippets with known values (no library involved) ----------
+SRC_LANG = '''
+module Demo
+const A, B = Cint(3), 2.5
+const P = Ptr{Float64}
+struct Pt
+    x::Cdouble; y::Cdouble
+    tag::Cint
+end
+mutable struct Box
+    p::Pt
+    n::Int
+end
+Pt(x::Real) = Pt(x, x, 0)
+norm1(p::Pt) = abs(p.x) + abs(p.y)
+norm1(b::Box) = b.n * norm1(b.p)
+pick(a::Integer, b=10; scale=1) = (a + b) * scale
+pick(a::Pt, rest::Integer...) = length(rest)
+kind(::Type{T}) where {T<:Union{Float64,Float32}} = T == Float32 ? 1 : 0
+function total(xs::Vector{Float64}; start=0.0)
+    acc = start
+    for (i, x) in enumerate(xs)
+        acc += i * x
+        i == 3 && break
+    end
+    return acc, length(xs)
+end
+cell() = Ref{Cint}(7)
+end # module
+'''
+
+
+def test_language_features_of_the_shim_interpreter():
+    s = jl_shim.ShimScript(SRC_LANG)
+    s.finish_loading()
+    env = {}
+    snippet_src = ("p = Pt(1.5, -2.0, 4)\nq = Pt(3)\nb = Box(p, 2)\nn1 = norm1(p); n2 = norm1(b); n3 = norm1(q)\n"
+                   "k1 = pick(1); k2 = pick(1, 2); k3 = pick(1, 2; scale=3); k4 = pick(p, 1, 2, 3)\n"
+                   "t64 = kind(Float64); t32 = kind(Float32)\nacc, n = total([1.0, 2.0, 3.0, 4.0]; start=0.5)\n"
+                   "r = cell(); v0 = r[]; r[] = 9; v1 = r[]\nsq = map(x -> x * x, [1, 2, 3])\nd = 7 ÷ 2\n"
+                   "same = p.tag === 4 ? :yes : :no\nz = [i * 2 for i in 1:3]\nty = Cint[i for i in 1:2]\nconsts = (A, B)")
+    sn = jl_shim.ShimScript(snippet_src, imports=[s])
+    sn.run_lines(1, snippet_src.count("\n") + 1, env)
+    assert (env["n1"], env["n2"], env["n3"]) == (3.5, 7.0, 6.0)
+    assert (env["k1"], env["k2"], env["k3"], env["k4"]) == (11, 3, 9, 3)
+    assert (env["t64"], env["t32"]) == (0, 1)
+    assert env["acc"] == 0.5 + 1 * 1.0 + 2 * 2.0 + 3 * 3.0 and env["n"] == 4
+    assert (env["v0"], env["v1"]) == (7, 9) and env["sq"] == [1, 4, 9] and env["d"] == 3
+    assert env["same"] == ("sym", "yes") and env["z"] == [2, 4, 6] and env["consts"] == (3, 2.5)
+    assert env["ty"].dtype == np.int32 and list(env["ty"]) == [1, 2]
+    with pytest.raises(JlError, match="MethodError"):
+        sn2 = jl_shim.ShimScript("bad = norm1(1.0)", imports=[s])
+        sn2.run_lines(1, 1, {})
+    with pytest.raises(JlError, match="ccall without a library"):
+        sn3 = jl_shim.ShimScript('rc = ccall((:ns3d_version, LIB), Cstring, ())', imports=[s])
+        sn3.run_lines(1, 1, {"LIB": None})
