@@ -70,6 +70,10 @@ def run_ranks(world, grid, nt, lz, how="step", options=None):
     (2, (12, 9, 50), 12, 98 / 12, "pt_random", {}),
     (2, (12, 9, 50), 13, 98 / 12, "pt_random", {"ptv_bands": 3, "graphs": 0}),
     (2, (12, 9, 50), 2, 98 / 12, "step", {}),
+    # the two z-slab configurations at which the IGG emulation itself is pinned to the reference script's TEXT
+    # (tests/jl_cases.py RANK_CASES "z2", "z3"; tests/test_jl_reference.py): library == emulation == text
+    (2, (24, 15, 15), 2, 28 / 24, "step", {}),
+    (3, (24, 15, 15), 2, 41 / 24, "step", {}),
 ])
 def test_rank_processes_match_igg_emulation(world, grid, nt, lz, how, options):
     results = run_ranks(world, grid, nt, lz, how, options)
