@@ -1151,6 +1151,8 @@ class JuliaScript:
             vals = list(val) if len(targets) > 1 else [val]
         else:
             vals = [self.ev(v, env) for v in values]
+        if len(values) == 1 and len(vals) > len(targets) > 1:
+            vals = vals[:len(targets)]             # a, b = f()  takes the first two of a longer tuple
         if len(vals) != len(targets):
             raise JlError(f"line {line}: {len(targets)} targets, {len(vals)} values")
         for t, v in zip(targets, vals):

@@ -209,6 +209,30 @@ class ShimParser(Parser):
             else:
                 return a
 
+    def call_args(self):
+        self.eat("(")
+        save, self.in_index = self.in_index, 0
+        args, kwargs = [], {}
+        while not self.is_op(")"):
+            if self.is_op(";"):
+                self.i += 1
+                continue
+            if self.cur.kind == "id" and self.peek().kind == "op" and self.peek().val == "=":
+                name = self.cur.val
+                self.i += 2
+                kwargs[name] = self.expr()
+            else:
+                a = self.expr()
+                if self.is_op("..."):
+                    self.i += 1
+                    a = ("splat", a)
+                args.append(a)
+            if self.is_op(","):
+                self.i += 1
+        self.eat(")")
+        self.in_index = save
+        return args, kwargs
+
     def index_or_typed_comprehension(self, base):
         self.i += 1
         save = self.in_index
@@ -595,6 +619,24 @@ class ShimScript(JuliaScript):
             return obj[name]
         return getattr(obj, name.rstrip("!") + ("_b" if name.endswith("!") else ""))
 
+    def comprehension(self, e, env):
+        """Vectorised over the index box where every callee takes lane vectors; element by element otherwise
+        (e.g. `z_g(iz, dz, C)` of the shim dispatches on `iz::Integer`)."""
+        try:
+            return super().comprehension(e, env)
+        except JlError as exc:
+            if "MethodError" not in str(exc):
+                raise
+        gens = [(var, self.ev(r, env)) for var, r in e[2]]
+        shape = tuple(r[2] - r[1] + 1 for _, r in gens)
+        out = np.empty(shape, dtype=np.float64, order="F")
+        scope = dict(env)
+        for idx in np.ndindex(*shape):
+            for (var, r), i in zip(gens, idx):
+                scope[var] = r[1] + i
+            out[idx] = self.ev(e[1], scope)
+        return out
+
     def scalar_comprehension(self, e, env):
         base = self.ev(e[1], env) if e[1] is not None else None
         out = []
@@ -623,7 +665,10 @@ class ShimScript(JuliaScript):
         fn = self.ev(e[1], env, ps)
         args = []
         for x in e[2]:
-            args.append(self.ev(x, env, ps))
+            if x[0] == "splat":
+                args.extend(self.ev(x[1], env, ps))
+            else:
+                args.append(self.ev(x, env, ps))
         kwargs = {n: self.ev(x, env, ps) for n, x in e[3].items()}
         return self.apply(fn, args, kwargs, dotted=e[4])
 
@@ -736,7 +781,7 @@ class ShimScript(JuliaScript):
             T = self.structs[name]
             if len(args) == len(T.fields) and not kwargs:
                 return JStruct(T, list(args))
-        if name in self._builtins:
+        if name in ("size", "length", "Array") and name in self._builtins:     # Base functions the shim only EXTENDS
             return self._builtins[name](*args, **kwargs)
         sigs = [", ".join((p["name"] or "") + ("::…" if p["type"] else "") for p in d.sig) for d in self.methods.get(name, [])]
         raise JlError(f"MethodError: no method matching {name}({', '.join(self.describe(a) for a in args)}"
@@ -1064,3 +1109,43 @@ def run_multi_b200(lib, shim_path, script_path, nx, nt, use_fused=True, mode=0):
             returned = r.val
     _finalize(shim, scr)
     return returned, local, iters, (shim, scr, mpi)
+
+
+def run_multi_gpu_lookalike_b200(lib, shim_path, script_path, nx, nt, use_fused=True, mode=0):
+    """scripts/NavierStokes3D_multi_gpu_b200.jl (the M script's text on the look-alike surface) on one rank: the body of
+    `run_navierstokes3D` up to the end of the time loop, the local fields read back, then the gathers, `finalize_global_grid`
+    and the return statement.  Returns (returned interiors, local fields, iterations per step, err histories, scripts)."""
+    shim = load_shim(shim_path, lib)
+    scr = load_script(script_path, shim)
+    scr.frozen = {"USE_FUSED": use_fused}
+    mpi = SingleRankMPI()
+    scr.globals["MPI"] = mpi
+    with np.errstate(all="ignore"):
+        for n, ln in enumerate(scr.text.split("\n"), 1):
+            if ln.startswith("const "):
+                scr.run_lines(n, n, scr.globals)
+        head = scr.find_line(r"function run_navierstokes3D\(")
+        n_grid = scr.find_line(r"init_global_grid\(nx, ny, nz", head)
+        first = scr.find_line(r"^\s*for it = 1:nt", head)
+        last = scr.find_line(r"^\s*# gather the interiors", first) - 1
+        ret_last = scr.find_line(r"^\s*return C_v", last)
+        env = {"do_vis": False, "do_save": False, "do_print": False, "nx": nx, "nt": nt}
+        scr.run_lines(head + 1, n_grid, env)
+        ctx = shim.globals["DEFAULT"].v
+        scr.apply(shim.lookup("set_mode!", {}), [ctx, mode], {})
+        scr.run_lines(n_grid + 1, first - 1, env)
+        body = scr.parse_lines(first, last)
+        iters, errs = [], []
+        for it in range(1, nt + 1):
+            env["it"] = it
+            scr.exec_block(body[0][3], env, host=True)
+            iters.append(int(env["iters"] if use_fused else env["iter"]))
+            errs.append([float(e) for e in env["err_evo"]])
+        local = {k: scr.apply(shim.lookup("to_host", {}), [ctx, env[k]], {}) for k in ("Pr", "Vx", "Vy", "Vz", "C")}
+        try:
+            scr.run_lines(last + 1, ret_last, env)
+            returned = None
+        except _Return as r:
+            returned = r.val
+    _finalize(shim, scr)
+    return returned, local, iters, errs, (shim, scr, mpi)

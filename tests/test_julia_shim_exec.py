@@ -28,6 +28,7 @@ from tests.test_julia_shim_static import SHIM, ccalls
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G_B200 = os.path.join(ROOT, "scripts", "NavierStokes3D_gpu_b200.jl")
 M_B200 = os.path.join(ROOT, "scripts", "NavierStokes3D_b200.jl")
+M_LOOKALIKE = os.path.join(ROOT, "scripts", "NavierStokes3D_multi_gpu_b200.jl")
 REACHED = set()          # C symbols the shim's ccalls reached in this session (per library kind)
 
 
@@ -76,6 +77,25 @@ def check_multi_script(lib, fx, fused):
     assert len(ret) == 5                             # M:535: C_v, Pr_v, Vx_v, Vy_v, Vz_v
     for got, n in zip(ret, ("C", "Pr", "Vx", "Vy", "Vz")):
         assert np.array_equal(got, z[f"run/M31/{n}"][1:-1, 1:-1, 1:-1]), n
+    return shim
+
+
+def check_multi_lookalike_script(lib, fx, fused):
+    """scripts/NavierStokes3D_multi_gpu_b200.jl: the M script's own text on the look-alike surface (`init_global_grid`,
+    `update_halo!`, `max_g`, `gather!`, `finalize_global_grid` of the shim)."""
+    z, meta = fx
+    ret, f, iters, errs, (shim, scr, mpi) = jl_shim.run_multi_gpu_lookalike_b200(lib, SHIM, M_LOOKALIKE, 31, 3, use_fused=fused)
+    note(shim)
+    m = meta["run"]["M31"]
+    assert iters == m["iters"] and errs == m["errs"]
+    for n in J.RUN_FIELDS:
+        assert J.digest(f[n]) == m["digest"][n], n
+    assert mpi.calls == ["Bcast!", "Finalize"]
+    for got, n in zip(ret, ("C", "Pr", "Vx", "Vy", "Vz")):
+        assert np.array_equal(got, z[f"run/M31/{n}"][1:-1, 1:-1, 1:-1]), n
+    n_halo = sum(1 for s, _ in shim.ccalls if s == "ns3d_update_halo")
+    if not fused:       # the text's ten call sites: 2 at start-up, 5 + 3 per PT iteration in every time step
+        assert n_halo == 2 + 3 * 5 + 3 * sum(m["iters"])
     return shim
 
 
@@ -209,6 +229,11 @@ def test_multi_gpu_script_through_the_shim(fx, fused):
     check_multi_script(emu_lib(), fx, fused)
 
 
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "level1"])
+def test_multi_gpu_script_with_its_text_kept_through_the_shim(fx, fused):
+    check_multi_lookalike_script(emu_lib(), fx, fused)
+
+
 def test_level2_structs_through_the_shim(fx):
     check_level2(emu_lib(), fx)
 
@@ -245,6 +270,16 @@ def test_gpu_script_through_the_shim_on_the_device(fx, fused):
 def test_multi_gpu_script_through_the_shim_on_the_device(fx):
     try:
         check_multi_script(gpu_lib(), fx, True)
+    except JlError as e:
+        if "NCCL" in str(e) or "nccl" in str(e):
+            pytest.skip(f"no NCCL in this process: {e}")
+        raise
+
+
+@pytest.mark.gpu
+def test_multi_gpu_script_with_its_text_kept_on_the_device(fx):
+    try:
+        check_multi_lookalike_script(gpu_lib(), fx, True)
     except JlError as e:
         if "NCCL" in str(e) or "nccl" in str(e):
             pytest.skip(f"no NCCL in this process: {e}")

@@ -18,7 +18,8 @@ from oracle.jl_interp import _BLOCK_OPEN, tokenize
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHIM = os.path.join(ROOT, "julia", "NS3DNative.jl")
-SCRIPTS = [os.path.join(ROOT, "scripts", "NavierStokes3D_b200.jl"), os.path.join(ROOT, "scripts", "NavierStokes3D_gpu_b200.jl")]
+SCRIPTS = [os.path.join(ROOT, "scripts", "NavierStokes3D_b200.jl"), os.path.join(ROOT, "scripts", "NavierStokes3D_gpu_b200.jl"),
+           os.path.join(ROOT, "scripts", "NavierStokes3D_multi_gpu_b200.jl")]
 HEADER = os.path.join(ROOT, "include", "ns3d.h")
 
 
