@@ -1111,14 +1111,37 @@ def run_multi_b200(lib, shim_path, script_path, nx, nt, use_fused=True, mode=0):
     return returned, local, iters, (shim, scr, mpi)
 
 
-def run_multi_gpu_lookalike_b200(lib, shim_path, script_path, nx, nt, use_fused=True, mode=0):
+class PipeMPI(SingleRankMPI):
+    """MPI.jl stand-in for rank processes of a test: rank / size fixed, `Bcast!` from rank 0 over pipes."""
+
+    def __init__(self, rank, size, pipes):
+        super().__init__()
+        self.rank, self.size, self.pipes = rank, size, pipes   # rank 0: the write ends; others: their read end
+
+    def Comm_rank(self, comm):
+        return self.rank
+
+    def Comm_size(self, comm):
+        return self.size
+
+    def Bcast_b(self, buf, root, comm):
+        self.calls.append("Bcast!")
+        if self.rank == root:
+            for w in self.pipes:
+                w.send(buf.tobytes())
+        else:
+            buf[...] = np.frombuffer(self.pipes.recv(), dtype=buf.dtype).reshape(buf.shape)
+        return buf
+
+
+def run_multi_gpu_lookalike_b200(lib, shim_path, script_path, nx, nt, use_fused=True, mode=0, mpi=None, literals=None):
     """scripts/NavierStokes3D_multi_gpu_b200.jl (the M script's text on the look-alike surface) on one rank: the body of
     `run_navierstokes3D` up to the end of the time loop, the local fields read back, then the gathers, `finalize_global_grid`
     and the return statement.  Returns (returned interiors, local fields, iterations per step, err histories, scripts)."""
     shim = load_shim(shim_path, lib)
     scr = load_script(script_path, shim)
-    scr.frozen = {"USE_FUSED": use_fused}
-    mpi = SingleRankMPI()
+    scr.frozen = {"USE_FUSED": use_fused, **(literals or {})}
+    mpi = mpi or SingleRankMPI()
     scr.globals["MPI"] = mpi
     with np.errstate(all="ignore"):
         for n, ln in enumerate(scr.text.split("\n"), 1):
@@ -1141,7 +1164,8 @@ def run_multi_gpu_lookalike_b200(lib, shim_path, script_path, nx, nt, use_fused=
             scr.exec_block(body[0][3], env, host=True)
             iters.append(int(env["iters"] if use_fused else env["iter"]))
             errs.append([float(e) for e in env["err_evo"]])
-        local = {k: scr.apply(shim.lookup("to_host", {}), [ctx, env[k]], {}) for k in ("Pr", "Vx", "Vy", "Vz", "C")}
+        local = {k: scr.apply(shim.lookup("to_host", {}), [ctx, env[j]], {})
+                 for k, j in (("Pr", "Pr"), ("Vx", "Vx"), ("Vy", "Vy"), ("Vz", "Vz"), ("C", "C"), ("dPrdtau", "dPrdτ"), ("divV", "∇V"))}
         try:
             scr.run_lines(last + 1, ret_last, env)
             returned = None

@@ -124,3 +124,37 @@ def multi_rank_main(rank, world, grid, nt, lz, how, options, uid_pipes, queue):
     except BaseException as exc:  # noqa: BLE001
         import traceback
         queue.put((rank, ["exception: " + repr(exc) + "\n" + traceback.format_exc()], None, 0, False))
+
+
+def julia_rank_main(rank, world, nx, nt, literals, fused, case_id, pipes, queue):
+    """One rank PROCESS of the Julia multi-GPU script: scripts/NavierStokes3D_multi_gpu_b200.jl (the reference script's text on
+    the shim's look-alike surface) interpreted by oracle/jl_shim.py, every ccall into the emulated library of this process,
+    MPI.jl replaced by a stand-in that broadcasts the NCCL id over pipes.  Checked against the per-rank digests that the
+    REFERENCE script's text yields on the same process grid (tests/golden/jl_reference_fixtures.npz, "ranks")."""
+    try:
+        import ctypes
+        import json
+        from oracle import jl_shim
+        from tests import jl_cases as J
+        from . import build_lib
+        lib = ctypes.CDLL(build_lib.build())
+        z = np.load(os.path.join(ROOT, "tests", "golden", "jl_reference_fixtures.npz"))
+        want = json.loads(str(z["meta"]))["ranks"][case_id][rank]
+        mpi = jl_shim.PipeMPI(rank, world, pipes)
+        ret, local, iters, errs, (shim, scr, _) = jl_shim.run_multi_gpu_lookalike_b200(
+            lib, os.path.join(ROOT, "julia", "NS3DNative.jl"), os.path.join(ROOT, "scripts", "NavierStokes3D_multi_gpu_b200.jl"),
+            nx, nt, use_fused=fused, mpi=mpi, literals=literals)
+        problems = []
+        if iters != want["iters"]:
+            problems.append(f"iterations {iters} != {want['iters']}")
+        if errs != want["errs"]:
+            problems.append("residual history differs")
+        for n in ("Pr", "Vx", "Vy", "Vz", "C", "dPrdtau", "divV"):
+            if J.digest(local[n]) != want["digest"][n]:
+                problems.append(f"{n} differs from the reference text's rank {rank}")
+        shapes = None if ret is None or ret[0] is None else [tuple(a.shape) for a in ret]
+        halos = sum(1 for s, _ in shim.ccalls if s == "ns3d_update_halo")
+        queue.put((rank, problems, iters, shapes, halos, [np.asarray(a) for a in ret] if rank == 0 else None))
+    except BaseException as exc:  # noqa: BLE001
+        import traceback
+        queue.put((rank, ["exception: " + repr(exc) + "\n" + traceback.format_exc()], None, None, 0, None))

@@ -62,7 +62,9 @@ template <class F>
 inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "fake CUDA runtime: unsupported"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+// one device per process unless NS3D_EMU_DEVICES says otherwise (rank processes of a "node" on which every rank sees all
+// GPUs and selects its own by ordinal, as ImplicitGlobalGrid does); every ordinal is this process's own fake device
+inline cudaError_t cudaGetDeviceCount(int* n) { const char* e = getenv("NS3D_EMU_DEVICES"); *n = e ? atoi(e) : 1; if (*n < 1) *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int)
 {

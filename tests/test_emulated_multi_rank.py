@@ -82,3 +82,64 @@ def test_rank_processes_match_igg_emulation(world, grid, nt, lz, how, options):
         assert not problems, f"rank {r}: " + "; ".join(problems)
         assert launches > 0 and iters is not None
     assert len({tuple(results[r][1]) for r in range(world)}) == 1   # every rank saw the same iteration counts
+
+
+# ---- the Julia multi-GPU script itself on several ranks -------------------------------------------------------------
+def run_julia_ranks(world, nx, nt, literals, fused, case_id):
+    build_lib.build()
+    saved = {k: os.environ.get(k) for k in ("NS3D_EMU_SHARED_ARENA", "LD_LIBRARY_PATH", "NS3D_EMU_DEVICES")}
+    os.environ["NS3D_EMU_SHARED_ARENA"] = "1"
+    os.environ["NS3D_EMU_DEVICES"] = str(world)   # init_global_grid selects device = rank, like ImplicitGlobalGrid on one node
+    os.environ["LD_LIBRARY_PATH"] = build_lib.OUT + os.pathsep + (saved["LD_LIBRARY_PATH"] or "")
+    try:
+        ctx = mp.get_context("spawn")
+        queue = ctx.Queue()
+        pipes = [ctx.Pipe(duplex=False) for _ in range(world - 1)]
+        procs = []
+        for r in range(world):
+            ends = [w for _, w in pipes] if r == 0 else pipes[r - 1][0]
+            procs.append(ctx.Process(target=emu.julia_rank_main, args=(r, world, nx, nt, literals, fused, case_id, ends, queue)))
+        for p in procs:
+            p.start()
+        results = {}
+        for _ in range(world):
+            res = queue.get(timeout=600)
+            results[res[0]] = res[1:]
+        for p in procs:
+            p.join(timeout=60)
+        return results
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("case_id,fused", [("z2", True), ("z2", False), ("z3", True)])
+def test_julia_multi_gpu_script_on_several_ranks(O, case_id, fused):
+    """scripts/NavierStokes3D_multi_gpu_b200.jl -- the reference's multi-GPU script with its text kept -- interpreted in one
+    process per rank (oracle/jl_shim.py), through julia/NS3DNative.jl's own text (`init_global_grid(...; MPI=MPI)`,
+    `comm_init_mpi!`, `update_halo!`, `max_g`, `gather!`), every ccall into the emulated library: each rank's local arrays,
+    iteration counts and residuals equal what the REFERENCE script's text yields on the same ImplicitGlobalGrid ranks
+    (fixtures "z2" / "z3"), and rank 0's return value is the global interior."""
+    import numpy as np
+    from tests import jl_cases as J
+    case = next(c for c in J.RANK_CASES if c[0] == case_id)
+    _, nx, ny, nz, dims, nt, literals, kw = case
+    world = dims[2]
+    results = run_julia_ranks(world, nx, nt, literals, fused, case_id)
+    for r in range(world):
+        problems = results[r][0]
+        assert not problems, f"rank {r}: " + "; ".join(problems)
+    truth = O.VirtualRanks(nx, ny, nz, dims, **kw)
+    for _ in range(nt):
+        truth.step()
+    ret = results[0][4]
+    for got, name in zip(ret, ("C", "Pr", "Vx", "Vy", "Vz")):
+        want = truth.assemble(name)[1:-1, 1:-1, 1:-1]
+        assert got.shape == want.shape and np.array_equal(got, want), name
+    for r in range(1, world):
+        assert results[r][2] == results[0][2]            # off the root the `zeros(...)` of M:386-390 come back, same shapes
+    if not fused:
+        assert results[0][3] == 2 + nt * 5 + 3 * sum(results[0][1])   # the text's ten update_halo! call sites
