@@ -357,3 +357,25 @@ def test_config_B_whole_time_steps_vs_the_shipped_scripts_text(ns):
                 assert got == s["digest"][name], f"{mode}: step {s['it']}: {name} differs from the script's text"
         c.close()
 
+
+def test_config_B_variant_M_vs_the_multi_gpu_scripts_text(ns):
+    """The same grid with the multi-GPU script (the base of the weak-scaling curve): `run_navierstokes3D(nx=255)` of
+    scripts/NavierStokes3D_multi_gpu.jl on one rank, three time steps executed from its text
+    (tests/golden/jl_reference_config_B_M.json: 152, 2 280, 2 280 PT iterations; the CPU oracle reproduces the record bit
+    for bit, checked when it was made).  PARITY: counts, residuals, five fields bit for bit after every step."""
+    import hashlib
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jl_reference_config_B_M.json")) as fh:
+        rec = json.load(fh)
+    assert rec["grid"] == [255, 153, 153] and len(rec["steps"]) == 3
+    c = ns.Context(0, ns.PARITY)
+    sim = ns.Simulation(ns.setup_multi_gpu(255), c)
+    for s in rec["steps"]:
+        it, hist = sim.step()
+        assert it == s["iters"], (s["it"], it)
+        assert hist == s["errs"], s["it"]
+        for name in ("Pr", "Vx", "Vy", "Vz", "C"):
+            got = hashlib.sha256(np.asfortranarray(sim.host(name)).tobytes(order="F")).hexdigest()
+            assert got == s["digest"][name], f"step {s['it']}: {name} differs from the script's text"
+    c.close()
+
