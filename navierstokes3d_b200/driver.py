@@ -383,8 +383,9 @@ def save_mat(fname: str, sim: Simulation, initial: bool = False):
 
 
 def runme(*, do_vis: bool = True, do_save: bool = False, nx: int = 255, nt: int = 10000, mode: int = native.FAST,
-          do_print: bool = True, return_sim: bool = False):
-    """Drop-in for ``runme`` of the single-GPU script (G:12); ``nx``/``nt`` are literals there (G:44,51)."""
+          do_print: bool = True, return_sim: bool = False, nsave: int | None = None):
+    """Drop-in for ``runme`` of the single-GPU script (G:12); ``nx``/``nt``/``nsave`` are literals there (G:44,51,52)."""
+    nsave = NSAVE if nsave is None else nsave
     s = setup_gpu(nx)
     sim = Simulation(s, native.Context(_dist_env()[2], mode))
     if do_save:                                                          # G:89
@@ -397,7 +398,7 @@ def runme(*, do_vis: bool = True, do_save: bool = False, nx: int = 255, nt: int 
         if do_print:
             for c, err in enumerate(hist, 1):
                 print("  #iter = %d, err = %1.3e" % (min(c * s.nchk, iters), err))   # G:134
-        if do_save and it % 10 == 0:                                     # G:168-170
+        if do_save and it % nsave == 0:                                  # G:168-170
             os.makedirs("out_save", exist_ok=True)
             save_mat(f"out_save/step_{it}.mat", sim)
     if return_sim:

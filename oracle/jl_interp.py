@@ -35,6 +35,7 @@ fixtures also certify that the kernels never index out of bounds for the tested 
 from __future__ import annotations
 
 import math
+import os
 import re
 import threading
 
@@ -210,8 +211,10 @@ class Parser:
                 return ("for", var, rng, body, c.line)
             if c.val == "return":
                 self.i += 1
-                val = None if self.at_stmt_end() else self.expr()
-                return ("return", val, c.line)
+                if self.at_stmt_end():
+                    return ("return", None, c.line)
+                vals = self.expr_list()
+                return ("return", vals[0] if len(vals) == 1 else ("tuple", vals), c.line)
             if c.val == "break":
                 self.i += 1
                 return ("break", c.line)
@@ -255,7 +258,11 @@ class Parser:
 
     # -- expressions (Julia precedence, lowest first)
     def expr(self):
-        return self.p_or()
+        a = self.p_or()
+        if self.is_op("=>"):                 # a pair, as in Dict("Pr"=>Array(Pr))
+            self.i += 1
+            return ("tuple", [a, self.expr()])
+        return a
 
     def p_or(self):
         a = self.p_and()
@@ -349,6 +356,9 @@ class Parser:
                 self.i += 1
                 a = ("attr", a, self.cur.val)
                 self.i += 1
+            elif self.is_op("'") and self.cur.start == prev_end:
+                self.i += 1
+                a = ("transpose", a)
             else:
                 return a
 
@@ -455,6 +465,9 @@ class Parser:
         if self.is_op(":") and self.peek().kind == "op" and self.peek().val == "(":
             self.i += 1      # quote  :( expr )
             return ("quote", self.p_primary())
+        if self.is_op(":") and self.peek().kind == "id" and self.peek().start == c.end:
+            self.i += 2      # a symbol  :log10
+            return ("sym", self.t[self.i - 1].val)
         raise ParseError(f"unexpected token {c!r}")
 
 
@@ -550,6 +563,7 @@ class JuliaScript:
         self.launches = []          # (kernel name, ranges) in launch order, for inspection by tests
         self.frozen: dict = {}      # host names whose assignments in the text are ignored (nx = 255 -> test size)
         self.comm, self.rank = None, 0   # set by run_ranks: several ranks of an ImplicitGlobalGrid
+        self.matwrites = []              # (file name, Dict) of every `matwrite` call (MAT.jl is not restated: recorded)
         self._builtins = self._make_builtins()
         self._scan_definitions()
 
@@ -764,6 +778,15 @@ class JuliaScript:
             "Data": {"Array": lambda x: np.array(x, dtype=np.float64, order="F"), "Number": JlType("Float64")},
             "MPI": {"Allreduce": self._allreduce, "MAX": "max", "COMM_WORLD": "world"},
             "nothing": None,
+            # the save path (M:27-30, 404-413, 515-523)
+            "ispath": os.path.exists, "isdir": os.path.isdir, "mkdir": os.mkdir,
+            "string": lambda *a: "".join(str(x) for x in a),
+            "open": lambda name, mode="r": open(name, {"w": "wb", "r": "rb"}[mode]),
+            "write": lambda out, A: out.write(np.asfortranarray(A).tobytes(order="F")),
+            "close": lambda out: out.close(),
+            "convert": lambda T, A: np.asarray(A).astype({"Float32": np.float32, "Float64": np.float64}[T.name]),
+            "Dict": lambda *pairs: {k: v for k, v in pairs},      # a repeated key keeps its LAST pair, as in Julia (G:89)
+            "matwrite": lambda fname, d: self.matwrites.append((fname, d)),
         }
 
     @staticmethod
@@ -810,7 +833,14 @@ class JuliaScript:
         if k == "id":
             return self.lookup(e[1], env)
         if k == "str":
-            return e[1]
+            text = e[1][3:-3] if e[1].startswith('"""') else e[1][1:-1]
+            if "$" in text:                                 # "$name" interpolation ("$(expr)" occurs in plot titles only)
+                text = re.sub(r"\$([^\W\d]\w*)", lambda m: str(self.lookup(m.group(1), env)), text)
+            return text
+        if k == "sym":
+            return ("sym", e[1])
+        if k == "transpose":
+            return np.transpose(self.ev(e[1], env, ps))
         if k == "endidx":                               # `end` inside an index: size of that dimension
             return env["__end__"]
         if k == "bin":
@@ -938,7 +968,9 @@ class JuliaScript:
             return self.ev(self.macros[name], env, ps)
         if name == "zeros":
             return np.zeros(tuple(self.ev(a, env) for a in args), dtype=np.float64, order="F")
-        if name in ("printf", "sprintf", "show"):
+        if name == "sprintf":                               # C-style formats: the same in Julia's Printf and in Python
+            return self.ev(args[0], env) % tuple(self.ev(a, env) for a in args[1:])
+        if name in ("printf", "show"):
             return None
         if ps is None:
             raise JlError(f"@{name} outside an @parallel function")

@@ -123,3 +123,40 @@ def run_G(nx: int, nt: int, path: str = G_PATH, on_step=None, literals: dict | N
     env = {"do_vis": False, "do_save": False}
     iters, errs = _run(s, prefix, loop, env, nt, on_step)
     return env, iters, errs, {"prefix": prefix, "loop": loop, "script": s}
+
+
+def run_M_whole(nx: int, nt: int, path: str = M_PATH, literals: dict | None = None, do_save: bool = False):
+    """The WHOLE body of `run_navierstokes3D` (M:288-535) executed in one piece -- parameter block, allocation, initial
+    gathers, the `do_save` frames (M:404-413, 515-523: `save_array` writes `out_save/out_<A>_v_%04d.bin` into the current
+    directory), the time loop with its `if (do_vis && ...) || (do_save && ...)` branch, the final gathers and the `return`
+    (plotting is parsed but, with do_vis=false, never reached).  Returns the function's return value."""
+    from .jl_interp import _Return
+    s = JuliaScript.from_file(path)
+    s.frozen = dict(literals or {})
+    head = s.find_line(r"function run_navierstokes3D\(")
+    last = s.find_line(r"^\s*return C_v,Pr_v,Vx_v,Vy_v,Vz_v", head)
+    env = {"nx": nx, "nt": nt, "do_vis": False, "do_save": do_save, "do_print": False}
+    with np.errstate(all="ignore"):
+        try:
+            s.run_lines(head + 1, last, env)
+        except _Return as r:
+            return r.val, env, (head + 1, last)
+    raise RuntimeError("the function body ended without `return`")
+
+
+def run_G_whole(nx: int, nt: int, path: str = G_PATH, literals: dict | None = None, do_save: bool = False):
+    """The WHOLE body of `runme` (G:13-172) in one piece, `nx`/`nt` literals replaced; with `do_save` the `.mat` dumps
+    (G:89, 168-170) are recorded as (file name, Dict) in `script.matwrites` (`out_save/` is created in the current
+    directory, as the script does)."""
+    from .jl_interp import _Return
+    s = JuliaScript.from_file(path)
+    s.frozen = {"nx": nx, "nt": nt, **(literals or {})}
+    head = s.find_line(r"function runme\(")
+    last = s.find_line(r"^\s*return\s*$", head)
+    env = {"do_vis": False, "do_save": do_save}
+    with np.errstate(all="ignore"):
+        try:
+            s.run_lines(head + 1, last, env)
+        except _Return:
+            pass
+    return env, s, (head + 1, last)

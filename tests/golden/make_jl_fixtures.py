@@ -13,7 +13,8 @@ bar) and, for the small grids, the arrays themselves; for the whole runs the PT 
 history, digests of the final Pr,Vx,Vy,Vz,C, the full arrays of the small runs, and -- for the M63 run, the
 size of test/test3D.jl -- the 64 samples `Pr[inds_x,inds_y,inds_z]` in that test's own layout; for the
 multi-rank cases (one interpreter thread per ImplicitGlobalGrid rank, `update_halo!` at the text's call sites)
-the digests of all 17 local arrays of every rank.
+the digests of all 17 local arrays of every rank; for the save path (the WHOLE bodies of the two run functions executed
+with do_save=true) the SHA-256 of every `out_save/out_<A>_v_%04d.bin` frame and the keys / digests of every `.mat` Dict.
 """
 import json
 import os
@@ -64,6 +65,8 @@ def main():
         meta["ranks"][case[0]] = [{"iters": iters, "errs": errs, "digest": {n: J.digest(f[n]) for n in J.RANK_FIELDS}}
                                   for f, iters, errs in res]
         print(case[0], case[4], res[0][1])
+    meta["save"] = J.save_path_records(jl_run)
+    print("save path:", len(meta["save"]["M31"]["files"]), "frames,", len(meta["save"]["G20"]), ".mat dumps")
     out["meta"] = np.array(json.dumps(meta, ensure_ascii=False))
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes;", len(J.KERNEL_CASES), "kernel cases,", len(J.RUN_CASES), "runs")

@@ -177,3 +177,28 @@ def run_ranks_oracle(O, case):
     for _ in range(nt):
         V.step()
     return [({n: f[n] for n in RANK_FIELDS}, V.iters, V.errs) for f in V.f]
+
+
+def save_path_records(jl_run):
+    """The scripts' `do_save` output from their text (whole function bodies, M:288-535 / G:13-172): M at nx = 31, nt = 3,
+    nsave = 1 -> the Float32 frames `out_save/out_<A>_v_%04d.bin` (M:404-413, 515-523) as SHA-256 of the file bytes;
+    G at nx = 20, nt = 2, nsave = 1 -> every `matwrite(name, Dict(...))` (G:89, 168-170) as keys + digests."""
+    import os
+    import tempfile
+    cwd = os.getcwd()
+    rec = {}
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        try:
+            ret, env, lines = jl_run.run_M_whole(31, 3, literals={"nsave": 1}, do_save=True)
+            files = {}
+            for fn in sorted(os.listdir("out_save")):
+                with open(os.path.join("out_save", fn), "rb") as fh:
+                    files[fn] = hashlib.sha256(fh.read()).hexdigest()
+            rec["M31"] = {"lines": list(lines), "files": files, "returned": [digest(a) for a in ret]}
+            env, s, lines = jl_run.run_G_whole(20, 2, literals={"nsave": 1}, do_save=True)
+            rec["G20"] = [{"file": f, "keys": sorted(dd), "digest": {k: (digest(v) if hasattr(v, "shape") else v) for k, v in dd.items()}}
+                          for f, dd in s.matwrites]
+        finally:
+            os.chdir(cwd)
+    return rec

@@ -47,6 +47,11 @@ def test_library_runs_equal_the_reference_text(ns, rid, path):
     D.test_library_runs_equal_the_reference_text(ns, rid, path)
 
 
+# ---- the scripts' do_save output against their own text --------------------------------------------------
+test_do_save_frames_equal_the_multi_gpu_scripts_text = Z.test_do_save_frames_equal_the_multi_gpu_scripts_text
+test_do_save_mat_dumps_equal_the_single_gpu_scripts_text = Z.test_do_save_mat_dumps_equal_the_single_gpu_scripts_text
+
+
 # ---- level 2 on CPU-sized grids ---------------------------------------------------------------------
 @pytest.mark.parametrize("variant", ["M", "G"])
 @pytest.mark.parametrize("grid", [(3, 3, 3), (5, 4, 3), (20, 12, 9)])

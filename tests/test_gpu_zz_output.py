@@ -99,3 +99,52 @@ def test_step_groups_equal_the_fused_step(O, ns, variant):
     for name in ("Pr", "dPrdtau", "Vx", "Vy", "Vz", "C", "divV", "Vx_o", "Vy_o", "Vz_o", "C_o"):
         assert np.array_equal(sim.host(name), f[name]), name
     sim.ctx.close()
+
+
+# ---- the scripts' do_save output against their own TEXT (tests/golden/jl_reference_fixtures.npz, "save") ----------
+def _save_records():
+    import json
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jl_reference_fixtures.npz"))
+    return json.loads(str(z["meta"]))["save"]
+
+
+def test_do_save_frames_equal_the_multi_gpu_scripts_text(ns, tmp_path, monkeypatch):
+    """`run_navierstokes3D(do_save=true)`: the same files with the same bytes as the script's own `save_array` calls write
+    (M:27-30, 404-413, 515-523; whole function body executed from the text with nsave = 1): frame 0 = initial conditions, one
+    frame per saved step, Float32 interiors of C, Pr, Vx, Vy, Vz -- converted on the device here."""
+    import hashlib
+    import os
+    rec = _save_records()["M31"]
+    monkeypatch.chdir(tmp_path)
+    out = ns.run_navierstokes3D(do_save=True, nx=31, nt=3, nsave=1, mode=ns.PARITY)
+    got = sorted(os.listdir(tmp_path / "out_save"))
+    assert got == sorted(rec["files"])
+    for fn in got:
+        with open(tmp_path / "out_save" / fn, "rb") as fh:
+            assert hashlib.sha256(fh.read()).hexdigest() == rec["files"][fn], fn
+    from tests import jl_cases as J
+    assert [J.digest(a) for a in out] == rec["returned"]          # M:535
+
+
+def test_do_save_mat_dumps_equal_the_single_gpu_scripts_text(ns, tmp_path, monkeypatch):
+    """`runme(do_save=true)`: the `.mat` files hold the keys and arrays of the script's own `matwrite` Dicts (G:89 with its
+    repeated "Vy" key, G:168-170), whole function body executed from the text with nsave = 1."""
+    from scipy.io import loadmat
+
+    from tests import jl_cases as J
+    rec = _save_records()["G20"]
+    monkeypatch.chdir(tmp_path)
+    ns.runme(do_vis=False, do_save=True, nx=20, nt=2, nsave=1, mode=ns.PARITY, do_print=False)
+    import os
+    assert sorted(os.listdir(tmp_path / "out_save")) == sorted(os.path.basename(r["file"]) for r in rec)
+    for r in rec:
+        m = loadmat(str(tmp_path / r["file"]))
+        keys = sorted(k for k in m if not k.startswith("__"))
+        assert keys == r["keys"], r["file"]
+        for k in keys:
+            want = r["digest"][k]
+            if isinstance(want, str):
+                assert J.digest(np.asfortranarray(m[k])) == want, (r["file"], k)
+            else:
+                assert float(np.asarray(m[k]).ravel()[0]) == want, (r["file"], k)

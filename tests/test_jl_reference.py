@@ -383,3 +383,16 @@ def test_oracle_equals_the_text_on_random_ragged_shapes(O, scripts):
                         assert same_bits(f[name], f2[name]), (J.case_id(case), name)
                 n += 1
     assert n == 2 * 8 * 11
+
+
+@live
+def test_save_path_records_are_what_the_text_writes(fx):
+    """The WHOLE bodies of the two run functions (M:288-535, G:13-172; plotting parsed, never reached) with do_save=true."""
+    z, meta = fx
+    rec = J.save_path_records(jl_run)
+    assert rec == meta["save"]
+    assert rec["M31"]["lines"] == [288, 535]
+    assert sorted(rec["M31"]["files"])[:2] == ["out_C_v_0000.bin", "out_C_v_0001.bin"] and len(rec["M31"]["files"]) == 20
+    assert [r["file"] for r in rec["G20"]] == ["out_save/step_0.mat", "out_save/step_1.mat", "out_save/step_2.mat"]
+    assert rec["G20"][0]["keys"] == ["C", "Pr", "Vx", "Vy", "dx", "dy", "dz"]            # G:89: "Vy" twice, no "Vz"
+    assert rec["G20"][0]["digest"]["Vy"] != rec["G20"][1]["digest"]["Vy"] and "Vz" in rec["G20"][1]["keys"]
