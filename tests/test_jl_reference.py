@@ -396,3 +396,20 @@ def test_save_path_records_are_what_the_text_writes(fx):
     assert [r["file"] for r in rec["G20"]] == ["out_save/step_0.mat", "out_save/step_1.mat", "out_save/step_2.mat"]
     assert rec["G20"][0]["keys"] == ["C", "Pr", "Vx", "Vy", "dx", "dy", "dz"]            # G:89: "Vy" twice, no "Vz"
     assert rec["G20"][0]["digest"]["Vy"] != rec["G20"][1]["digest"]["Vy"] and "Vz" in rec["G20"][1]["keys"]
+
+
+@live
+def test_whole_function_body_equals_the_stepwise_execution():
+    """The fixtures are produced by running the parameter block and then the loop body step by step (to record every
+    step's counts and residuals); executing the function body in ONE piece, `for it = 1:nt` and `return` included,
+    gives the same return value."""
+    ret, env, lines = jl_run.run_M_whole(31, 3)
+    env2, iters, errs, info = jl_run.run_M(31, 3, returns=True)
+    assert lines == (288, 535)
+    for a, n in zip(ret, ("C", "Pr", "Vx", "Vy", "Vz")):
+        assert same_bits(a, env2[n + "_v"]), n
+    env_g, s, lines_g = jl_run.run_G_whole(20, 2)
+    env_g2, _, _, _ = jl_run.run_G(20, 2)
+    assert lines_g == (13, 172)
+    for n in ("Pr", "Vx", "Vy", "Vz", "C"):
+        assert same_bits(env_g[n], env_g2[n]), n
