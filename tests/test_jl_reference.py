@@ -413,3 +413,75 @@ def test_whole_function_body_equals_the_stepwise_execution():
     assert lines_g == (13, 172)
     for n in ("Pr", "Vx", "Vy", "Vz", "C"):
         assert same_bits(env_g[n], env_g2[n]), n
+
+
+@live
+def test_projection_identity_holds_under_the_restated_macro_semantics(O, scripts, monkeypatch):
+    """An internal check of the one thing that IS restated (ParallelStencil's finite-difference macros): Chorin's projection
+    needs discrete div(grad) == the discrete Laplacian of the PT residual.  With the scripts' own kernels from the text --
+    `correct_V!` on V = 0 (`@d_xi`), `update_∇V!` (`@d_xa`, `@all`), `compute_res!` with zero divergence (`@d2_xi`, `@inn`) --
+    `∇V_inn == -(dt/ρ)·Rp` must hold to rounding; with a macro restated one cell off it fails at O(1)."""
+    S = scripts["M"]
+    p = O.params_M(11, 8, 7)
+    rng = np.random.default_rng(5)
+
+    def run():
+        f = O.alloc_fields(p)
+        f["Pr"][...] = rng.uniform(-1, 1, f["Pr"].shape)
+        S.launch(S.defs["correct_V!"], [f["Vx"], f["Vy"], f["Vz"], f["Pr"], p.dt, p.rho, p.dx, p.dy, p.dz])
+        S.launch(S.defs["update_∇V!"], [f["divV"], f["Vx"], f["Vy"], f["Vz"], p.dx, p.dy, p.dz])
+        div = f["divV"].copy()
+        f["divV"][...] = 0.0
+        S.launch(S.defs["compute_res!"], [f["Rp"], f["Pr"], f["divV"], p.rho, p.dt, p.dx, p.dy, p.dz])
+        lhs, rhs = div[1:-1, 1:-1, 1:-1], -(p.dt / p.rho) * f["Rp"]
+        return np.abs(lhs - rhs).max() / np.abs(rhs).max()
+
+    assert run() < 1e-12
+    orig = S.macrocall
+
+    def off_by_one(name, args, env, ps):          # @d_xi without the inner offset in y and z
+        if name == "d_xi" and ps is not None:
+            A = S.ev(args[0], env)
+            n = ps
+            return A[1:1 + n[0], 0:n[1], 0:n[2]] - A[0:n[0], 0:n[1], 0:n[2]]
+        return orig(name, args, env, ps)
+    monkeypatch.setattr(S, "macrocall", off_by_one)
+    assert run() > 0.1
+
+
+@live
+def test_predictor_is_second_order_at_the_scripts_own_node_positions(O, scripts, monkeypatch):
+    """A second check of the restated macros, anchored to the reference's text: `set_cylinder!` (M:250-279) says where the
+    unknowns live -- `Vx[ix,iy,iz]` at (xv, yc) with `yc = yco_g + (iy-1)*dy`.  For Vx = sin(2π(yc + ly/2)/ly), Vy = Vz = 0 the
+    predictor's increment (`update_τ!` then `predict_V!`, from the text) must equal dt·μ/ρ·Vx'' at those positions to SECOND
+    order; with `@d_ya` restated one cell off it drops to first order."""
+    S = scripts["M"]
+
+    def error(ny):
+        p = O.params_M(5, ny, 5)
+        f = O.alloc_fields(p)
+        yc = p.yco_g + np.arange(ny) * p.dy
+        k = 2 * np.pi / p.ly
+        f["Vx"][...] = np.sin(k * (yc + p.ly / 2))[None, :, None]
+        before = f["Vx"].copy()
+        S.launch(S.defs["update_τ!"], [f[n] for n in ("txx", "tyy", "tzz", "txy", "txz", "tyz", "Vx", "Vy", "Vz")] + [p.mu, p.dx, p.dy, p.dz])
+        S.launch(S.defs["predict_V!"], [f[n] for n in ("Vx", "Vy", "Vz", "txx", "tyy", "tzz", "txy", "txz", "tyz")]
+                 + [p.rho, 0.0, p.dt, p.dx, p.dy, p.dz])
+        got = (f["Vx"] - before)[1:-1, 1:-1, 1:-1]
+        want = (p.dt * p.mu / p.rho * -k * k * np.sin(k * (yc + p.ly / 2)))[None, 1:-1, None]
+        return np.abs(got - want).max() / np.abs(want).max()
+
+    e = [error(n) for n in (16, 32, 64)]
+    assert 3.6 < e[0] / e[1] < 4.4 and 3.8 < e[1] / e[2] < 4.2, e
+    orig = S.macrocall
+
+    def off_by_one(name, args, env, ps):          # @d_ya read one cell lower
+        if name == "d_ya" and ps is not None and args[0] == ("id", "τxy"):
+            A = S.ev(args[0], env)
+            n = ps
+            lo = np.concatenate([A[0:n[0], 0:1, 0:n[2]], A[0:n[0], 0:n[1] - 1, 0:n[2]]], axis=1)
+            return A[0:n[0], 0:n[1], 0:n[2]] - lo
+        return orig(name, args, env, ps)
+    monkeypatch.setattr(S, "macrocall", off_by_one)
+    e = [error(n) for n in (16, 32, 64)]
+    assert e[1] / e[2] < 2.6, e
