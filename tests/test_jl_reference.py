@@ -485,3 +485,20 @@ def test_predictor_is_second_order_at_the_scripts_own_node_positions(O, scripts,
     monkeypatch.setattr(S, "macrocall", off_by_one)
     e = [error(n) for n in (16, 32, 64)]
     assert e[1] / e[2] < 2.6, e
+
+
+@live
+def test_two_ranks_of_the_text_reproduce_its_single_rank_run():
+    """A check of the restated ImplicitGlobalGrid semantics (overlap 2, which planes `update_halo!` sends, `z_g`, `nz_g`):
+    the script's text on two z-ranks against the SAME text on one rank holding the global grid (nz = nz_g = 28): identical
+    PT iteration counts, every owned value equal to 1e-13 of the field's scale (not bit-equal: `backtrack!` works in local indices and the
+    max-reduction visits the residuals in another order)."""
+    lit = {"nz": 15, "lz_lx": 28 / 24}
+    ranks = jl_run.run_M_ranks(24, 2, (1, 1, 2), literals=lit)
+    env1, iters1, errs1, _ = jl_run.run_M(24, 2, literals={"nz": 28, "lz_lx": 28 / 24})
+    assert ranks[0][1] == ranks[1][1] == iters1
+    for name, scale in (("Pr", env1["psc"]), ("Vx", env1["vin"]), ("Vy", env1["vin"]), ("C", 1.0)):
+        g = env1[name]
+        lo, hi = ranks[0][0][name], ranks[1][0][name]
+        assert np.abs(lo[:, :, :14] - g[:, :, :14]).max() / scale < 1e-13, name        # rank 0 owns planes 1..14
+        assert np.abs(hi[:, :, 1:] - g[:, :, 14:]).max() / scale < 1e-13, name         # rank 1 owns global planes 15..28
