@@ -31,6 +31,9 @@ def free_port():
                                                      (4, (40, 24, 10), 3, 34 / 40, "fused"), (8, (40, 24, 6), 3, 34 / 40, "fused"),
                                                      # the fused loop alone on random fields: catches plane-offset
                                                      # errors the z-invariant flow would hide
+                                                     # the z-slab configuration at which the IGG emulation is pinned to the
+                                                     # reference script's text (tests/jl_cases.py RANK_CASES "z2")
+                                                     (2, (24, 15, 15), 2, 28 / 24, "fused"),
                                                      (2, (40, 24, 26), 12, 50 / 40, "pt_random"),
                                                      (4, (40, 24, 10), 7, 34 / 40, "pt_random")])
 def test_slabs_match_igg_emulation(world, grid, nt, lz, level):
