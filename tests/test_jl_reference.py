@@ -502,3 +502,23 @@ def test_two_ranks_of_the_text_reproduce_its_single_rank_run():
         lo, hi = ranks[0][0][name], ranks[1][0][name]
         assert np.abs(lo[:, :, :14] - g[:, :, :14]).max() / scale < 1e-13, name        # rank 0 owns planes 1..14
         assert np.abs(hi[:, :, 1:] - g[:, :, 14:]).max() / scale < 1e-13, name         # rank 1 owns global planes 15..28
+
+
+@live
+def test_the_stale_vector_is_copied_faithfully_from_the_references_test():
+    """tests/golden/test3D_pr_ref.json against test/test3D.jl itself: the 64 literals in file order ([z][y][x]), the three
+    index rows and the call (`nx=63, nt=1`) -- so that the recorded expected mismatch is a statement about the
+    reference's own test, not about a hand copy."""
+    import re
+    with open(os.path.join(jl_run.REFERENCE_ROOT, "test", "test3D.jl"), encoding="utf-8") as fh:
+        t = fh.read()
+    with open(os.path.join(GOLD, "test3D_pr_ref.json")) as fh:
+        j = json.load(fh)
+    block = t[t.index("Pr_ref = ["):t.index("# run reference tests")]
+    nums = [float(x) for x in re.findall(r"-?\d+\.\d+(?:e-?\d+)?", block)]
+    assert len(nums) == 64 and np.array_equal(np.array(j["Pr_ref"]).ravel(), np.array(nums))
+    for k in ("inds_x", "inds_y", "inds_z"):
+        row = re.search(k + r"\s*=\s*\[([^\]]*)\]", t).group(1)
+        assert [int(v) for v in row.split()] == j[k]
+    assert "run_navierstokes3D(do_vis=false, do_save=false, do_print=true, nx=63, nt=1)" in t
+    assert j["rtol"] == float(np.sqrt(np.finfo(np.float64).eps))            # Julia's default for `≈`
