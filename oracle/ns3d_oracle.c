@@ -613,3 +613,45 @@ EXPORT int oracle_step(const oracle_params *p, oracle_fields *f, double *err_his
 
 EXPORT size_t oracle_sizeof_params(void) { return sizeof(oracle_params); }
 EXPORT size_t oracle_sizeof_fields(void) { return sizeof(oracle_fields); }
+
+/* ---------------------------------------------------------------------------------------------
+ * The FAST arithmetic's division, checked against IEEE division (tests/test_oracle.py).
+ * The library's FAST mode computes x/d/d as div3(div3(x, d, y), d, y) with y = RN(1/d) and
+ *     div3(a, b, y) = fma(fma(-b, a*y, a), y, a*y)        (csrc/ns3d_pt_common.cuh)
+ * Markstein's theorem: with y the correctly rounded reciprocal and q = RN(a*y) (within one ulp of
+ * a/b), the corrected q' is the correctly rounded quotient -- for every normal a.  This routine
+ * draws n random numerators (random sign, 52 random mantissa bits, binary exponent in [emin, emax])
+ * and returns how many of them give div3(a, b, RN(1/b)) != a/b bit for bit.
+ * --------------------------------------------------------------------------------------------- */
+static inline uint64_t splitmix64(uint64_t* s)
+{
+    uint64_t z = (*s += 0x9e3779b97f4a7c15ULL);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+EXPORT long long oracle_div3_mismatches(double b, long long n, uint64_t seed, int emin, int emax, int twice)
+{
+    const double y = 1.0 / b;
+    long long bad = 0;
+    uint64_t st = seed;
+    for (long long i = 0; i < n; ++i) {
+        const uint64_t r = splitmix64(&st);
+        const uint64_t e = (uint64_t)(1023 + emin + (int)(splitmix64(&st) % (uint64_t)(emax - emin + 1)));
+        const uint64_t bits = (r & 0x800fffffffffffffULL) | (e << 52);
+        double a;
+        memcpy(&a, &bits, 8);
+        double q = a * y;
+        q = fma(fma(-b, q, a), y, q);
+        double want = a / b;
+        if (twice) {
+            double q2 = q * y;
+            q = fma(fma(-b, q2, q), y, q2);
+            want = want / b;
+        }
+        if (memcmp(&q, &want, 8) != 0) ++bad;
+    }
+    return bad;
+}
+

@@ -163,3 +163,20 @@ def test_frozen_fixtures(O):
         assert np.array_equal(np.array([e[-1] for e in errs]), fx[key + "_errs"])
         for name in ("Pr", "Vx", "Vy", "Vz", "C"):
             assert np.array_equal(f[name].ravel(order="F")[fx[f"{key}_{name}_idx"]], fx[f"{key}_{name}_val"]), name
+
+
+def test_fast_mode_division_is_ieee_division(O):
+    """The bench's default arithmetic (FAST) replaces `x/d/d` by two reciprocal multiplications with Markstein's FMA
+    correction (csrc/ns3d_pt_common.cuh `div3`).  By Markstein's theorem the corrected quotient is the correctly rounded
+    one for every normal numerator; here 2 x 10^7 random numerators (random mantissas, exponents 2^-200 .. 2^200) per
+    grid spacing of the benchmark configurations: not one differs from IEEE division, once or applied twice."""
+    import ctypes
+    fn = O.lib().oracle_div3_mismatches
+    fn.restype = ctypes.c_longlong
+    fn.argtypes = [ctypes.c_double, ctypes.c_longlong, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    spacings = {1.0 / 63, 0.6 / 38, 1.0 / 255, 0.6 / 153, 1.0 / 511, 1.0 / 1023, 1.0 / 31, 0.6 / 19, 1.0 / 40, 0.6 / 24}
+    for k, d in enumerate(sorted(spacings)):
+        for twice in (0, 1):
+            assert fn(d, 1_000_000, 1234 + k, -200, 200, twice) == 0, (d, twice)
+    assert fn(1.0 / 255, 10_000_000, 99, -30, 30, 1) == 0          # the range the pressure differences live in
+    assert fn(0.6 / 153, 10_000_000, 98, -30, 30, 1) == 0
