@@ -46,6 +46,8 @@ RUN_CASES = [
     ("G40", "G", 40, 2, {}, {}),
     # "what one edits in the source to run another case": a rotated, wider ellipse further downstream
     ("M40rot", "M", 40, 3, {"β": 0.3, "a_lx": 0.1, "ox_lx": -0.2}, {"beta": 0.3, "a_lx": 0.1, "ox_lx": -0.2}),
+    # explicit ny, nz with dx = dy = dz, the way BASELINE's configs D / E name their grids (1023x511x511, 511^3)
+    ("M20x14x9", "M", 20, 3, {"ny": 14, "nz": 9, "ly_lx": 14 / 20, "lz_lx": 9 / 20}, {"ny": 14, "nz": 9, "ly": 14 / 20, "lz": 9 / 20}),
 ]
 RUN_FIELDS = ("Pr", "Vx", "Vy", "Vz", "C")
 
@@ -60,7 +62,7 @@ RANK_CASES = [
 ]
 RANK_FIELDS = ("Pr", "dPrdtau", "C", "C_o", "Vx", "Vy", "Vz", "Vx_o", "Vy_o", "Vz_o", "divV", "txx", "tyy", "tzz", "txy", "txz", "tyz")
 JL_NAME = {"dPrdtau": "dPrdτ", "divV": "∇V", "txx": "τxx", "tyy": "τyy", "tzz": "τzz", "txy": "τxy", "txz": "τxz", "tyz": "τyz"}
-FULL_ARRAYS = {"M31", "G20"}      # the other runs are stored as digests + the test3D.jl samples
+FULL_ARRAYS = {"M31", "G20", "M20x14x9"}      # the other runs are stored as digests + the test3D.jl samples
 
 
 def case_id(case) -> str:

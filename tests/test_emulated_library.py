@@ -42,7 +42,7 @@ test_device_side_initialisers = D.test_device_side_initialisers_match_the_script
 
 # ---- whole runs against what the reference's own source text computes (jl_reference_fixtures.npz) ----
 @pytest.mark.parametrize("rid,path", [("M31", "fused"), ("M31", "level1"), ("M31", "groups"), ("G20", "fused"), ("G20", "level1"),
-                                      ("M40rot", "fused")])
+                                      ("M40rot", "fused"), ("M20x14x9", "fused")])
 def test_library_runs_equal_the_reference_text(ns, rid, path):
     D.test_library_runs_equal_the_reference_text(ns, rid, path)
 

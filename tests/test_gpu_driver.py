@@ -102,7 +102,7 @@ def _text_fixtures():
 
 
 @pytest.mark.parametrize("rid,path", [("M31", "fused"), ("M31", "level1"), ("M31", "groups"), ("G20", "fused"), ("G20", "level1"),
-                                      ("M40rot", "fused"), ("G40", "fused"), ("M63", "fused")])
+                                      ("M40rot", "fused"), ("G40", "fused"), ("M63", "fused"), ("M20x14x9", "fused")])
 def test_library_runs_equal_the_reference_text(ns, rid, path):
     """Whole runs of the two scripts through the C ABI (PARITY arithmetic) against what the scripts' own TEXT
     computes when oracle/jl_interp.py executes it (tests/golden/make_jl_fixtures.py; nothing of the C oracle is
@@ -112,8 +112,10 @@ def test_library_runs_equal_the_reference_text(ns, rid, path):
     from tests import jl_cases as J
     z, meta = _text_fixtures()
     _, variant, nx, nt, _, lit = next(rc for rc in J.RUN_CASES if rc[0] == rid)
-    ph = ns.Physics(**lit) if lit else None
-    s = ns.setup_multi_gpu(nx, physics=ph) if variant == "M" else ns.setup_gpu(nx, physics=ph)
+    geo = {k: lit[k] for k in ("ny", "nz", "ly", "lz") if k in lit}            # explicit dims (configs D / E style)
+    phys = {k: v for k, v in lit.items() if k not in geo}
+    ph = ns.Physics(**phys) if phys else None
+    s = ns.setup_multi_gpu(nx, physics=ph, **geo) if variant == "M" else ns.setup_gpu(nx, physics=ph)
     sim = ns.Simulation(s, mode=ns.PARITY, device=0)
     for _ in range(nt):
         {"fused": sim.step, "level1": sim.step_level1, "groups": sim.step_groups}[path]()

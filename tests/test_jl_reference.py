@@ -8,7 +8,7 @@ FiniteDifferences3D macros and launch ranges, ImplicitGlobalGrid on one rank, Ba
 restated there.  tests/golden/make_jl_fixtures.py stored what that execution produces.
 
 * always (the fixtures travel, /root/reference does not): the C oracle against the fixtures, BIT-EXACT --
-  78 single launches on seeded random fields and 5 whole runs incl. PT iteration counts and err histories;
+  78 single launches on seeded random fields and 6 whole runs incl. PT iteration counts and err histories;
 * when /root/reference is present: the fixtures re-derived from the text (they cannot drift from it), and
   the line ranges the runs execute checked against the cited ones;
 * the interpreter itself on Julia snippets whose value is known (precedence, `2μ`, `^`, `%`, short-circuit,
