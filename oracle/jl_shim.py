@@ -1072,14 +1072,14 @@ class SingleRankMPI:
         self.calls.append("Finalize")
 
 
-def run_multi_b200(lib, shim_path, script_path, nx, nt, use_fused=True, mode=0):
+def run_multi_b200(lib, shim_path, script_path, nx, nt, use_fused=True, mode=0, mpi=None, literals=None):
     """scripts/NavierStokes3D_b200.jl on one rank: the body of `run_navierstokes3D` from its first line to the end of the
     time loop (the `do_save` branch is not executed) and the return statement; `Ctx(...; mode=FAST)` is followed by
     `set_mode!(ctx, mode)`.  Returns (the five returned interiors C, Pr, Vx, Vy, Vz; local fields; iterations; scripts)."""
     shim = load_shim(shim_path, lib)
     scr = load_script(script_path, shim)
-    scr.frozen = {"USE_FUSED_PT": use_fused}
-    mpi = SingleRankMPI()
+    scr.frozen = {"USE_FUSED_PT": use_fused, **(literals or {})}
+    mpi = mpi or SingleRankMPI()
     scr.globals["MPI"] = mpi
     with np.errstate(all="ignore"):
         for n, ln in enumerate(scr.text.split("\n"), 1):
@@ -1101,7 +1101,8 @@ def run_multi_b200(lib, shim_path, script_path, nx, nt, use_fused=True, mode=0):
             env["it"] = it
             scr.exec_block(body[0][3], env, host=True)
             iters.append(int(env["iters"] if use_fused else env["iter"]))
-        local = {k: scr.apply(shim.lookup("to_host", {}), [env["ctx"], env[k]], {}) for k in ("Pr", "Vx", "Vy", "Vz", "C")}
+        local = {k: scr.apply(shim.lookup("to_host", {}), [env["ctx"], env[j]], {})
+                 for k, j in (("Pr", "Pr"), ("Vx", "Vx"), ("Vy", "Vy"), ("Vz", "Vz"), ("C", "C"), ("dPrdtau", "dPrdτ"), ("divV", "∇V"))}
         try:
             scr.run_lines(ret_first, ret_last, env)
             returned = None

@@ -126,7 +126,7 @@ def multi_rank_main(rank, world, grid, nt, lz, how, options, uid_pipes, queue):
         queue.put((rank, ["exception: " + repr(exc) + "\n" + traceback.format_exc()], None, 0, False))
 
 
-def julia_rank_main(rank, world, nx, nt, literals, fused, case_id, pipes, queue):
+def julia_rank_main(rank, world, nx, nt, literals, fused, case_id, pipes, queue, script="lookalike"):
     """One rank PROCESS of the Julia multi-GPU script: scripts/NavierStokes3D_multi_gpu_b200.jl (the reference script's text on
     the shim's look-alike surface) interpreted by oracle/jl_shim.py, every ccall into the emulated library of this process,
     MPI.jl replaced by a stand-in that broadcasts the NCCL id over pipes.  Checked against the per-rank digests that the
@@ -141,9 +141,15 @@ def julia_rank_main(rank, world, nx, nt, literals, fused, case_id, pipes, queue)
         z = np.load(os.path.join(ROOT, "tests", "golden", "jl_reference_fixtures.npz"))
         want = json.loads(str(z["meta"]))["ranks"][case_id][rank]
         mpi = jl_shim.PipeMPI(rank, world, pipes)
-        ret, local, iters, errs, (shim, scr, _) = jl_shim.run_multi_gpu_lookalike_b200(
-            lib, os.path.join(ROOT, "julia", "NS3DNative.jl"), os.path.join(ROOT, "scripts", "NavierStokes3D_multi_gpu_b200.jl"),
-            nx, nt, use_fused=fused, mpi=mpi, literals=literals)
+        if script == "lookalike":
+            ret, local, iters, errs, (shim, scr, _) = jl_shim.run_multi_gpu_lookalike_b200(
+                lib, os.path.join(ROOT, "julia", "NS3DNative.jl"), os.path.join(ROOT, "scripts", "NavierStokes3D_multi_gpu_b200.jl"),
+                nx, nt, use_fused=fused, mpi=mpi, literals=literals)
+        else:                                   # the explicit-context script (it keeps no residual history)
+            ret, local, iters, (shim, scr, _) = jl_shim.run_multi_b200(
+                lib, os.path.join(ROOT, "julia", "NS3DNative.jl"), os.path.join(ROOT, "scripts", "NavierStokes3D_b200.jl"),
+                nx, nt, use_fused=fused, mpi=mpi, literals=literals)
+            errs = want["errs"]
         problems = []
         if iters != want["iters"]:
             problems.append(f"iterations {iters} != {want['iters']}")
@@ -155,6 +161,7 @@ def julia_rank_main(rank, world, nx, nt, literals, fused, case_id, pipes, queue)
         shapes = None if ret is None or ret[0] is None else [tuple(a.shape) for a in ret]
         halos = sum(1 for s, _ in shim.ccalls if s == "ns3d_update_halo")
         queue.put((rank, problems, iters, shapes, halos, [np.asarray(a) for a in ret] if rank == 0 else None))
+        return
     except BaseException as exc:  # noqa: BLE001
         import traceback
         queue.put((rank, ["exception: " + repr(exc) + "\n" + traceback.format_exc()], None, None, 0, None))

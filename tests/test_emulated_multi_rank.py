@@ -85,7 +85,7 @@ def test_rank_processes_match_igg_emulation(world, grid, nt, lz, how, options):
 
 
 # ---- the Julia multi-GPU script itself on several ranks -------------------------------------------------------------
-def run_julia_ranks(world, nx, nt, literals, fused, case_id):
+def run_julia_ranks(world, nx, nt, literals, fused, case_id, script="lookalike"):
     build_lib.build()
     saved = {k: os.environ.get(k) for k in ("NS3D_EMU_SHARED_ARENA", "LD_LIBRARY_PATH", "NS3D_EMU_DEVICES")}
     os.environ["NS3D_EMU_SHARED_ARENA"] = "1"
@@ -98,7 +98,7 @@ def run_julia_ranks(world, nx, nt, literals, fused, case_id):
         procs = []
         for r in range(world):
             ends = [w for _, w in pipes] if r == 0 else pipes[r - 1][0]
-            procs.append(ctx.Process(target=emu.julia_rank_main, args=(r, world, nx, nt, literals, fused, case_id, ends, queue)))
+            procs.append(ctx.Process(target=emu.julia_rank_main, args=(r, world, nx, nt, literals, fused, case_id, ends, queue, script)))
         for p in procs:
             p.start()
         results = {}
@@ -143,3 +143,23 @@ def test_julia_multi_gpu_script_on_several_ranks(O, case_id, fused):
         assert results[r][2] == results[0][2]            # off the root the `zeros(...)` of M:386-390 come back, same shapes
     if not fused:
         assert results[0][3] == 2 + nt * 5 + 3 * sum(results[0][1])   # the text's ten update_halo! call sites
+
+
+def test_julia_explicit_context_script_on_two_ranks(O):
+    """scripts/NavierStokes3D_b200.jl (the same run written against the explicit-context API: `comm_init_mpi!`,
+    `update_halo!(ctx, nz, ...)`, `gather_inner`) on two rank processes: every rank equals the reference text's rank, rank 0
+    returns the global interior, the other rank `nothing`."""
+    import numpy as np
+    from tests import jl_cases as J
+    _, nx, ny, nz, dims, nt, literals, kw = next(c for c in J.RANK_CASES if c[0] == "z2")
+    lit = {"nz": literals["nz"], "lz": literals["lz_lx"]}        # this script spells `ly, lz = 0.6 * lx, 0.6 * lx`
+    results = run_julia_ranks(2, nx, nt, lit, True, "z2", script="explicit")
+    for r in range(2):
+        assert not results[r][0], f"rank {r}: " + "; ".join(results[r][0])
+    truth = O.VirtualRanks(nx, ny, nz, dims, **kw)
+    for _ in range(nt):
+        truth.step()
+    for got, name in zip(results[0][4], ("C", "Pr", "Vx", "Vy", "Vz")):
+        want = truth.assemble(name)[1:-1, 1:-1, 1:-1]
+        assert got.shape == want.shape and np.array_equal(got, want), name
+    assert results[1][2] is None
